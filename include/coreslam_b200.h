@@ -1,0 +1,173 @@
+/* coreslam_b200.h — C ABI of the B200-native CoreSLAM scan-to-map hot path.
+ *
+ * Drop-in boundary for SLAM.NET's CoreSLAMProcessor (C#).  The reference has no FFI layer; the
+ * boundary is the public surface of CoreSLAM/CoreSLAMProcessor.cs, which a C# wrapper keeps verbatim
+ * and forwards here through P/Invoke (see INTEGRATION.md for the [DllImport] stubs).  Plain C types
+ * only: pointers, sizes, PODs.  Every entry point returns a cs_status (0 = ok); cs_last_error()
+ * gives the text.  There is no CPU fallback: without a CUDA device cs_create fails with
+ * CS_ERR_NO_DEVICE.
+ *
+ * Citations "file:line" are relative to the reference tree (mikkleini/slam.net @ 7abc587).
+ *
+ * Threading: calls on one handle are caller-serialised (CoreSLAMProcessor.Update is blocking and
+ * non-reentrant, BaseSLAM/ParallelWorker.cs:94-97).  Distinct handles may be used from distinct
+ * threads; each owns one CUDA stream.
+ */
+#ifndef CORESLAM_B200_H
+#define CORESLAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_ABI_VERSION 1
+
+typedef enum cs_status {
+  CS_OK = 0,
+  CS_ERR_INVALID_ARGUMENT = 1,
+  CS_ERR_NO_DEVICE = 2,   /* no CUDA device / driver: the product path never falls back to the CPU */
+  CS_ERR_CUDA = 3,        /* sticky: the handle is unusable afterwards */
+  CS_ERR_OUT_OF_MEMORY = 4,
+  CS_ERR_CAPACITY = 5,    /* more points / candidates than the handle was created for */
+  CS_ERR_STATE = 6,
+  CS_ERR_NCCL = 7
+} cs_status;
+
+/* cs_config.flags */
+#define CS_FLAG_ROW_MAJOR_MAP 0x1u /* keep the device map row-major (default: 8x8-cell tiled, one 128 B line per tile) */
+#define CS_FLAG_TIMING 0x2u        /* record CUDA events around every kernel (cs_get_timing) */
+#define CS_FLAG_KEEP_DISTANCES 0x4u /* cs_update also stores all per-candidate distances (cs_get_distances) */
+#define CS_FLAG_NO_HOST_SPIN 0x8u  /* wait for the pose with cudaEventSynchronize instead of polling mapped memory */
+#define CS_FLAG_L2_PERSIST 0x10u   /* put a persisting L2 access-policy window over the map */
+
+typedef struct cs_processor cs_processor; /* opaque; replaces a CoreSLAMProcessor instance */
+typedef struct cs_scanlog cs_scanlog;     /* opaque; device-resident scan log for replays */
+typedef struct cs_batch cs_batch;         /* opaque; N independent sessions on one GPU */
+
+/* Mirrors the constructor CoreSLAMProcessor(physicalMapSize, holeMapSize, obstacleMapSize, startPose,
+ * sigmaXY, sigmaTheta, iterationsPerThread, numSearchThreads), CoreSLAMProcessor.cs:119-120.
+ * obstacleMapSize is not taken: the ObstacleMap half of Update stays in C# (out of scope). */
+typedef struct cs_config {
+  float physical_map_size;   /* metres, edge of the square map */
+  int32_t hole_map_size;     /* pixels per edge (HoleMap.Size, HoleMap.cs:17-22) */
+  float start_pose[3];       /* x, y (m), theta (rad) */
+  float sigma_xy;            /* metres */
+  float sigma_theta;         /* radians */
+  int32_t iterations_per_thread;
+  int32_t num_search_threads; /* <= 0: SingleMonteCarloSearch (:662-665), candidates = iterations */
+  int32_t device;            /* CUDA device ordinal */
+  int32_t max_points;        /* scan staging capacity; 0 -> 16384 */
+  uint64_t seed;             /* Philox seed for production-mode candidates */
+  void* stream;              /* optional cudaStream_t to run on; NULL -> the handle creates its own */
+  uint32_t flags;            /* CS_FLAG_* */
+  uint32_t reserved;
+} cs_config;
+
+/* Result of one search / update.  distance = INT32_MAX and index = 0 when nothing was in bounds or
+ * when the scan was integrated without a search (scanCount < PositionSearchBeginning, :726-743). */
+typedef struct cs_result {
+  float pose[3];      /* CoreSLAMProcessor.Pose after the call (theta normalised, :745-747) */
+  int32_t distance;   /* winner's "distance" (:253) */
+  int32_t index;      /* flat candidate index: 0 = searchPose, 1 + t*I + i (:674-710 tie-break order) */
+  int32_t searched;   /* 1 if a pose search ran for this scan */
+  int64_t visits;     /* HoleMap cells written by the integration (sum over rays of dxc+1) */
+} cs_result;
+
+typedef struct cs_timing {
+  float search_ms, finalize_ms, integrate_ms; /* device time of the last call's kernels (CS_FLAG_TIMING) */
+  float h2d_ms;
+  float total_device_ms;
+  double host_wait_ms;                        /* host wall time of the last cs_update until the pose was available */
+} cs_timing;
+
+int32_t cs_abi_version(void);
+const char* cs_last_error(const cs_processor* h); /* h may be NULL: error of the last failed create on this thread */
+int32_t cs_device_count(void);                    /* number of CUDA devices, 0 when the driver is absent */
+
+/* ---- lifetime: ctor :119-162, Reset :167-175, Dispose :757-773 ------------------------------------ */
+cs_status cs_create(const cs_config* cfg, cs_processor** out);
+cs_status cs_destroy(cs_processor* h);
+cs_status cs_reset(cs_processor* h); /* map := 32750, Pose := startPose, lastOdometryPose := 0, scanCount := 0 */
+
+/* ---- properties :40-106 ---------------------------------------------------------------------------- */
+cs_status cs_set_quality(cs_processor* h, int32_t quality);                  /* Quality, 1..255, default 50 */
+cs_status cs_set_hole_width(cs_processor* h, float metres);                  /* HoleWidth, default 0.6 */
+cs_status cs_set_position_search_beginning(cs_processor* h, int32_t scans);  /* default 5 */
+cs_status cs_get_pose(cs_processor* h, float pose[3]);                       /* Pose */
+cs_status cs_set_pose(cs_processor* h, const float pose[3], const float last_odometry[3], int32_t scan_count);
+cs_status cs_get_map_info(const cs_processor* h, int32_t* size, float* scale); /* HoleMap.Size / HoleMap.Scale */
+
+/* ---- the hot path ---------------------------------------------------------------------------------- */
+
+/* ParallelMonteCarloSearch (:674-710) with explicit inputs: evaluates CalculateDistanceSISD
+ * (:226-259) for searchPose (flat index 0) and n_cand candidate poses, returns the arg-min under the
+ * reference's tie-break order.  Does not touch the processor state or the map.
+ *   points       n_points * (x, y), metres, lidar frame (ScanCloud.Points, BaseSLAM/ScanCloud.cs:10-21)
+ *   cand_poses   n_cand * (x, y, theta) absolute poses — "upload the reference's candidates" mode.
+ *                NULL: the handle's Philox stream is used for scan index `scan_index` (n_cand must then
+ *                be T*I).
+ *   cand_cs      optional (n_cand+1) * (cos theta, sin theta), unscaled, entry 0 = searchPose: host libm
+ *                values for callers whose libm is not glibc x86-64.  NULL: computed on the device with
+ *                the glibc-identical routine.
+ *   distances    optional out, n_cand+1 values in flat order.                                        */
+cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, const float search_pose[3],
+                    const float* cand_poses, const float* cand_cs, int32_t n_cand, uint32_t scan_index,
+                    cs_result* best, int32_t* distances);
+
+/* UpdateHoleMap (:496-534) + DrawLaserRayOnHoleMap (:359-443) + ClipRay (:320-345) for an explicit
+ * pose; uses the handle's HoleWidth and Quality.  pose_cs: optional host (cos, sin) of pose[2].
+ * Asynchronous: returns after enqueueing; visits (optional) forces a wait for the count.            */
+cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, const float pose[3],
+                       const float* pose_cs, int64_t* visits);
+
+/* CoreSLAMProcessor.Update (:717-752) after ScanSegmentsToCloud: search gate, searchPose = Pose +
+ * (odo - lastOdo), search, NormalizeAngle, state update, HoleMap integration.  Returns as soon as the
+ * new pose is known; the integration keeps running on the stream and is ordered before the next call.
+ *   cand_offsets  T*I * (dx, dy, dtheta): the values the reference would dequeue for this scan
+ *                 (verification mode, :633-638).  NULL: on-device Philox Gaussian (production mode). */
+cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                    const float* cand_offsets, cs_result* out);
+
+/* Wait until everything enqueued on the handle (including the last integration) has finished. */
+cs_status cs_sync(cs_processor* h);
+
+/* ---- map access: HoleMap.Pixels (public field, HoleMap.cs:27), row-major y*Size+x ------------------ */
+cs_status cs_map_download(cs_processor* h, uint16_t* pixels);      /* Size*Size values */
+cs_status cs_map_upload(cs_processor* h, const uint16_t* pixels);
+cs_status cs_map_fill(cs_processor* h, uint16_t value);
+cs_status cs_map_packed(cs_processor* h, uint8_t* packed);          /* HoleMap.GetPackedPixels, HoleMap.cs:44-55 */
+cs_status cs_map_checksum(cs_processor* h, uint64_t* checksum);     /* position-dependent 64-bit hash computed on the device */
+uint64_t cs_host_map_checksum(const uint16_t* pixels, int32_t size); /* same hash of a host row-major map */
+
+/* ---- diagnostics ------------------------------------------------------------------------------------ */
+cs_status cs_get_timing(cs_processor* h, cs_timing* t);
+cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count); /* needs CS_FLAG_KEEP_DISTANCES */
+cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points);         /* x1,y1,x2,y2,xp,yp of the last integration */
+cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches);              /* kernels launched so far by this handle */
+
+/* ---- pinned staging so the C# side can fill ScanCloud points in place ------------------------------- */
+cs_status cs_pinned_alloc(void** ptr, uint64_t bytes);
+cs_status cs_pinned_free(void* ptr);
+
+/* ---- device-resident scan logs: replays with no host round trip per scan ---------------------------- */
+cs_status cs_scanlog_create(int32_t device, int32_t n_scans, int32_t max_points, int32_t n_offsets, cs_scanlog** out);
+cs_status cs_scanlog_set(cs_scanlog* log, int32_t scan, const float* points, int32_t n_points,
+                         const float odometry_pose[3], const float* cand_offsets /* n_offsets*3 or NULL */);
+cs_status cs_scanlog_upload(cs_scanlog* log);
+cs_status cs_scanlog_destroy(cs_scanlog* log);
+/* Runs Update for scans [first, first+count) back to back on the device; results[count] optional. */
+cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);
+
+/* ---- host twins of the device generators (for building verification tables; not a compute path) ----- */
+/* offsets[n*3] = the Philox deviates the device uses for candidates 0..n-1 of scan `scan_index`. */
+void cs_philox_offsets(uint64_t seed, uint32_t scan_index, int32_t n, float sigma_xy, float sigma_theta, float* offsets);
+void cs_host_sincos(const float* angles, int32_t n, float* cos_out, float* sin_out); /* the library's cosf/sinf, host build */
+cs_status cs_device_sincos(int32_t device, const float* angles, int32_t n, float* cos_out, float* sin_out);
+float cs_host_normalize_angle(float a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORESLAM_B200_H */

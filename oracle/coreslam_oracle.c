@@ -487,6 +487,18 @@ void or_parallel_search_mt(or_worker* w, const or_holemap* m, const float* point
   best_pose[0] = best[0]; best_pose[1] = best[1]; best_pose[2] = best[2];
 }
 
+/* host libm over arrays: what MathF.Cos / MathF.Sin / NormalizeAngle give on this machine */
+void or_libm_sincos(const float* in, int64_t n, float* cos_out, float* sin_out) {
+  for (int64_t i = 0; i < n; i++) {
+    cos_out[i] = cosf(in[i]);
+    sin_out[i] = sinf(in[i]);
+  }
+}
+
+void or_normalize_angle_array(const float* in, int64_t n, float* out) {
+  for (int64_t i = 0; i < n; i++) out[i] = or_normalize_angle(in[i]);
+}
+
 /* zlib CRC-32 (poly 0xEDB88320), for map checksums in KATs */
 uint32_t or_crc32(const void* data, uint64_t nbytes) {
   static uint32_t table[256];

@@ -117,6 +117,8 @@ void or_parallel_search_mt(or_worker* w, const or_holemap* m, const float* point
 void or_processor_update_mt(or_processor* p, or_worker* w, const float* points, int n,
                             const float odometry_pose[3], const float* offsets);
 
+void or_libm_sincos(const float* in, int64_t n, float* cos_out, float* sin_out);
+void or_normalize_angle_array(const float* in, int64_t n, float* out);
 uint32_t or_crc32(const void* data, uint64_t nbytes);
 
 #ifdef __cplusplus

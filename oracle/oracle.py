@@ -90,6 +90,8 @@ def lib():
     L.or_worker_destroy.argtypes = [C.c_void_p]
     L.or_parallel_search_mt.argtypes = [C.c_void_p, C.POINTER(_HoleMap), fp, C.c_int, fp, fp, C.c_int, fp, ip]
     L.or_processor_update_mt.argtypes = [C.POINTER(_Processor), C.c_void_p, fp, C.c_int, fp, fp]
+    L.or_libm_sincos.argtypes = [fp, C.c_int64, fp, fp]
+    L.or_normalize_angle_array.argtypes = [fp, C.c_int64, fp]
     L.or_crc32.restype = C.c_uint32
     L.or_crc32.argtypes = [C.c_void_p, C.c_uint64]
     _lib = L
@@ -138,6 +140,21 @@ def cvt(f: float) -> int:
 
 def normalize_angle(a: float) -> float:
     return float(lib().or_normalize_angle(float(np.float32(a))))
+
+
+def libm_sincos(angles):
+    a, ap = _f(angles)
+    c = np.empty_like(a)
+    s = np.empty_like(a)
+    lib().or_libm_sincos(ap, a.size, c.ctypes.data_as(C.POINTER(C.c_float)), s.ctypes.data_as(C.POINTER(C.c_float)))
+    return c, s
+
+
+def normalize_angle_array(angles):
+    a, ap = _f(angles)
+    out = np.empty_like(a)
+    lib().or_normalize_angle_array(ap, a.size, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
 
 
 def distance(m: HoleMap, points, pose) -> int:

@@ -1,0 +1,887 @@
+// cs_api.cu — the C ABI of include/coreslam_b200.h over the kernels in cs_kernels.cuh.
+//
+// One cs_processor replaces one CoreSLAMProcessor (CoreSLAM/CoreSLAMProcessor.cs): it owns the
+// device-resident HoleMap, the pinned staging block the scan is written into, one CUDA stream and a
+// mapped result slot the finalize kernel stores the pose into.  No CPU fallback exists: every compute
+// entry point launches kernels or fails.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/coreslam_b200.h"
+#include "cs_kernels.cuh"
+
+static_assert(sizeof(CsDevResult) == sizeof(cs_result), "cs_result layout");
+static_assert(sizeof(cs_config) == 72, "cs_config layout (ctypes / P/Invoke mirror it)");
+static_assert(sizeof(CsRay) == 32, "CsRay is staged as two int4");
+static_assert(sizeof(CsStepHeader) == 48, "CsStepHeader");
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t kHdrBytes = 64;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Timing {
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool valid = false;
+};
+
+}  // namespace
+
+struct cs_processor {
+  cs_config cfg{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool tiled = true;
+  int size = 0, pitch_tiles = 0, max_points = 0, n_cand = 0;
+  float scale = 0.f;
+  size_t map_cells = 0;  // allocated cells (tiled: pitch_tiles^2 * 64)
+
+  CsSession hs{};            // host mirror of the session descriptor
+  CsSession* d_sess = nullptr;
+  uint16_t* d_map = nullptr;
+  uint16_t* d_linear = nullptr;  // lazily allocated row-major scratch for upload/download
+  uint8_t* d_packed = nullptr;
+  CsRay* d_rays = nullptr;
+  int* d_ray_dbg = nullptr;
+  int* d_distances = nullptr;
+  unsigned long long* d_checksum = nullptr;
+
+  // staging: [hdr 64][points][cand][cand_cs]
+  size_t stage_bytes = 0;
+  uint8_t* h_stage = nullptr;  // pinned
+  uint8_t* d_stage = nullptr;
+
+  // mapped result slot
+  uint8_t* h_slot = nullptr;  // pinned+mapped: CsDevResult at 0, seq flag at 64
+  uint8_t* d_slot = nullptr;
+  unsigned seq = 0;
+
+  // host mirrors of the deterministic parts of the state machine
+  int scan_count = 0;  // CoreSLAMProcessor.cs:34 (saturates at PositionSearchBeginning)
+  int search_begin = 5;
+  unsigned update_count = 0;  // Philox scan index
+
+  uint64_t launches = 0;
+  Timing tm;
+  cs_timing last_timing{};
+  std::string error;
+  bool poisoned = false;
+};
+
+struct cs_scanlog {
+  int device = 0, n_scans = 0, max_points = 0, n_offsets = 0;
+  std::vector<CsStepHeader> h_hdr;
+  std::vector<float> h_points;   // n_scans * max_points * 2
+  std::vector<float> h_offsets;  // n_scans * n_offsets * 3
+  CsStepHeader* d_hdr = nullptr;
+  float2* d_points = nullptr;
+  float* d_offsets = nullptr;
+  CsDevResult* d_results = nullptr;
+  bool uploaded = false;
+};
+
+namespace {
+
+cs_status fail(cs_processor* h, cs_status code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) {
+    h->error = buf;
+    if (code == CS_ERR_CUDA) h->poisoned = true;
+  } else {
+    g_create_error = buf;
+  }
+  return code;
+}
+
+#define CS_CUDA(h, expr)                                                                         \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      return fail((h), CS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define CS_CHECK_HANDLE(h)                                                          \
+  do {                                                                              \
+    if (!(h)) return CS_ERR_INVALID_ARGUMENT;                                       \
+    if ((h)->poisoned) return CS_ERR_CUDA;                                          \
+    cudaError_t _e = cudaSetDevice((h)->device);                                    \
+    if (_e != cudaSuccess) return fail((h), CS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
+  } while (0)
+
+cs_status push_session(cs_processor* h) {
+  CS_CUDA(h, cudaMemcpyAsync(h->d_sess, &h->hs, sizeof(CsSession), cudaMemcpyHostToDevice, h->stream));
+  return CS_OK;
+}
+
+// session fields the host owns; state/key/x1.. are device-owned, so properties are patched individually
+cs_status patch_session(cs_processor* h, size_t offset, const void* src, size_t bytes) {
+  CS_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_sess) + offset, src, bytes, cudaMemcpyHostToDevice,
+                             h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));  // src may be a stack temporary
+  return CS_OK;
+}
+
+template <typename F>
+void dispatch_layout(bool tiled, F&& f) {
+  if (tiled) f(std::true_type{});
+  else f(std::false_type{});
+}
+
+cs_status launch_fill(cs_processor* h, uint16_t value) {
+  cs_fill_kernel<<<148 * 4, 256, 0, h->stream>>>(h->d_map, h->map_cells, value);
+  h->launches++;
+  CS_CUDA(h, cudaGetLastError());
+  return CS_OK;
+}
+
+struct StagePlan {
+  size_t off_points, off_cand, off_cs, total;
+};
+
+StagePlan plan_stage(int n_points, int n_cand_floats3, bool with_cs) {
+  StagePlan p;
+  p.off_points = kHdrBytes;
+  p.off_cand = align_up(p.off_points + (size_t)n_points * 8, 16);
+  p.off_cs = align_up(p.off_cand + (size_t)n_cand_floats3 * 12, 16);
+  p.total = align_up(p.off_cs + (with_cs ? (size_t)(n_cand_floats3 + 1) * 8 : 0), 16);
+  return p;
+}
+
+cs_status launch_step(cs_processor* h, const CsStepArgs& a, int n_points_hint, bool timing, int ev_base) {
+  const bool do_search_kernel = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
+  if (do_search_kernel) {
+    dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), 1);
+    dispatch_layout(h->tiled, [&](auto T) {
+      cs_search_kernel<decltype(T)::value><<<grid, CS_SEARCH_WARPS * 32, 0, h->stream>>>(h->d_sess, a);
+    });
+    h->launches++;
+  }
+  if (timing) cudaEventRecord(h->tm.ev[ev_base + 0], h->stream);
+  cs_finalize_kernel<<<1, CS_FINALIZE_THREADS, 0, h->stream>>>(h->d_sess, a);
+  h->launches++;
+  if (timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN))) cudaEventRecord(h->tm.ev[ev_base + 1], h->stream);
+  if (a.step_mode != CS_STEP_SEARCH_ONLY && n_points_hint > 0) {
+    dim3 grid((unsigned)((h->size + CS_INT_WARPS - 1) / CS_INT_WARPS), 1);
+    dispatch_layout(h->tiled, [&](auto T) {
+      cs_integrate_kernel<decltype(T)::value><<<grid, CS_INT_WARPS * 32, 0, h->stream>>>(h->d_sess);
+    });
+    h->launches++;
+  }
+  if (timing) cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
+  CS_CUDA(h, cudaGetLastError());
+  return CS_OK;
+}
+
+cs_status wait_for_pose(cs_processor* h, unsigned seq, cudaEvent_t fallback_event) {
+  auto t0 = std::chrono::steady_clock::now();
+  if (h->cfg.flags & CS_FLAG_NO_HOST_SPIN) {
+    CS_CUDA(h, cudaEventSynchronize(fallback_event));
+  } else {
+    volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(h->h_slot + 64);
+    unsigned spins = 0;
+    while (*flag != seq) {
+      if ((++spins & 0x3fff) == 0) {
+        cudaError_t e = cudaStreamQuery(h->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady)
+          return fail(h, CS_ERR_CUDA, "stream error while waiting for the pose: %s", cudaGetErrorString(e));
+        if (e == cudaSuccess && *flag != seq)
+          return fail(h, CS_ERR_CUDA, "stream drained but the pose flag was never written");
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  auto t1 = std::chrono::steady_clock::now();
+  h->last_timing.host_wait_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+  return CS_OK;
+}
+
+void copy_result(cs_result* out, const CsDevResult* r) {
+  out->pose[0] = r->pose[0]; out->pose[1] = r->pose[1]; out->pose[2] = r->pose[2];
+  out->distance = r->distance;
+  out->index = r->index;
+  out->searched = r->searched;
+  out->visits = r->visits;
+}
+
+cs_status collect_timing(cs_processor* h, bool had_h2d) {
+  CS_CUDA(h, cudaEventSynchronize(h->tm.ev[4]));
+  float ms = 0;
+  cs_timing& t = h->last_timing;
+  if (had_h2d) { cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[1]); t.h2d_ms = ms; } else t.h2d_ms = 0;
+  cudaEventElapsedTime(&ms, h->tm.ev[1], h->tm.ev[2]); t.search_ms = ms;
+  cudaEventElapsedTime(&ms, h->tm.ev[2], h->tm.ev[3]); t.finalize_ms = ms;
+  cudaEventElapsedTime(&ms, h->tm.ev[3], h->tm.ev[4]); t.integrate_ms = ms;
+  cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[4]); t.total_device_ms = ms;
+  return CS_OK;
+}
+
+bool finite3(const float* p) { return p[0] == p[0] && p[1] == p[1] && p[2] == p[2]; }
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int32_t cs_abi_version(void) { return CS_ABI_VERSION; }
+
+const char* cs_last_error(const cs_processor* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int32_t cs_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+cs_status cs_create(const cs_config* cfg, cs_processor** out) {
+  if (!cfg || !out) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_create: null argument");
+  *out = nullptr;
+  if (cfg->hole_map_size < 8 || cfg->hole_map_size > 16384)
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "hole_map_size must be in [8, 16384], got %d", cfg->hole_map_size);
+  if (!(cfg->physical_map_size > 0.f))
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "physical_map_size must be positive");
+  if (cfg->iterations_per_thread < 0 || cfg->iterations_per_thread > (1 << 24))
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "iterations_per_thread out of range");
+  const int threads = cfg->num_search_threads > 0 ? cfg->num_search_threads : 1;
+  const long long n_cand = (long long)threads * cfg->iterations_per_thread;
+  if (n_cand > (1ll << 26)) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "too many candidates per scan");
+  const int max_points = cfg->max_points > 0 ? cfg->max_points : 16384;
+  if (max_points > 65536) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "max_points must be <= 65536");
+
+  int ndev = cs_device_count();
+  if (ndev <= 0)
+    return fail(nullptr, CS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path (cudaGetDeviceCount = 0)");
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "device %d out of range (have %d)", cfg->device, ndev);
+
+  cs_processor* h = new cs_processor();
+  h->cfg = *cfg;
+  h->device = cfg->device;
+  h->tiled = !(cfg->flags & CS_FLAG_ROW_MAJOR_MAP);
+  h->size = cfg->hole_map_size;
+  h->pitch_tiles = (h->size + 7) / 8;
+  h->max_points = max_points;
+  h->n_cand = (int)n_cand;
+  h->scale = (float)cfg->hole_map_size / cfg->physical_map_size;  // HoleMap.cs:20
+  h->map_cells = h->tiled ? (size_t)h->pitch_tiles * h->pitch_tiles * 64 : (size_t)h->size * h->size;
+
+  auto bail = [&](cs_status st) {
+    g_create_error = h->error;
+    cs_destroy(h);
+    return st;
+  };
+#define CS_CREATE_CUDA(expr)                                                                           \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) {                                                                           \
+      fail(h, _e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "%s failed: %s", #expr, \
+           cudaGetErrorString(_e));                                                                    \
+      return bail(_e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA);               \
+    }                                                                                                  \
+  } while (0)
+
+  CS_CREATE_CUDA(cudaSetDevice(h->device));
+  if (cfg->stream) {
+    h->stream = (cudaStream_t)cfg->stream;
+  } else {
+    CS_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  CS_CREATE_CUDA(cudaMalloc(&h->d_map, h->map_cells * sizeof(uint16_t)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_sess, sizeof(CsSession)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)max_points * sizeof(CsRay)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_ray_dbg, (size_t)max_points * 6 * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
+  h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total;
+  CS_CREATE_CUDA(cudaHostAlloc(&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_stage, h->stage_bytes));
+  CS_CREATE_CUDA(cudaHostAlloc(&h->h_slot, 128, cudaHostAllocMapped));
+  CS_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_slot, h->h_slot, 0));
+  memset(h->h_slot, 0, 128);
+  for (auto& e : h->tm.ev) CS_CREATE_CUDA(cudaEventCreate(&e));
+
+  // Optional L2 persistence window over the map (the gathers are served from L2 either way when the
+  // map fits the 126 MB L2; the window only matters next to other L2-hungry work).
+  {
+    cudaDeviceProp prop;
+    if ((cfg->flags & CS_FLAG_L2_PERSIST) && cudaGetDeviceProperties(&prop, h->device) == cudaSuccess &&
+        prop.persistingL2CacheMaxSize > 0) {
+      size_t bytes = h->map_cells * sizeof(uint16_t);
+      size_t win = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : (size_t)prop.accessPolicyMaxWindowSize;
+      size_t carve = win < (size_t)prop.persistingL2CacheMaxSize ? win : (size_t)prop.persistingL2CacheMaxSize;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+        cudaStreamAttrValue attr{};
+        attr.accessPolicyWindow.base_ptr = h->d_map;
+        attr.accessPolicyWindow.num_bytes = win;
+        attr.accessPolicyWindow.hitRatio = win <= carve ? 1.0f : (float)carve / (float)win;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      }
+      cudaGetLastError();
+    }
+  }
+
+  CsSession& s = h->hs;
+  memset(&s, 0, sizeof(s));
+  s.map = h->d_map;
+  s.size = h->size;
+  s.pitch_tiles = h->pitch_tiles;
+  s.scale = h->scale;
+  s.sigma_xy = cfg->sigma_xy;
+  s.sigma_theta = cfg->sigma_theta;
+  s.iters = cfg->iterations_per_thread;
+  s.threads = cfg->num_search_threads;
+  s.n_cand = h->n_cand;
+  s.quality = 50;        // :82
+  s.hole_width = 0.6f;   // :87
+  s.search_begin = 5;    // :92
+  s.seed = cfg->seed;
+  s.rays = h->d_rays;
+  s.ray_dbg = h->d_ray_dbg;
+  s.distances = (cfg->flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
+  s.max_ring = -1;
+  cs_status st = cs_reset(h);
+  if (st != CS_OK) return bail(st);
+  *out = h;
+  return CS_OK;
+#undef CS_CREATE_CUDA
+}
+
+cs_status cs_destroy(cs_processor* h) {
+  if (!h) return CS_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& e : h->tm.ev)
+    if (e) cudaEventDestroy(e);
+  cudaFree(h->d_map);
+  cudaFree(h->d_linear);
+  cudaFree(h->d_packed);
+  cudaFree(h->d_sess);
+  cudaFree(h->d_rays);
+  cudaFree(h->d_ray_dbg);
+  cudaFree(h->d_distances);
+  cudaFree(h->d_checksum);
+  cudaFree(h->d_stage);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  if (h->h_slot) cudaFreeHost(h->h_slot);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+  return CS_OK;
+}
+
+cs_status cs_reset(cs_processor* h) {  // CoreSLAMProcessor.cs:167-175
+  CS_CHECK_HANDLE(h);
+  CsSession& s = h->hs;
+  memset(s.state, 0, sizeof(s.state));
+  for (int k = 0; k < 3; k++) s.state[0].pose[k] = h->cfg.start_pose[k];  // :172
+  s.state[0].scan_count = 0;                                               // :174 (lastOdometryPose = 0, :173)
+  s.key[0] = s.key[1] = ~0ull;
+  s.max_ring = -1;
+  s.n_rays = 0;
+  s.visits = 0;
+  h->scan_count = 0;
+  h->update_count = 0;
+  h->search_begin = s.search_begin;
+  cs_status st = push_session(h);
+  if (st != CS_OK) return st;
+  st = launch_fill(h, (uint16_t)((CS_TS_OBSTACLE + CS_TS_NO_OBSTACLE) / 2));  // :169
+  if (st != CS_OK) return st;
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_set_quality(cs_processor* h, int32_t quality) {
+  CS_CHECK_HANDLE(h);
+  if (quality < 1 || quality > 255) return fail(h, CS_ERR_INVALID_ARGUMENT, "Quality must be 1..255 (CoreSLAMProcessor.cs:76-82)");
+  h->hs.quality = quality;
+  return patch_session(h, offsetof(CsSession, quality), &h->hs.quality, sizeof(int));
+}
+
+cs_status cs_set_hole_width(cs_processor* h, float metres) {
+  CS_CHECK_HANDLE(h);
+  if (!(metres >= 0.f) || !(metres * h->scale < 60000.f))
+    return fail(h, CS_ERR_INVALID_ARGUMENT, "HoleWidth*Scale must be in [0, 60000) cells");
+  h->hs.hole_width = metres;
+  return patch_session(h, offsetof(CsSession, hole_width), &h->hs.hole_width, sizeof(float));
+}
+
+cs_status cs_set_position_search_beginning(cs_processor* h, int32_t scans) {
+  CS_CHECK_HANDLE(h);
+  h->hs.search_begin = scans;
+  h->search_begin = scans;
+  return patch_session(h, offsetof(CsSession, search_begin), &h->hs.search_begin, sizeof(int));
+}
+
+cs_status cs_get_pose(cs_processor* h, float pose[3]) {
+  CS_CHECK_HANDLE(h);
+  if (!pose) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pose");
+  CsState st;
+  CS_CUDA(h, cudaMemcpyAsync(&st, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, state), sizeof(CsState),
+                             cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  pose[0] = st.pose[0]; pose[1] = st.pose[1]; pose[2] = st.pose[2];
+  return CS_OK;
+}
+
+cs_status cs_set_pose(cs_processor* h, const float pose[3], const float last_odometry[3], int32_t scan_count) {
+  CS_CHECK_HANDLE(h);
+  if (!pose || !last_odometry) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pose");
+  CsState st{};
+  for (int k = 0; k < 3; k++) { st.pose[k] = pose[k]; st.last_odo[k] = last_odometry[k]; }
+  st.scan_count = scan_count;
+  h->scan_count = scan_count;
+  return patch_session(h, offsetof(CsSession, state), &st, sizeof(CsState));
+}
+
+cs_status cs_get_map_info(const cs_processor* h, int32_t* size, float* scale) {
+  if (!h) return CS_ERR_INVALID_ARGUMENT;
+  if (size) *size = h->size;
+  if (scale) *scale = h->scale;
+  return CS_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, const float search_pose[3],
+                    const float* cand_poses, const float* cand_cs, int32_t n_cand, uint32_t scan_index,
+                    cs_result* best, int32_t* distances) {
+  CS_CHECK_HANDLE(h);
+  if (!points || !search_pose || !best || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_search: bad argument");
+  if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
+  if (n_cand < 0 || n_cand > h->n_cand) return fail(h, CS_ERR_CAPACITY, "n_cand %d > T*I = %d", n_cand, h->n_cand);
+  if (!cand_poses && n_cand != h->n_cand) return fail(h, CS_ERR_INVALID_ARGUMENT, "Philox mode evaluates exactly T*I candidates");
+
+  StagePlan sp = plan_stage(n_points, n_cand, cand_cs != nullptr);
+  CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h->h_stage);
+  memset(hdr, 0, kHdrBytes);
+  hdr->odo[0] = search_pose[0]; hdr->odo[1] = search_pose[1]; hdr->odo[2] = search_pose[2];
+  hdr->n_points = n_points;
+  memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
+  if (cand_poses) memcpy(h->h_stage + sp.off_cand, cand_poses, (size_t)n_cand * 12);
+  if (cand_cs) memcpy(h->h_stage + sp.off_cs, cand_cs, (size_t)(n_cand + 1) * 8);
+  CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+
+  // distances requested: point the session at the buffer for this call
+  int* dist_ptr = distances ? h->d_distances : h->hs.distances;
+  if (dist_ptr != h->hs.distances) {
+    CS_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, distances), &dist_ptr,
+                               sizeof(int*), cudaMemcpyHostToDevice, h->stream));
+  }
+
+  CsStepArgs a{};
+  a.hdr = reinterpret_cast<const CsStepHeader*>(h->d_stage);
+  a.points = reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
+  a.cand = cand_poses ? reinterpret_cast<const float*>(h->d_stage + sp.off_cand) : nullptr;
+  a.cand_cs = cand_cs ? reinterpret_cast<const float*>(h->d_stage + sp.off_cs) : nullptr;
+  a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
+  a.seq_flag = reinterpret_cast<volatile unsigned*>(h->d_slot + 64);
+  a.seq_value = ++h->seq;
+  a.scan_index = scan_index;
+  a.cand_mode = cand_poses ? CS_CAND_ABSOLUTE : CS_CAND_PHILOX;
+  a.step_mode = CS_STEP_SEARCH_ONLY;
+  a.parity = 0;
+  a.do_search = 1;
+  a.n_cand = n_cand;
+  a.cand_first = 0;
+  a.cand_count = n_cand + 1;
+  cs_status st = launch_step(h, a, 0, false, 0);
+  if (st != CS_OK) return st;
+  if (distances) {
+    CS_CUDA(h, cudaMemcpyAsync(distances, h->d_distances, (size_t)(n_cand + 1) * sizeof(int), cudaMemcpyDeviceToHost,
+                               h->stream));
+    int* restore = h->hs.distances;
+    CS_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, distances), &restore,
+                               sizeof(int*), cudaMemcpyHostToDevice, h->stream));
+  }
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  copy_result(best, reinterpret_cast<const CsDevResult*>(h->h_slot));
+  best->visits = 0;
+  return CS_OK;
+}
+
+cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, const float pose[3],
+                       const float* pose_cs, int64_t* visits) {
+  CS_CHECK_HANDLE(h);
+  if (!points || !pose || n_points < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_integrate: bad argument");
+  if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
+  // No sync needed before refilling the pinned block: the previous call returned only after its pose
+  // flag, which the device writes after that call's H2D copy completed; the device-side block is
+  // protected by stream order.
+  StagePlan sp = plan_stage(n_points, 0, false);
+  CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h->h_stage);
+  memset(hdr, 0, kHdrBytes);
+  hdr->odo[0] = pose[0]; hdr->odo[1] = pose[1]; hdr->odo[2] = pose[2];
+  hdr->n_points = n_points;
+  if (pose_cs) { hdr->cs[0] = pose_cs[0]; hdr->cs[1] = pose_cs[1]; hdr->has_cs = 1; }
+  memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
+  CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+  CsStepArgs a{};
+  a.hdr = reinterpret_cast<const CsStepHeader*>(h->d_stage);
+  a.points = reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
+  a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
+  a.step_mode = CS_STEP_INTEGRATE_ONLY;
+  cs_status st = launch_step(h, a, n_points, false, 0);
+  if (st != CS_OK) return st;
+  if (visits) {
+    CS_CUDA(h, cudaStreamSynchronize(h->stream));
+    *visits = reinterpret_cast<const CsDevResult*>(h->h_slot)->visits;
+  }
+  return CS_OK;
+}
+
+cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                    const float* cand_offsets, cs_result* out) {
+  CS_CHECK_HANDLE(h);
+  if (!points || !odometry_pose || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
+  if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
+  if (!finite3(odometry_pose)) return fail(h, CS_ERR_INVALID_ARGUMENT, "odometry pose is NaN");
+  const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
+
+  // The previous call's integration may still be running: the pinned block is free again (its H2D copy
+  // finished before that call's pose flag), the device block is protected by stream order.
+  const bool do_search = h->scan_count >= h->search_begin;  // :726
+  const bool with_offsets = cand_offsets != nullptr && do_search;
+  StagePlan sp = plan_stage(n_points, with_offsets ? h->n_cand : 0, false);
+  CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h->h_stage);
+  memset(hdr, 0, kHdrBytes);
+  hdr->odo[0] = odometry_pose[0]; hdr->odo[1] = odometry_pose[1]; hdr->odo[2] = odometry_pose[2];
+  hdr->n_points = n_points;
+  memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
+  if (with_offsets) memcpy(h->h_stage + sp.off_cand, cand_offsets, (size_t)h->n_cand * 12);
+
+  if (timing) cudaEventRecord(h->tm.ev[0], h->stream);
+  CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+  if (timing) cudaEventRecord(h->tm.ev[1], h->stream);
+
+  CsStepArgs a{};
+  a.hdr = reinterpret_cast<const CsStepHeader*>(h->d_stage);
+  a.points = reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
+  a.cand = with_offsets ? reinterpret_cast<const float*>(h->d_stage + sp.off_cand) : nullptr;
+  a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
+  a.seq_flag = reinterpret_cast<volatile unsigned*>(h->d_slot + 64);
+  a.seq_value = ++h->seq;
+  a.scan_index = h->update_count;
+  a.cand_mode = with_offsets ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
+  a.step_mode = CS_STEP_UPDATE;
+  a.parity = 0;
+  a.do_search = do_search ? 1 : 0;
+  a.n_cand = h->n_cand;
+  a.cand_first = 0;
+  a.cand_count = h->n_cand + 1;
+  cs_status st = launch_step(h, a, n_points, timing, 2);
+  if (st != CS_OK) return st;
+  h->update_count++;
+  if (!do_search) h->scan_count++;  // :741
+
+  st = wait_for_pose(h, a.seq_value, h->tm.ev[3]);
+  if (st != CS_OK) return st;
+  if (timing) {
+    st = collect_timing(h, true);
+    if (st != CS_OK) return st;
+  }
+  if (out) {
+    copy_result(out, reinterpret_cast<const CsDevResult*>(h->h_slot));
+    if (!timing) out->visits = -1;  // the integration is still running; cs_sync + cs_get_timing path reports it
+  }
+  return CS_OK;
+}
+
+cs_status cs_sync(cs_processor* h) {
+  CS_CHECK_HANDLE(h);
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+static cs_status ensure_linear(cs_processor* h) {
+  if (!h->d_linear) CS_CUDA(h, cudaMalloc(&h->d_linear, (size_t)h->size * h->size * sizeof(uint16_t)));
+  return CS_OK;
+}
+
+cs_status cs_map_download(cs_processor* h, uint16_t* pixels) {
+  CS_CHECK_HANDLE(h);
+  if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
+  cs_status st = ensure_linear(h);
+  if (st != CS_OK) return st;
+  dispatch_layout(h->tiled, [&](auto T) {
+    cs_relayout_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->d_linear, h->size, h->pitch_tiles, 0);
+  });
+  h->launches++;
+  CS_CUDA(h, cudaMemcpyAsync(pixels, h->d_linear, (size_t)h->size * h->size * 2, cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_map_upload(cs_processor* h, const uint16_t* pixels) {
+  CS_CHECK_HANDLE(h);
+  if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
+  cs_status st = ensure_linear(h);
+  if (st != CS_OK) return st;
+  CS_CUDA(h, cudaMemcpyAsync(h->d_linear, pixels, (size_t)h->size * h->size * 2, cudaMemcpyHostToDevice, h->stream));
+  dispatch_layout(h->tiled, [&](auto T) {
+    cs_relayout_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->d_linear, h->size, h->pitch_tiles, 1);
+  });
+  h->launches++;
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_map_fill(cs_processor* h, uint16_t value) {
+  CS_CHECK_HANDLE(h);
+  cs_status st = launch_fill(h, value);
+  if (st != CS_OK) return st;
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_map_packed(cs_processor* h, uint8_t* packed) {
+  CS_CHECK_HANDLE(h);
+  if (!packed) return fail(h, CS_ERR_INVALID_ARGUMENT, "null packed");
+  size_t n = ((size_t)h->size * h->size) / 2;
+  if (!h->d_packed) CS_CUDA(h, cudaMalloc(&h->d_packed, n));
+  dispatch_layout(h->tiled, [&](auto T) {
+    cs_pack_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->size, h->pitch_tiles, h->d_packed);
+  });
+  h->launches++;
+  CS_CUDA(h, cudaMemcpyAsync(packed, h->d_packed, n, cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_map_checksum(cs_processor* h, uint64_t* checksum) {
+  CS_CHECK_HANDLE(h);
+  if (!checksum) return fail(h, CS_ERR_INVALID_ARGUMENT, "null checksum");
+  CS_CUDA(h, cudaMemsetAsync(h->d_checksum, 0, sizeof(unsigned long long), h->stream));
+  dispatch_layout(h->tiled, [&](auto T) {
+    cs_checksum_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->size, h->pitch_tiles, h->d_checksum);
+  });
+  h->launches++;
+  unsigned long long v = 0;
+  CS_CUDA(h, cudaMemcpyAsync(&v, h->d_checksum, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *checksum = v;
+  return CS_OK;
+}
+
+uint64_t cs_host_map_checksum(const uint16_t* pixels, int32_t size) {
+  unsigned long long acc = 0;
+  const size_t n = (size_t)size * (size_t)size;
+  for (size_t i = 0; i < n; i++) acc += ((unsigned long long)pixels[i] + 1ull) * cs_mix64((unsigned long long)i);
+  return acc;
+}
+
+// -----------------------------------------------------------------------------------------------------
+cs_status cs_get_timing(cs_processor* h, cs_timing* t) {
+  if (!h || !t) return CS_ERR_INVALID_ARGUMENT;
+  *t = h->last_timing;
+  return CS_OK;
+}
+
+cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count) {
+  CS_CHECK_HANDLE(h);
+  if (!h->hs.distances) return fail(h, CS_ERR_STATE, "handle was created without CS_FLAG_KEEP_DISTANCES");
+  if (!distances || count < 0 || count > h->n_cand + 1) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
+  CS_CUDA(h, cudaMemcpyAsync(distances, h->d_distances, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points) {
+  CS_CHECK_HANDLE(h);
+  if (!rays || n_points < 0 || n_points > h->max_points) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad n_points");
+  CS_CUDA(h, cudaMemcpyAsync(rays, h->d_ray_dbg, (size_t)n_points * 6 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches) {
+  if (!h || !launches) return CS_ERR_INVALID_ARGUMENT;
+  *launches = h->launches;
+  return CS_OK;
+}
+
+cs_status cs_pinned_alloc(void** ptr, uint64_t bytes) {
+  if (!ptr) return CS_ERR_INVALID_ARGUMENT;
+  cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    fail(nullptr, CS_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return CS_ERR_OUT_OF_MEMORY;
+  }
+  return CS_OK;
+}
+
+cs_status cs_pinned_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+  return CS_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+cs_status cs_scanlog_create(int32_t device, int32_t n_scans, int32_t max_points, int32_t n_offsets, cs_scanlog** out) {
+  if (!out || n_scans <= 0 || max_points <= 0 || n_offsets < 0 || max_points > 65536)
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_create: bad argument");
+  *out = nullptr;
+  if (cs_device_count() <= device) return fail(nullptr, CS_ERR_NO_DEVICE, "no such CUDA device");
+  cs_scanlog* log = new cs_scanlog();
+  log->device = device;
+  log->n_scans = n_scans;
+  log->max_points = (max_points + 1) & ~1;  // keep every scan's points 16-byte aligned
+  log->n_offsets = n_offsets;
+  log->h_hdr.assign((size_t)n_scans, CsStepHeader{});
+  log->h_points.assign((size_t)n_scans * log->max_points * 2, 0.f);
+  log->h_offsets.assign((size_t)n_scans * n_offsets * 3, 0.f);
+  cudaSetDevice(device);
+  bool ok = cudaMalloc(&log->d_hdr, sizeof(CsStepHeader) * n_scans) == cudaSuccess &&
+            cudaMalloc(&log->d_points, sizeof(float2) * (size_t)n_scans * log->max_points) == cudaSuccess &&
+            cudaMalloc(&log->d_offsets, sizeof(float) * 3 * (size_t)n_scans * (n_offsets > 0 ? n_offsets : 1)) == cudaSuccess &&
+            cudaMalloc(&log->d_results, sizeof(CsDevResult) * n_scans) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    cs_scanlog_destroy(log);
+    return fail(nullptr, CS_ERR_OUT_OF_MEMORY, "cs_scanlog_create: device allocation failed");
+  }
+  *out = log;
+  return CS_OK;
+}
+
+cs_status cs_scanlog_set(cs_scanlog* log, int32_t scan, const float* points, int32_t n_points,
+                         const float odometry_pose[3], const float* cand_offsets) {
+  if (!log || !points || !odometry_pose || scan < 0 || scan >= log->n_scans || n_points <= 0 || n_points > log->max_points)
+    return CS_ERR_INVALID_ARGUMENT;
+  CsStepHeader& hd = log->h_hdr[scan];
+  memset(&hd, 0, sizeof(hd));
+  hd.odo[0] = odometry_pose[0]; hd.odo[1] = odometry_pose[1]; hd.odo[2] = odometry_pose[2];
+  hd.n_points = n_points;
+  memcpy(&log->h_points[(size_t)scan * log->max_points * 2], points, (size_t)n_points * 8);
+  if (cand_offsets && log->n_offsets > 0)
+    memcpy(&log->h_offsets[(size_t)scan * log->n_offsets * 3], cand_offsets, (size_t)log->n_offsets * 12);
+  log->uploaded = false;
+  return CS_OK;
+}
+
+cs_status cs_scanlog_upload(cs_scanlog* log) {
+  if (!log) return CS_ERR_INVALID_ARGUMENT;
+  cudaSetDevice(log->device);
+  bool ok = cudaMemcpy(log->d_hdr, log->h_hdr.data(), sizeof(CsStepHeader) * log->n_scans, cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(log->d_points, log->h_points.data(), log->h_points.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok && log->n_offsets > 0)
+    ok = cudaMemcpy(log->d_offsets, log->h_offsets.data(), log->h_offsets.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (!ok) return fail(nullptr, CS_ERR_CUDA, "cs_scanlog_upload: %s", cudaGetErrorString(cudaGetLastError()));
+  log->uploaded = true;
+  return CS_OK;
+}
+
+cs_status cs_scanlog_destroy(cs_scanlog* log) {
+  if (!log) return CS_OK;
+  cudaSetDevice(log->device);
+  cudaFree(log->d_hdr);
+  cudaFree(log->d_points);
+  cudaFree(log->d_offsets);
+  cudaFree(log->d_results);
+  cudaGetLastError();
+  delete log;
+  return CS_OK;
+}
+
+cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results) {
+  CS_CHECK_HANDLE(h);
+  if (!log || !log->uploaded) return fail(h, CS_ERR_STATE, "scan log not uploaded");
+  if (log->device != h->device) return fail(h, CS_ERR_INVALID_ARGUMENT, "scan log lives on another device");
+  if (first < 0 || count < 0 || first + count > log->n_scans) return fail(h, CS_ERR_INVALID_ARGUMENT, "scan range");
+  if (log->n_offsets > 0 && log->n_offsets != h->n_cand)
+    return fail(h, CS_ERR_INVALID_ARGUMENT, "scan log carries %d offsets per scan, handle needs T*I = %d", log->n_offsets, h->n_cand);
+  if (log->max_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "scan log max_points exceeds the handle's");
+  const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
+  if (timing) cudaEventRecord(h->tm.ev[0], h->stream);
+  for (int i = 0; i < count; i++) {
+    const int sidx = first + i;
+    const bool do_search = h->scan_count >= h->search_begin;
+    CsStepArgs a{};
+    a.hdr = log->d_hdr + sidx;
+    a.points = log->d_points + (size_t)sidx * log->max_points;
+    a.cand = log->n_offsets > 0 ? log->d_offsets + (size_t)sidx * log->n_offsets * 3 : nullptr;
+    a.result = log->d_results + sidx;
+    a.scan_index = h->update_count;
+    a.cand_mode = log->n_offsets > 0 ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
+    a.step_mode = CS_STEP_UPDATE;
+    a.do_search = do_search ? 1 : 0;
+    a.n_cand = h->n_cand;
+    a.cand_first = 0;
+    a.cand_count = h->n_cand + 1;
+    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, false, 0);
+    if (st != CS_OK) return st;
+    h->update_count++;
+    if (!do_search) h->scan_count++;
+  }
+  if (timing) cudaEventRecord(h->tm.ev[4], h->stream);
+  if (results && count > 0) {
+    static_assert(sizeof(cs_result) == sizeof(CsDevResult), "");
+    CS_CUDA(h, cudaMemcpyAsync(results, log->d_results + first, sizeof(CsDevResult) * count, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (timing) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[4]);
+    h->last_timing = cs_timing{};
+    h->last_timing.total_device_ms = ms;
+  }
+  return CS_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------
+void cs_philox_offsets(uint64_t seed, uint32_t scan_index, int32_t n, float sigma_xy, float sigma_theta, float* offsets) {
+  for (int32_t i = 0; i < n; i++) cs_gauss3(seed, scan_index, (uint32_t)i, sigma_xy, sigma_theta, offsets + 3 * (size_t)i);
+}
+
+void cs_host_sincos(const float* angles, int32_t n, float* cos_out, float* sin_out) {
+  for (int32_t i = 0; i < n; i++) {
+    if (cos_out) cos_out[i] = cs_cosf(angles[i]);
+    if (sin_out) sin_out[i] = cs_sinf(angles[i]);
+  }
+}
+
+float cs_host_normalize_angle(float a) { return cs_normalize_angle(a); }
+
+cs_status cs_device_sincos(int32_t device, const float* angles, int32_t n, float* cos_out, float* sin_out) {
+  if (!angles || !cos_out || !sin_out || n <= 0) return CS_ERR_INVALID_ARGUMENT;
+  if (cs_device_count() <= device) return fail(nullptr, CS_ERR_NO_DEVICE, "no such CUDA device");
+  cudaSetDevice(device);
+  float *d_in = nullptr, *d_c = nullptr, *d_s = nullptr;
+  size_t bytes = (size_t)n * sizeof(float);
+  bool ok = cudaMalloc(&d_in, bytes) == cudaSuccess && cudaMalloc(&d_c, bytes) == cudaSuccess &&
+            cudaMalloc(&d_s, bytes) == cudaSuccess && cudaMemcpy(d_in, angles, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    cs_sincos_kernel<<<(n + 255) / 256, 256>>>(d_in, n, d_c, d_s);
+    ok = cudaMemcpy(cos_out, d_c, bytes, cudaMemcpyDeviceToHost) == cudaSuccess &&
+         cudaMemcpy(sin_out, d_s, bytes, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d_in); cudaFree(d_c); cudaFree(d_s);
+  if (!ok) return fail(nullptr, CS_ERR_CUDA, "cs_device_sincos: %s", cudaGetErrorString(cudaGetLastError()));
+  return CS_OK;
+}
+
+}  // extern "C"
