@@ -142,9 +142,13 @@ cs_status cs_map_checksum(cs_processor* h, uint64_t* checksum);     /* position-
 uint64_t cs_host_map_checksum(const uint16_t* pixels, int32_t size); /* same hash of a host row-major map */
 
 /* ---- diagnostics ------------------------------------------------------------------------------------ */
+cs_status cs_set_flags(cs_processor* h, uint32_t flags);   /* TIMING / KEEP_DISTANCES / NO_HOST_SPIN can change at run time */
 cs_status cs_get_timing(cs_processor* h, cs_timing* t);
 cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count); /* needs CS_FLAG_KEEP_DISTANCES */
 cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points);         /* x1,y1,x2,y2,xp,yp of the last integration */
+/* Diagnostics: cycles each ring's warp spent in the last integrate kernel.  The first call enables
+ * the recording (and returns nothing); later calls copy `count` values (ring 0..count-1). */
+cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count);
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches);              /* kernels launched so far by this handle */
 
 /* ---- pinned staging so the C# side can fill ScanCloud points in place ------------------------------- */
@@ -166,6 +170,9 @@ void cs_philox_offsets(uint64_t seed, uint32_t scan_index, int32_t n, float sigm
 void cs_host_sincos(const float* angles, int32_t n, float* cos_out, float* sin_out); /* the library's cosf/sinf, host build */
 cs_status cs_device_sincos(int32_t device, const float* angles, int32_t n, float* cos_out, float* sin_out);
 float cs_host_normalize_angle(float a);
+/* Measured ceiling for the search's access pattern: random 2-byte loads over a table of `cells`
+ * uint16 (L2-resident when it fits), best of `repeats`.  Used by bench.py as the gather roofline. */
+cs_status cs_gather_peak(int32_t device, int64_t cells, int32_t per_thread, int32_t repeats, double* lookups_per_s);
 
 #ifdef __cplusplus
 }

@@ -5,8 +5,8 @@ this package is the loader plus the host-side mirror of the reference's public c
 """
 from . import _native
 from ._native import CoreSlamError, build, lib
-from .coreslam import (CoreSLAMProcessor, HoleMap, Processor, Ray, ScanCloud, ScanLog, ScanSegment, SearchResult,
+from .coreslam import (CoreSLAMProcessor, gather_peak, HoleMap, Processor, Ray, ScanCloud, ScanLog, ScanSegment, SearchResult,
                        host_map_checksum, philox_offsets, scan_segments_to_cloud)
 
 __all__ = ["CoreSLAMProcessor", "HoleMap", "Processor", "Ray", "ScanCloud", "ScanLog", "ScanSegment", "SearchResult",
-           "CoreSlamError", "build", "lib", "host_map_checksum", "philox_offsets", "scan_segments_to_cloud", "_native"]
+           "CoreSlamError", "gather_peak", "build", "lib", "host_map_checksum", "philox_offsets", "scan_segments_to_cloud", "_native"]

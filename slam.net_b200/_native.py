@@ -129,9 +129,11 @@ SIGNATURES = {
     "cs_map_packed": (C.c_int, [_vp, _vp]),
     "cs_map_checksum": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_host_map_checksum": (C.c_uint64, [_vp, C.c_int32]),
+    "cs_set_flags": (C.c_int, [_vp, C.c_uint32]),
     "cs_get_timing": (C.c_int, [_vp, C.POINTER(Timing)]),
     "cs_get_distances": (C.c_int, [_vp, _ip, C.c_int32]),
     "cs_get_rays": (C.c_int, [_vp, _ip, C.c_int32]),
+    "cs_get_ring_cycles": (C.c_int, [_vp, C.POINTER(C.c_int64), C.c_int32]),
     "cs_get_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_pinned_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "cs_pinned_free": (C.c_int, [_vp]),
@@ -144,6 +146,7 @@ SIGNATURES = {
     "cs_host_sincos": (None, [_fp, C.c_int32, _fp, _fp]),
     "cs_device_sincos": (C.c_int, [C.c_int32, _fp, C.c_int32, _fp, _fp]),
     "cs_host_normalize_angle": (C.c_float, [C.c_float]),
+    "cs_gather_peak": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -268,6 +268,9 @@ class Processor:
         return int(v.value)
 
     # -- diagnostics ------------------------------------------------------------------------------
+    def set_flags(self, flags: int):
+        self._ck(N.lib().cs_set_flags(self._h, int(flags)))
+
     def timing(self) -> N.Timing:
         t = N.Timing()
         self._ck(N.lib().cs_get_timing(self._h, C.byref(t)))
@@ -284,10 +287,24 @@ class Processor:
         self._ck(N.lib().cs_get_rays(self._h, r.ctypes.data_as(C.POINTER(C.c_int32)), n_points))
         return r
 
+    def ring_cycles(self, count: Optional[int] = None) -> np.ndarray:
+        """Diagnostics (first call enables recording): cycles per ring warp of the last integration."""
+        count = self.size if count is None else count
+        out = np.zeros(count, dtype=np.int64)
+        self._ck(N.lib().cs_get_ring_cycles(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), count))
+        return out
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         self._ck(N.lib().cs_get_launch_count(self._h, C.byref(v)))
         return int(v.value)
+
+
+def gather_peak(cells: int, per_thread: int = 256, repeats: int = 5, device: int = 0) -> float:
+    """Measured random 2-byte gather rate (lookups/s) over a table of `cells` uint16."""
+    v = C.c_double()
+    N.check(N.lib().cs_gather_peak(device, int(cells), per_thread, repeats, C.byref(v)))
+    return float(v.value)
 
 
 def host_map_checksum(pixels, size: int) -> int:

@@ -57,6 +57,7 @@ struct cs_processor {
   CsRay* d_rays = nullptr;
   int* d_ray_dbg = nullptr;
   int* d_distances = nullptr;
+  long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
 
   // staging: [hdr 64][points][cand][cand_cs]
@@ -384,6 +385,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_rays);
   cudaFree(h->d_ray_dbg);
   cudaFree(h->d_distances);
+  cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
   cudaFree(h->d_stage);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -718,6 +720,22 @@ cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points) {
   return CS_OK;
 }
 
+cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count) {
+  CS_CHECK_HANDLE(h);
+  if (count < 0 || count > h->size) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
+  if (!h->d_ring_cycles) {  // first call switches the diagnostics on
+    CS_CUDA(h, cudaMalloc(&h->d_ring_cycles, (size_t)h->size * sizeof(long long)));
+    CS_CUDA(h, cudaMemsetAsync(h->d_ring_cycles, 0, (size_t)h->size * sizeof(long long), h->stream));
+    h->hs.ring_cycles = h->d_ring_cycles;
+    return patch_session(h, offsetof(CsSession, ring_cycles), &h->hs.ring_cycles, sizeof(long long*));
+  }
+  if (cycles && count > 0) {
+    CS_CUDA(h, cudaMemcpyAsync(cycles, h->d_ring_cycles, (size_t)count * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return CS_OK;
+}
+
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches) {
   if (!h || !launches) return CS_ERR_INVALID_ARGUMENT;
   *launches = h->launches;
@@ -816,7 +834,11 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     return fail(h, CS_ERR_INVALID_ARGUMENT, "scan log carries %d offsets per scan, handle needs T*I = %d", log->n_offsets, h->n_cand);
   if (log->max_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "scan log max_points exceeds the handle's");
   const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
-  if (timing) cudaEventRecord(h->tm.ev[0], h->stream);
+  const bool per_kernel = timing && count == 1;
+  if (timing) {
+    cudaEventRecord(h->tm.ev[0], h->stream);
+    if (per_kernel) cudaEventRecord(h->tm.ev[1], h->stream);
+  }
   for (int i = 0; i < count; i++) {
     const int sidx = first + i;
     const bool do_search = h->scan_count >= h->search_begin;
@@ -832,23 +854,97 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     a.n_cand = h->n_cand;
     a.cand_first = 0;
     a.cand_count = h->n_cand + 1;
-    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, false, 0);
+    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, per_kernel, 2);
     if (st != CS_OK) return st;
     h->update_count++;
     if (!do_search) h->scan_count++;
   }
-  if (timing) cudaEventRecord(h->tm.ev[4], h->stream);
+  if (timing && !per_kernel) cudaEventRecord(h->tm.ev[4], h->stream);
   if (results && count > 0) {
     static_assert(sizeof(cs_result) == sizeof(CsDevResult), "");
     CS_CUDA(h, cudaMemcpyAsync(results, log->d_results + first, sizeof(CsDevResult) * count, cudaMemcpyDeviceToHost, h->stream));
   }
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
-  if (timing) {
+  if (per_kernel) {
+    cs_status st = collect_timing(h, false);
+    if (st != CS_OK) return st;
+  } else if (timing) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[4]);
     h->last_timing = cs_timing{};
     h->last_timing.total_device_ms = ms;
   }
+  return CS_OK;
+}
+
+cs_status cs_set_flags(cs_processor* h, uint32_t flags) {
+  CS_CHECK_HANDLE(h);
+  const uint32_t fixed = CS_FLAG_ROW_MAJOR_MAP | CS_FLAG_L2_PERSIST;
+  if ((flags & fixed) != (h->cfg.flags & fixed)) return fail(h, CS_ERR_INVALID_ARGUMENT, "map layout / L2 window are fixed at creation");
+  h->cfg.flags = flags;
+  int* dist = (flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
+  h->hs.distances = dist;
+  return patch_session(h, offsetof(CsSession, distances), &dist, sizeof(int*));
+}
+
+// Random 2-byte gather micro-benchmark: the measured ceiling the search kernel's lookup rate is
+// compared with.  Every thread issues `per_thread` independent loads at hashed cell
+// indices of a table of `cells` uint16 (L2-resident when it fits), eight in flight at a time.
+__global__ void cs_gather_peak_kernel(const uint16_t* __restrict__ table, unsigned mask, int per_thread,
+                                      unsigned long long* __restrict__ sink) {
+  unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long z = cs_mix64(tid);
+  unsigned acc = 0;
+  for (int i = 0; i < per_thread; i += 8) {
+    unsigned v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      z = z * 6364136223846793005ull + 1442695040888963407ull;
+      v[k] = __ldg(table + ((unsigned)(z >> 33) & mask));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc += v[k];
+  }
+  if (acc == 0xffffffffu) atomicAdd(sink, 1ull);
+}
+
+cs_status cs_gather_peak(int32_t device, int64_t cells, int32_t per_thread, int32_t repeats, double* lookups_per_s) {
+  if (!lookups_per_s || cells < 1024 || per_thread < 8 || repeats < 1) return CS_ERR_INVALID_ARGUMENT;
+  if (cs_device_count() <= device) return fail(nullptr, CS_ERR_NO_DEVICE, "no such CUDA device");
+  cudaSetDevice(device);
+  unsigned pow2 = 1024;
+  while ((int64_t)pow2 * 2 <= cells && pow2 < (1u << 30)) pow2 *= 2;
+  uint16_t* table = nullptr;
+  unsigned long long* sink = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&table, (size_t)pow2 * 2) != cudaSuccess || cudaMalloc(&sink, 8) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(table);
+    return fail(nullptr, CS_ERR_OUT_OF_MEMORY, "cs_gather_peak: allocation failed");
+  }
+  cudaMemset(table, 1, (size_t)pow2 * 2);
+  cudaMemset(sink, 0, 8);
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = 148 * 8, threads = 256;
+  double best = 0;
+  for (int r = 0; r < repeats + 2; r++) {
+    cudaEventRecord(e0);
+    cs_gather_peak_kernel<<<blocks, threads>>>(table, pow2 - 1, per_thread, sink);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double rate = (double)blocks * threads * (double)(per_thread / 8 * 8) / (ms * 1e-3);
+    if (r >= 2 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(table);
+  cudaFree(sink);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, CS_ERR_CUDA, "cs_gather_peak: %s", cudaGetErrorString(e));
+  *lookups_per_s = best;
   return CS_OK;
 }
 

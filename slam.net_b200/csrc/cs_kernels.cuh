@@ -70,6 +70,7 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   CsRay* rays;                 // capacity max_points
   int* ray_dbg;                // optional 6 ints per ray (x1,y1,x2,y2,xp,yp)
   int* distances;              // optional n_cand+1
+  long long* ring_cycles;      // optional diagnostics: cycles each ring's warp spent in the integrate kernel
   int x1, y1;                  // ray origin cell of the current integration (:505-506)
   int max_ring;                // max dxc over valid rays, -1 if nothing to draw
   int n_rays;
@@ -506,6 +507,7 @@ cs_integrate_kernel(CsSession* __restrict__ sessions) {
   uint16_t* __restrict__ map = S.map;
   const CsRay* __restrict__ rays = S.rays;
   const unsigned lt_mask = (1u << lane) - 1u;
+  const long long t_begin = S.ring_cycles ? clock64() : 0;
 
   for (int base = 0; base < n; base += CS_INT_CHUNK) {
     const int cn = min(CS_INT_CHUNK, n - base);
@@ -570,6 +572,7 @@ cs_integrate_kernel(CsSession* __restrict__ sessions) {
       __syncwarp();
     }
   }
+  if (S.ring_cycles && lane == 0 && k <= max_ring) S.ring_cycles[k] = clock64() - t_begin;
 }
 
 // ---------------------------------------------------------------------------------------------------
