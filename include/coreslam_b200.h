@@ -41,6 +41,7 @@ typedef enum cs_status {
 #define CS_FLAG_KEEP_DISTANCES 0x4u /* cs_update also stores all per-candidate distances (cs_get_distances) */
 #define CS_FLAG_NO_HOST_SPIN 0x8u  /* wait for the pose with cudaEventSynchronize instead of polling mapped memory */
 #define CS_FLAG_L2_PERSIST 0x10u   /* put a persisting L2 access-policy window over the map */
+#define CS_FLAG_DEBUG_RAYS 0x20u   /* keep x1,y1,x2,y2,xp,yp of every ray of the last integration (cs_get_rays) */
 
 typedef struct cs_processor cs_processor; /* opaque; replaces a CoreSLAMProcessor instance */
 typedef struct cs_scanlog cs_scanlog;     /* opaque; device-resident scan log for replays */
@@ -76,7 +77,8 @@ typedef struct cs_result {
 } cs_result;
 
 typedef struct cs_timing {
-  float search_ms, finalize_ms, integrate_ms; /* device time of the last call's kernels (CS_FLAG_TIMING) */
+  float search_ms, finalize_ms, integrate_ms; /* device time of the last call's kernels (CS_FLAG_TIMING); the glue
+                                                 now runs inside the update kernel, so finalize_ms is 0 */
   float h2d_ms;
   float total_device_ms;
   double host_wait_ms;                        /* host wall time of the last cs_update until the pose was available */
@@ -145,9 +147,12 @@ uint64_t cs_host_map_checksum(const uint16_t* pixels, int32_t size); /* same has
 cs_status cs_set_flags(cs_processor* h, uint32_t flags);   /* TIMING / KEEP_DISTANCES / NO_HOST_SPIN can change at run time */
 cs_status cs_get_timing(cs_processor* h, cs_timing* t);
 cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count); /* needs CS_FLAG_KEEP_DISTANCES */
-cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points);         /* x1,y1,x2,y2,xp,yp of the last integration */
-/* Diagnostics: cycles each ring's warp spent in the last integrate kernel.  The first call enables
- * the recording (and returns nothing); later calls copy `count` values (ring 0..count-1). */
+cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points);         /* x1,y1,x2,y2,xp,yp of the last integration (CS_FLAG_DEBUG_RAYS) */
+cs_status cs_get_visits(cs_processor* h, int64_t* visits);   /* cells written by the last integration (waits for it) */
+/* Diagnostics: per ring of the last rings kernel, 8 cycle stamps since the ring's block started:
+ * [0] end, [4] session loaded, [5] table cleared, [6] rays loaded, [7] cells evaluated, [1] groups formed,
+ * [2] table built, [3] blends applied.  The first call enables the recording (and returns nothing);
+ * later calls copy `count` values (ring r at 8*r). */
 cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count);
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches);              /* kernels launched so far by this handle */
 

@@ -99,6 +99,7 @@ FLAG_TIMING = 0x2
 FLAG_KEEP_DISTANCES = 0x4
 FLAG_NO_HOST_SPIN = 0x8
 FLAG_L2_PERSIST = 0x10
+FLAG_DEBUG_RAYS = 0x20
 
 STATUS_NAMES = {0: "CS_OK", 1: "CS_ERR_INVALID_ARGUMENT", 2: "CS_ERR_NO_DEVICE", 3: "CS_ERR_CUDA",
                 4: "CS_ERR_OUT_OF_MEMORY", 5: "CS_ERR_CAPACITY", 6: "CS_ERR_STATE", 7: "CS_ERR_NCCL"}
@@ -133,6 +134,7 @@ SIGNATURES = {
     "cs_get_timing": (C.c_int, [_vp, C.POINTER(Timing)]),
     "cs_get_distances": (C.c_int, [_vp, _ip, C.c_int32]),
     "cs_get_rays": (C.c_int, [_vp, _ip, C.c_int32]),
+    "cs_get_visits": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cs_get_ring_cycles": (C.c_int, [_vp, C.POINTER(C.c_int64), C.c_int32]),
     "cs_get_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_pinned_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),

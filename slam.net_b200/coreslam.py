@@ -287,12 +287,17 @@ class Processor:
         self._ck(N.lib().cs_get_rays(self._h, r.ctypes.data_as(C.POINTER(C.c_int32)), n_points))
         return r
 
+    def visits(self) -> int:
+        v = C.c_int64()
+        self._ck(N.lib().cs_get_visits(self._h, C.byref(v)))
+        return int(v.value)
+
     def ring_cycles(self, count: Optional[int] = None) -> np.ndarray:
-        """Diagnostics (first call enables recording): cycles per ring warp of the last integration."""
+        """Diagnostics (first call enables recording): (rings, 8) cycle stamps of the last rings kernel."""
         count = self.size if count is None else count
-        out = np.zeros(count, dtype=np.int64)
-        self._ck(N.lib().cs_get_ring_cycles(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), count))
-        return out
+        out = np.zeros(count * 8, dtype=np.int64)
+        self._ck(N.lib().cs_get_ring_cycles(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), count * 8))
+        return out.reshape(count, 8)
 
     def launch_count(self) -> int:
         v = C.c_uint64()

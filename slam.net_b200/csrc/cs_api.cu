@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <atomic>
 #include <string>
@@ -21,7 +22,6 @@
 
 static_assert(sizeof(CsDevResult) == sizeof(cs_result), "cs_result layout");
 static_assert(sizeof(cs_config) == 72, "cs_config layout (ctypes / P/Invoke mirror it)");
-static_assert(sizeof(CsRay) == 32, "CsRay is staged as two int4");
 static_assert(sizeof(CsStepHeader) == 48, "CsStepHeader");
 
 namespace {
@@ -54,7 +54,8 @@ struct cs_processor {
   uint16_t* d_map = nullptr;
   uint16_t* d_linear = nullptr;  // lazily allocated row-major scratch for upload/download
   uint8_t* d_packed = nullptr;
-  CsRay* d_rays = nullptr;
+  int4* d_rays = nullptr;
+  int* d_batch_max = nullptr;
   int* d_ray_dbg = nullptr;
   int* d_distances = nullptr;
   long long* d_ring_cycles = nullptr;
@@ -71,6 +72,7 @@ struct cs_processor {
   unsigned seq = 0;
 
   // host mirrors of the deterministic parts of the state machine
+  int parity = 0;      // which CsSession::state / key slot is current
   int scan_count = 0;  // CoreSLAMProcessor.cs:34 (saturates at PositionSearchBeginning)
   int search_begin = 5;
   unsigned update_count = 0;  // Philox scan index
@@ -87,6 +89,7 @@ struct cs_scanlog {
   std::vector<CsStepHeader> h_hdr;
   std::vector<float> h_points;   // n_scans * max_points * 2
   std::vector<float> h_offsets;  // n_scans * n_offsets * 3
+  std::vector<double> h_max_range;  // per scan, sizes the update kernel's grid
   CsStepHeader* d_hdr = nullptr;
   float2* d_points = nullptr;
   float* d_offsets = nullptr;
@@ -165,27 +168,67 @@ StagePlan plan_stage(int n_points, int n_cand_floats3, bool with_cs) {
   return p;
 }
 
-cs_status launch_step(cs_processor* h, const CsStepArgs& a, int n_points_hint, bool timing, int ev_base) {
-  const bool do_search_kernel = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
-  if (do_search_kernel) {
+// Upper bound on the ring count of a scan: |rotated, scaled point| + half the hole width, plus rounding slack.
+int rings_hint(const cs_processor* h, double max_range) {
+  if (!(max_range == max_range) || max_range > 1e30) return h->size;
+  double cells = max_range * (double)h->scale * 1.00001 + 0.5 * (double)h->hs.hole_width * (double)h->scale + 4.0;
+  if (cells >= (double)h->size) return h->size;
+  return (int)cells + 1;
+}
+
+double max_range_of(const float* points, int n) {
+  double m = 0.0;
+  for (int i = 0; i < n; i++) {
+    double x = points[2 * i], y = points[2 * i + 1];
+    double r2 = x * x + y * y;
+    if (!(r2 <= m)) m = r2;  // NaN sticks
+  }
+  return std::sqrt(m);
+}
+
+// One step on the handle's stream: [search kernel, whose last block publishes the pose and prepares the
+// rays] or [set-up kernel] -> (big scans: multi-block ray preparation) -> rings kernel.
+cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base) {
+  const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
+  const bool draws = a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0;
+  const bool big = n_points > CS_FUSE_RAYS_MAX;
+  a.fuse_publish = 1;
+  a.fuse_rays = (draws && !big) ? 1 : 0;
+  a.rays_only = 0;
+  a.max_ring_hint = rings - 1;
+  a.diag = h->d_ring_cycles;
+  if (searching) {
     dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), 1);
     dispatch_layout(h->tiled, [&](auto T) {
       cs_search_kernel<decltype(T)::value><<<grid, CS_SEARCH_WARPS * 32, 0, h->stream>>>(h->d_sess, a);
     });
-    h->launches++;
+  } else {
+    cs_setup_kernel<<<dim3(1, 1), CS_SETUP_THREADS, 0, h->stream>>>(h->d_sess, a);
   }
-  if (timing) cudaEventRecord(h->tm.ev[ev_base + 0], h->stream);
-  cs_finalize_kernel<<<1, CS_FINALIZE_THREADS, 0, h->stream>>>(h->d_sess, a);
   h->launches++;
-  if (timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN))) cudaEventRecord(h->tm.ev[ev_base + 1], h->stream);
-  if (a.step_mode != CS_STEP_SEARCH_ONLY && n_points_hint > 0) {
-    dim3 grid((unsigned)((h->size + CS_INT_WARPS - 1) / CS_INT_WARPS), 1);
+  // the pose is out once this kernel has finished
+  if (timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN))) cudaEventRecord(h->tm.ev[ev_base + 0], h->stream);
+  if (draws) {
+    if (big) {
+      CsStepArgs b = a;
+      b.rays_only = 1;
+      cs_setup_kernel<<<dim3((unsigned)((n_points + 1023) / 1024), 1), CS_SETUP_THREADS, 0, h->stream>>>(h->d_sess, b);
+      h->launches++;
+    }
+    int warps = (n_points + CS_RING_GROUP - 1) / CS_RING_GROUP;
+    if (warps < 1) warps = 1;
+    if (warps > CS_RING_MAX_WARPS) warps = CS_RING_MAX_WARPS;
+    while (warps & (warps - 1)) warps++;  // the kernel's table size must be a power of two
+    if (rings < 1) rings = 1;
     dispatch_layout(h->tiled, [&](auto T) {
-      cs_integrate_kernel<decltype(T)::value><<<grid, CS_INT_WARPS * 32, 0, h->stream>>>(h->d_sess);
+      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)rings, 1), warps * 32, (size_t)warps * CS_RING_SMEM_PER_WARP, h->stream>>>(h->d_sess, a);
     });
     h->launches++;
   }
-  if (timing) cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
+  if (timing) {
+    cudaEventRecord(h->tm.ev[ev_base + 1], h->stream);
+    cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
+  }
   CS_CUDA(h, cudaGetLastError());
   return CS_OK;
 }
@@ -230,8 +273,8 @@ cs_status collect_timing(cs_processor* h, bool had_h2d) {
   cs_timing& t = h->last_timing;
   if (had_h2d) { cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[1]); t.h2d_ms = ms; } else t.h2d_ms = 0;
   cudaEventElapsedTime(&ms, h->tm.ev[1], h->tm.ev[2]); t.search_ms = ms;
-  cudaEventElapsedTime(&ms, h->tm.ev[2], h->tm.ev[3]); t.finalize_ms = ms;
-  cudaEventElapsedTime(&ms, h->tm.ev[3], h->tm.ev[4]); t.integrate_ms = ms;
+  cudaEventElapsedTime(&ms, h->tm.ev[2], h->tm.ev[3]); t.integrate_ms = ms;  // rings kernel (+ set-up kernels of big scans)
+  t.finalize_ms = 0.f;
   cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[4]); t.total_device_ms = ms;
   return CS_OK;
 }
@@ -312,8 +355,13 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   }
   CS_CREATE_CUDA(cudaMalloc(&h->d_map, h->map_cells * sizeof(uint16_t)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_sess, sizeof(CsSession)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)max_points * sizeof(CsRay)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_ray_dbg, (size_t)max_points * 6 * sizeof(int)));
+  if (cfg->flags & CS_FLAG_DEBUG_RAYS) CS_CREATE_CUDA(cudaMalloc(&h->d_ray_dbg, (size_t)max_points * 6 * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)max_points * sizeof(int4)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, ((size_t)max_points / 32 + 1) * sizeof(int)));
+  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP));
+  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total;
@@ -362,9 +410,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   s.search_begin = 5;    // :92
   s.seed = cfg->seed;
   s.rays = h->d_rays;
+  s.batch_max = h->d_batch_max;
   s.ray_dbg = h->d_ray_dbg;
   s.distances = (cfg->flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
-  s.max_ring = -1;
   cs_status st = cs_reset(h);
   if (st != CS_OK) return bail(st);
   *out = h;
@@ -383,6 +431,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_packed);
   cudaFree(h->d_sess);
   cudaFree(h->d_rays);
+  cudaFree(h->d_batch_max);
   cudaFree(h->d_ray_dbg);
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
@@ -404,8 +453,9 @@ cs_status cs_reset(cs_processor* h) {  // CoreSLAMProcessor.cs:167-175
   s.state[0].scan_count = 0;                                               // :174 (lastOdometryPose = 0, :173)
   s.key[0] = s.key[1] = ~0ull;
   s.max_ring = -1;
-  s.n_rays = 0;
+  s.search_done = 0;
   s.visits = 0;
+  h->parity = 0;
   h->scan_count = 0;
   h->update_count = 0;
   h->search_begin = s.search_begin;
@@ -443,8 +493,8 @@ cs_status cs_get_pose(cs_processor* h, float pose[3]) {
   CS_CHECK_HANDLE(h);
   if (!pose) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pose");
   CsState st;
-  CS_CUDA(h, cudaMemcpyAsync(&st, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, state), sizeof(CsState),
-                             cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaMemcpyAsync(&st, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, state) + h->parity * sizeof(CsState),
+                             sizeof(CsState), cudaMemcpyDeviceToHost, h->stream));
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
   pose[0] = st.pose[0]; pose[1] = st.pose[1]; pose[2] = st.pose[2];
   return CS_OK;
@@ -457,7 +507,7 @@ cs_status cs_set_pose(cs_processor* h, const float pose[3], const float last_odo
   for (int k = 0; k < 3; k++) { st.pose[k] = pose[k]; st.last_odo[k] = last_odometry[k]; }
   st.scan_count = scan_count;
   h->scan_count = scan_count;
-  return patch_session(h, offsetof(CsSession, state), &st, sizeof(CsState));
+  return patch_session(h, offsetof(CsSession, state) + h->parity * sizeof(CsState), &st, sizeof(CsState));
 }
 
 cs_status cs_get_map_info(const cs_processor* h, int32_t* size, float* scale) {
@@ -505,12 +555,12 @@ cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, cons
   a.scan_index = scan_index;
   a.cand_mode = cand_poses ? CS_CAND_ABSOLUTE : CS_CAND_PHILOX;
   a.step_mode = CS_STEP_SEARCH_ONLY;
-  a.parity = 0;
+  a.parity = h->parity;
   a.do_search = 1;
   a.n_cand = n_cand;
   a.cand_first = 0;
   a.cand_count = n_cand + 1;
-  cs_status st = launch_step(h, a, 0, false, 0);
+  cs_status st = launch_step(h, a, 0, 0, false, 0);
   if (st != CS_OK) return st;
   if (distances) {
     CS_CUDA(h, cudaMemcpyAsync(distances, h->d_distances, (size_t)(n_cand + 1) * sizeof(int), cudaMemcpyDeviceToHost,
@@ -546,11 +596,15 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
   a.points = reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
   a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
   a.step_mode = CS_STEP_INTEGRATE_ONLY;
-  cs_status st = launch_step(h, a, n_points, false, 0);
+  a.parity = h->parity;
+  cs_status st = launch_step(h, a, n_points, rings_hint(h, max_range_of(points, n_points)), false, 0);
   if (st != CS_OK) return st;
   if (visits) {
+    long long v = 0;
+    CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+                               cudaMemcpyDeviceToHost, h->stream));
     CS_CUDA(h, cudaStreamSynchronize(h->stream));
-    *visits = reinterpret_cast<const CsDevResult*>(h->h_slot)->visits;
+    *visits = v;
   }
   return CS_OK;
 }
@@ -589,17 +643,18 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
   a.scan_index = h->update_count;
   a.cand_mode = with_offsets ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
   a.step_mode = CS_STEP_UPDATE;
-  a.parity = 0;
+  a.parity = h->parity;
   a.do_search = do_search ? 1 : 0;
   a.n_cand = h->n_cand;
   a.cand_first = 0;
   a.cand_count = h->n_cand + 1;
-  cs_status st = launch_step(h, a, n_points, timing, 2);
+  cs_status st = launch_step(h, a, n_points, rings_hint(h, max_range_of(points, n_points)), timing, 2);
   if (st != CS_OK) return st;
+  h->parity ^= 1;
   h->update_count++;
   if (!do_search) h->scan_count++;  // :741
 
-  st = wait_for_pose(h, a.seq_value, h->tm.ev[3]);
+  st = wait_for_pose(h, a.seq_value, h->tm.ev[2]);
   if (st != CS_OK) return st;
   if (timing) {
     st = collect_timing(h, true);
@@ -607,7 +662,14 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
   }
   if (out) {
     copy_result(out, reinterpret_cast<const CsDevResult*>(h->h_slot));
-    if (!timing) out->visits = -1;  // the integration is still running; cs_sync + cs_get_timing path reports it
+    out->visits = -1;  // counted on the device while the integration runs; cs_get_visits() after cs_sync()
+    if (timing) {
+      long long v = 0;
+      CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+                                 cudaMemcpyDeviceToHost, h->stream));
+      CS_CUDA(h, cudaStreamSynchronize(h->stream));
+      out->visits = v;
+    }
   }
   return CS_OK;
 }
@@ -714,18 +776,30 @@ cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count) {
 
 cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points) {
   CS_CHECK_HANDLE(h);
+  if (!h->d_ray_dbg) return fail(h, CS_ERR_STATE, "handle was created without CS_FLAG_DEBUG_RAYS");
   if (!rays || n_points < 0 || n_points > h->max_points) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad n_points");
   CS_CUDA(h, cudaMemcpyAsync(rays, h->d_ray_dbg, (size_t)n_points * 6 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
   return CS_OK;
 }
 
+cs_status cs_get_visits(cs_processor* h, int64_t* visits) {
+  CS_CHECK_HANDLE(h);
+  if (!visits) return fail(h, CS_ERR_INVALID_ARGUMENT, "null visits");
+  long long v = 0;
+  CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+                             cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *visits = v;
+  return CS_OK;
+}
+
 cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count) {
   CS_CHECK_HANDLE(h);
-  if (count < 0 || count > h->size) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
+  if (count < 0 || count > h->size * 8) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
   if (!h->d_ring_cycles) {  // first call switches the diagnostics on
-    CS_CUDA(h, cudaMalloc(&h->d_ring_cycles, (size_t)h->size * sizeof(long long)));
-    CS_CUDA(h, cudaMemsetAsync(h->d_ring_cycles, 0, (size_t)h->size * sizeof(long long), h->stream));
+    CS_CUDA(h, cudaMalloc(&h->d_ring_cycles, (size_t)h->size * 8 * sizeof(long long)));
+    CS_CUDA(h, cudaMemsetAsync(h->d_ring_cycles, 0, (size_t)h->size * 8 * sizeof(long long), h->stream));
     h->hs.ring_cycles = h->d_ring_cycles;
     return patch_session(h, offsetof(CsSession, ring_cycles), &h->hs.ring_cycles, sizeof(long long*));
   }
@@ -772,6 +846,7 @@ cs_status cs_scanlog_create(int32_t device, int32_t n_scans, int32_t max_points,
   log->h_hdr.assign((size_t)n_scans, CsStepHeader{});
   log->h_points.assign((size_t)n_scans * log->max_points * 2, 0.f);
   log->h_offsets.assign((size_t)n_scans * n_offsets * 3, 0.f);
+  log->h_max_range.assign((size_t)n_scans, 0.0);
   cudaSetDevice(device);
   bool ok = cudaMalloc(&log->d_hdr, sizeof(CsStepHeader) * n_scans) == cudaSuccess &&
             cudaMalloc(&log->d_points, sizeof(float2) * (size_t)n_scans * log->max_points) == cudaSuccess &&
@@ -795,6 +870,7 @@ cs_status cs_scanlog_set(cs_scanlog* log, int32_t scan, const float* points, int
   hd.odo[0] = odometry_pose[0]; hd.odo[1] = odometry_pose[1]; hd.odo[2] = odometry_pose[2];
   hd.n_points = n_points;
   memcpy(&log->h_points[(size_t)scan * log->max_points * 2], points, (size_t)n_points * 8);
+  log->h_max_range[scan] = max_range_of(points, n_points);
   if (cand_offsets && log->n_offsets > 0)
     memcpy(&log->h_offsets[(size_t)scan * log->n_offsets * 3], cand_offsets, (size_t)log->n_offsets * 12);
   log->uploaded = false;
@@ -847,15 +923,18 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     a.points = log->d_points + (size_t)sidx * log->max_points;
     a.cand = log->n_offsets > 0 ? log->d_offsets + (size_t)sidx * log->n_offsets * 3 : nullptr;
     a.result = log->d_results + sidx;
+    a.visits_out = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(log->d_results + sidx) + offsetof(CsDevResult, visits));
     a.scan_index = h->update_count;
     a.cand_mode = log->n_offsets > 0 ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
     a.step_mode = CS_STEP_UPDATE;
+    a.parity = h->parity;
     a.do_search = do_search ? 1 : 0;
     a.n_cand = h->n_cand;
     a.cand_first = 0;
     a.cand_count = h->n_cand + 1;
-    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, per_kernel, 2);
+    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, rings_hint(h, log->h_max_range[sidx]), per_kernel, 2);
     if (st != CS_OK) return st;
+    h->parity ^= 1;
     h->update_count++;
     if (!do_search) h->scan_count++;
   }
@@ -879,7 +958,7 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
 
 cs_status cs_set_flags(cs_processor* h, uint32_t flags) {
   CS_CHECK_HANDLE(h);
-  const uint32_t fixed = CS_FLAG_ROW_MAJOR_MAP | CS_FLAG_L2_PERSIST;
+  const uint32_t fixed = CS_FLAG_ROW_MAJOR_MAP | CS_FLAG_L2_PERSIST | CS_FLAG_DEBUG_RAYS;
   if ((flags & fixed) != (h->cfg.flags & fixed)) return fail(h, CS_ERR_INVALID_ARGUMENT, "map layout / L2 window are fixed at creation");
   h->cfg.flags = flags;
   int* dist = (flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;

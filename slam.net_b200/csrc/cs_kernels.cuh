@@ -2,9 +2,12 @@
 //
 //   cs_search_kernel     CalculateDistanceSISD + MonteCarloSearch + ParallelMonteCarloSearch arg-min
 //                        (CoreSLAM/CoreSLAMProcessor.cs:226-259, 624-653, 674-710)
-//   cs_finalize_kernel   Update glue (:717-752: gate, searchPose, NormalizeAngle, state) and the per-ray
-//                        part of UpdateHoleMap / DrawLaserRayOnHoleMap / ClipRay (:496-534, 359-402, 320-345)
-//   cs_integrate_kernel  the draw loop (:404-442) re-organised by rings (see below) so the ordered
+//                        The last block to finish also runs the Update glue (:717-752: gate, searchPose,
+//                        NormalizeAngle, state), publishes the pose and prepares the rays, so the pose
+//                        leaves the device at the end of the search kernel itself.
+//   cs_setup_kernel      the same glue + per-ray part of UpdateHoleMap / DrawLaserRayOnHoleMap / ClipRay
+//                        (:496-534, 359-402, 320-345) on its own, for scans without a search and big scans
+//   cs_rings_kernel      the draw loop (:404-442) re-organised by rings (see below) so the ordered
 //                        read-modify-write is exact without atomics or sorting
 //
 // No tensor cores: nothing here is a contraction.  The search is a 2-byte gather per (candidate, point)
@@ -46,6 +49,24 @@ struct CsRay {  // 32 B: everything the draw loop needs to know about one ray, i
   int flags;      // bit0 valid, bit1 steep (major axis = y), bit2 major step negative, bit3 minor step negative
 };
 
+// 16-byte form kept in global memory (every field fits: sizes <= 16384, |incv| <= 65500)
+__device__ __forceinline__ int4 cs_pack_ray(const CsRay& r) {
+  int4 q;
+  q.x = r.dxc | (r.dyc << 14) | (r.flags << 28);
+  q.y = r.a0 | ((r.b0 + 1) << 15);
+  q.z = (-r.incv) | (r.nd_total << 16);
+  q.w = r.kc;
+  return q;
+}
+__device__ __forceinline__ CsRay cs_unpack_ray(const int4 q) {
+  CsRay r;
+  r.dxc = q.x & 0x3fff; r.dyc = (q.x >> 14) & 0x3fff; r.flags = (int)((unsigned)q.x >> 28);
+  r.a0 = q.y & 0x7fff; r.b0 = ((q.y >> 15) & 0x7fff) - 1;
+  r.incv = -(q.z & 0xffff); r.nd_total = (int)((unsigned)q.z >> 16);
+  r.kc = q.w;
+  return r;
+}
+
 struct CsDevResult {  // device twin of cs_result (include/coreslam_b200.h)
   float pose[3];
   int distance;
@@ -65,16 +86,18 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   float hole_width;  // :87
   int search_begin;  // :92
   unsigned long long seed;
-  CsState state[2];            // slot 0 is live (slot 1 spare)
-  unsigned long long key[2];   // packed (distance << 32 | flat index) arg-min of the running search
-  CsRay* rays;                 // capacity max_points
-  int* ray_dbg;                // optional 6 ints per ray (x1,y1,x2,y2,xp,yp)
+  CsState state[2];            // state[parity] is current; an Update writes state[parity^1] and the host flips parity
+  unsigned long long key[2];   // packed (distance << 32 | flat index) arg-min; key[parity] belongs to the current step
+  int4* rays;                  // packed per-ray draw parameters of the current integration (capacity max_points)
+  int* batch_max;              // per 32 consecutive rays: largest dxc of a valid ray, -1 if none
+  int* ray_dbg;                // optional 6 ints per ray (x1,y1,x2,y2,xp,yp), CS_FLAG_DEBUG_RAYS
   int* distances;              // optional n_cand+1
-  long long* ring_cycles;      // optional diagnostics: cycles each ring's warp spent in the integrate kernel
-  int x1, y1;                  // ray origin cell of the current integration (:505-506)
-  int max_ring;                // max dxc over valid rays, -1 if nothing to draw
-  int n_rays;
-  long long visits;
+  long long* ring_cycles;      // optional diagnostics: cycles each ring's block spent in the rings kernel
+  float cur_pose[3];           // pose the current integration draws from (Pose after :745-747)
+  float cur_cs[2];             // its (cos, sin), unscaled
+  int max_ring;                // largest dxc of a valid ray, -1: nothing to draw, INT_MAX: unknown (multi-block set-up)
+  unsigned search_done;        // blocks of the running search kernel that have finished
+  long long visits;            // cells written by the current integration = sum over valid rays of dxc+1
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
@@ -88,11 +111,17 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned scan_index;
   int cand_mode;   // CsCandMode
   int step_mode;   // CsStepMode
-  int parity;      // which state/key slot this handle uses (0)
+  int parity;      // state[parity]/key[parity] are read; an UPDATE step writes state[parity^1] and arms key[parity^1]
   int do_search;   // host mirror of scanCount >= PositionSearchBeginning (:726)
   int n_cand;      // random candidates evaluated this step (excludes searchPose)
   int cand_first;  // first flat index evaluated by this GPU (multi-GPU candidate split), normally 0
   int cand_count;  // number of flat indices evaluated by this GPU, normally n_cand+1
+  int fuse_publish;  // search kernel: its last block runs the Update glue and publishes the pose
+  int fuse_rays;     // ... and prepares the rays (scans of up to CS_FUSE_RAYS_MAX points)
+  int rays_only;     // set-up kernel: the pose was already published, only prepare rays from cur_pose
+  int max_ring_hint; // rings the host launched blocks for, minus one
+  long long* visits_out;  // optional device slot that receives the visit count
+  long long* diag;        // optional diagnostics buffer (8 values per ring), see cs_get_ring_cycles
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -152,6 +181,269 @@ __device__ __forceinline__ void cs_candidate_pose(const CsSession& S, const CsSt
   pose[0] = __fadd_rn(sp[0], off[0]);  // :635-637
   pose[1] = __fadd_rn(sp[1], off[1]);
   pose[2] = __fadd_rn(sp[2], off[2]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ray set-up (ClipRay :320-345 and the prologue of DrawLaserRayOnHoleMap :361-402)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cs_clip_ray(int size, int& xyc, int& yxc, int xy, int yx) {
+  if (xyc < 0) {
+    if (xyc == xy) return false;
+    yxc = cs_wadd(yxc, cs_wdiv(cs_wmul(cs_wsub(yxc, yx), cs_wsub(0, xyc)), cs_wsub(xyc, xy)));
+    xyc = 0;
+  }
+  if (xyc >= size) {
+    if (xyc == xy) return false;
+    yxc = cs_wadd(yxc, cs_wdiv(cs_wmul(cs_wsub(yxc, yx), cs_wsub(size - 1, xyc)), cs_wsub(xyc, xy)));
+    xyc = size - 1;
+  }
+  return true;
+}
+
+__device__ __forceinline__ CsRay cs_make_ray(int size, int x1, int y1, int x2, int y2, int xp, int yp) {
+  CsRay r;
+  r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
+  int x2c = x2, y2c = y2;
+  if (!cs_clip_ray(size, x2c, y2c, x1, y1)) return r;  // :365
+  if (!cs_clip_ray(size, y2c, x2c, y1, x1)) return r;  // :366
+  int dx = cs_wabs(cs_wsub(x2, x1)), dy = cs_wabs(cs_wsub(y2, y1));        // :368-369
+  int dxc = cs_wabs(cs_wsub(x2c, x1)), dyc = cs_wabs(cs_wsub(y2c, y1));    // :370-371
+  int sx = cs_sign(cs_wsub(x2, x1)), sy = cs_sign(cs_wsub(y2, y1));        // :372-373
+  int D, smaj, smin;
+  bool steep;
+  if (dx > dy) {  // :377
+    steep = false;
+    D = cs_wabs(cs_wsub(xp, x2));
+    smaj = sx; smin = sy;
+  } else {
+    steep = true;
+    dx = dy;
+    int t = dxc; dxc = dyc; dyc = t;
+    D = cs_wabs(cs_wsub(yp, y2));
+    smaj = sy; smin = sx;
+  }
+  if (D == 0) return r;  // :389-392
+  // the walk below never leaves the box [start, clipped end]; reject anything a wrapped clip produced
+  if (dxc >= size || dyc >= size || D < 0) return r;
+  const int value = CS_TS_OBSTACLE;
+  int incv = (value - CS_TS_NO_OBSTACLE) / D;                     // :398
+  int rem = -(value - CS_TS_NO_OBSTACLE - cs_wmul(D, incv));      // -incerrorv >= 0, :399
+  // zone thresholds in 64 bit: descending while t2 < x <= t1, ascending while x > t2 and x > t1 (:406-408)
+  long long t2 = (long long)cs_wsub(dx, cs_wmul(2, D)) + 1;       // first x with x > dx - 2*derrorv
+  long long t1 = (long long)cs_wsub(dx, D);
+  long long a0 = t2 > 0 ? t2 : 0;
+  long long lim = (long long)size + 1;                            // beyond any x <= dxc
+  if (a0 > lim) a0 = lim;
+  if (t1 > lim) t1 = lim;
+  if (t1 < -1) t1 = -1;
+  long long nd_total = t1 - a0 + 1;
+  if (nd_total < 0) nd_total = 0;
+  long long e0 = (long long)(D / 2) - nd_total * (long long)rem;  // errorv entering the ascending zone (:397, :411)
+  long long need = -e0 - (long long)rem;
+  long long kc = 0;
+  if (need > 0) {
+    const long long knum = need + (long long)rem + (long long)D - 1, kden = (long long)rem + (long long)D;
+    kc = (knum < 0x7fffffffLL) ? (long long)((unsigned)knum / (unsigned)kden) : knum / kden;  // 32-bit in practice
+  }
+  if (kc > lim) kc = lim;
+  r.dxc = dxc; r.dyc = dyc;
+  r.a0 = (int)a0; r.b0 = (int)t1;
+  r.incv = incv; r.kc = (int)kc; r.nd_total = (int)nd_total;
+  r.flags = 1 | (steep ? 2 : 0) | (smaj < 0 ? 4 : 0) | (smin < 0 ? 8 : 0);
+  return r;
+}
+
+// pixval written at major step x of ray r (closed form of :402-428)
+__device__ __forceinline__ int cs_ray_pixval(const CsRay& r, int x) {
+  if (x <= r.b0) {
+    int nd = x - r.a0 + 1;
+    nd = nd > 0 ? nd : 0;
+    return CS_TS_NO_OBSTACLE + nd * r.incv;
+  }
+  int c0 = max(r.a0, r.b0 + 1);
+  if (x < c0) return CS_TS_NO_OBSTACLE;
+  int j = x - c0 + 1;
+  return CS_TS_NO_OBSTACLE + (r.nd_total - j) * r.incv + min(j, r.kc);
+}
+
+// minor-axis offset after x major steps (closed form of the Bresenham error walk :394-396, 433-441)
+__device__ __forceinline__ int cs_ray_minor(const CsRay& r, int x) {
+  if (x == 0) return 0;
+  // floor(num / den) with num < 2^30, den <= 2^15: a float estimate is within +-1, fixed up exactly
+  const int num = 2 * r.dyc * x + r.dxc - 1;
+  const int den = 2 * r.dxc;
+  int q = __float2int_rz(__fmul_rz(__int2float_rz(num), __frcp_rz(__int2float_rz(den))));
+  int rem = num - q * den;
+  if (rem < 0) { q--; rem += den; }
+  if (rem >= den) q++;
+  return min(q, x);
+}
+
+
+
+// ---------------------------------------------------------------------------------------------------
+// Update glue (:717-752) — run by ONE thread.  cs_glue_pose decodes the arg-min, applies the search gate
+// and normalises the angle; cs_glue_publish stores state / result / flag and leaves the pose and its
+// (cos, sin) in the session's cur_pose / cur_cs for the ray preparation and the rings kernel.
+// ---------------------------------------------------------------------------------------------------
+struct CsGlue {
+  float pose[3];
+  float cs[2];
+  int dist, index, searched;
+};
+
+// pure part: which pose does this step end on (no side effects)
+__device__ __forceinline__ void cs_glue_pose(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
+                                             CsGlue& g) {
+  g.dist = 2147483647; g.index = 0; g.searched = 0;
+  bool have_cs = false;
+  if (a.step_mode == CS_STEP_INTEGRATE_ONLY) {
+    g.pose[0] = hdr.odo[0]; g.pose[1] = hdr.odo[1]; g.pose[2] = hdr.odo[2];
+    if (hdr.has_cs) { have_cs = true; g.cs[0] = hdr.cs[0]; g.cs[1] = hdr.cs[1]; }
+  } else {
+    float sp[3];
+    cs_search_pose(S, hdr, a, sp);
+    if (a.do_search) {
+      const unsigned long long key = atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
+      g.dist = (int)(unsigned)(key >> 32);
+      g.index = (int)(unsigned)(key & 0xffffffffu);
+      g.searched = 1;
+      cs_candidate_pose(S, a, cand, sp, g.index, g.pose);
+    } else {
+      g.pose[0] = hdr.odo[0]; g.pose[1] = hdr.odo[1]; g.pose[2] = hdr.odo[2];  // :742
+    }
+    if (a.step_mode == CS_STEP_UPDATE) g.pose[2] = cs_normalize_angle(g.pose[2]);  // :746
+  }
+  if (!have_cs) { g.cs[0] = cs_cosf(g.pose[2]); g.cs[1] = cs_sinf(g.pose[2]); }
+}
+
+// side effects: processor state, arg-min re-arm, result record + flag, session scratch for the integration
+__device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a,
+                                                CsDevResult* result, const CsGlue& g) {
+  if (a.step_mode == CS_STEP_UPDATE) {
+    const CsState& st0 = S.state[a.parity];
+    CsState& st1 = S.state[a.parity ^ 1];
+    st1.pose[0] = g.pose[0]; st1.pose[1] = g.pose[1]; st1.pose[2] = g.pose[2];                   // :747
+    st1.last_odo[0] = hdr.odo[0]; st1.last_odo[1] = hdr.odo[1]; st1.last_odo[2] = hdr.odo[2];   // :745
+    st1.scan_count = st0.scan_count + (a.do_search ? 0 : 1);                                     // :741
+    S.key[a.parity ^ 1] = ~0ull;  // arm the next step's arg-min
+  } else if (a.step_mode == CS_STEP_SEARCH_ONLY) {
+    S.key[a.parity] = ~0ull;  // re-arm in place
+  }
+  S.cur_pose[0] = g.pose[0]; S.cur_pose[1] = g.pose[1]; S.cur_pose[2] = g.pose[2];
+  S.cur_cs[0] = g.cs[0]; S.cur_cs[1] = g.cs[1];
+  S.max_ring = 2147483647;  // unknown until the rays are prepared (a multi-block set-up leaves it there)
+  S.visits = 0;
+  if (result) {
+    result->pose[0] = g.pose[0]; result->pose[1] = g.pose[1]; result->pose[2] = g.pose[2];
+    result->distance = g.dist;
+    result->index = g.index;
+    result->searched = g.searched;
+    result->visits = 0;
+    if (a.seq_flag) {
+      __threadfence_system();
+      *a.seq_flag = a.seq_value;
+    }
+  }
+}
+
+// Per-ray part of UpdateHoleMap (:517-530) + ClipRay + the prologue of DrawLaserRayOnHoleMap for rays
+// first, first+stride, ... < n.  Returns this thread's (max dxc, visits) contribution.
+__device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __restrict__ points, int n, int first, int stride,
+                                                const float pose[3], const float cs[2], bool write_dbg,
+                                                int& max_ring, long long& visits) {
+  const float scale = S.scale;
+  const int size = S.size;
+  const float px = __fadd_rn(__fmul_rn(pose[0], scale), 0.5f);  // :499
+  const float py = __fadd_rn(__fmul_rn(pose[1], scale), 0.5f);  // :500
+  const float c = __fmul_rn(cs[0], scale);                       // :501
+  const float s = __fmul_rn(cs[1], scale);                       // :502
+  const int x1 = cs_cvt_i32(px), y1 = cs_cvt_i32(py);            // :505-506
+  const bool on_map = !(x1 < 0 || x1 >= size || y1 < 0 || y1 >= size);  // :509-512
+  const float hw = S.hole_width;
+  for (int i = first; i < n; i += stride) {
+    CsRay r;
+    r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
+    int x2 = 0, y2 = 0, xp = 0, yp = 0;
+    if (on_map) {
+      const float2 p = points[i];
+      float x2p = __fsub_rn(__fmul_rn(c, p.x), __fmul_rn(s, p.y));  // :519
+      float y2p = __fadd_rn(__fmul_rn(s, p.x), __fmul_rn(c, p.y));  // :520
+      xp = cs_cvt_i32(__fadd_rn(px, x2p));                          // :521
+      yp = cs_cvt_i32(__fadd_rn(py, y2p));                          // :522
+      float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(x2p, x2p), __fmul_rn(y2p, y2p)));  // :524
+      float add = __fdiv_rn(__fdiv_rn(__fmul_rn(hw, scale), 2.0f), dist);            // :525
+      float k1 = __fadd_rn(1.0f, add);
+      x2p = __fmul_rn(x2p, k1);                                     // :527
+      y2p = __fmul_rn(y2p, k1);                                     // :528
+      x2 = cs_cvt_i32(__fadd_rn(px, x2p));                          // :529
+      y2 = cs_cvt_i32(__fadd_rn(py, y2p));                          // :530
+      r = cs_make_ray(size, x1, y1, x2, y2, xp, yp);
+      if (r.flags & 1) {
+        max_ring = max(max_ring, r.dxc);
+        visits += (long long)r.dxc + 1;
+      }
+    }
+    S.rays[i] = cs_pack_ray(r);
+    {  // the 32 lanes of a warp hold 32 consecutive rays (first and stride are multiples of 32 apart)
+      int bm = (r.flags & 1) ? r.dxc : -1;
+      bm = __reduce_max_sync(__activemask(), bm);
+      if ((i & 31) == 0) S.batch_max[i >> 5] = bm;
+    }
+    if (write_dbg && S.ray_dbg) {
+      int* d = S.ray_dbg + 6 * (size_t)i;
+      d[0] = x1; d[1] = y1; d[2] = x2; d[3] = y2; d[4] = xp; d[5] = yp;
+    }
+  }
+}
+
+// Block-wide: glue by thread 0 (publish), then all threads prepare the n rays; exact max_ring / visits.
+#define CS_FUSE_RAYS_MAX 2048
+template <int THREADS>
+__device__ __forceinline__ void cs_publish_and_prepare(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a,
+                                                       const float2* __restrict__ points, const float* cand,
+                                                       CsDevResult* result, bool with_rays) {
+  __shared__ float sh_pose[3];
+  __shared__ float sh_cs[2];
+  __shared__ int sh_ring[THREADS / 32];
+  __shared__ long long sh_vis[THREADS / 32];
+  CsGlue g;
+  if (threadIdx.x == 0) {
+    cs_glue_pose(S, hdr, a, cand, g);
+    sh_pose[0] = g.pose[0]; sh_pose[1] = g.pose[1]; sh_pose[2] = g.pose[2];
+    sh_cs[0] = g.cs[0]; sh_cs[1] = g.cs[1];
+  }
+  if (!with_rays) {
+    if (threadIdx.x == 0) cs_glue_publish(S, hdr, a, result, g);
+    return;
+  }
+  __syncthreads();
+  // the other threads start on the rays while thread 0 publishes (system-scope fence + flag for the host)
+  if (threadIdx.x == 0) cs_glue_publish(S, hdr, a, result, g);
+  const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
+  const float cs[2] = {sh_cs[0], sh_cs[1]};
+  int max_ring = -1;
+  long long visits = 0;
+  cs_prepare_rays(S, points, hdr.n_points, threadIdx.x, THREADS, pose, cs, true, max_ring, visits);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    max_ring = max(max_ring, __shfl_xor_sync(0xffffffffu, max_ring, o));
+    visits += __shfl_xor_sync(0xffffffffu, visits, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh_ring[threadIdx.x >> 5] = max_ring;
+    sh_vis[threadIdx.x >> 5] = visits;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < THREADS / 32; w++) {
+      max_ring = max(max_ring, sh_ring[w]);
+      visits += sh_vis[w];
+    }
+    S.max_ring = max_ring;
+    S.visits = visits;
+    if (a.visits_out) *a.visits_out = visits;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -245,334 +537,329 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   }
   if (lane == 0) s_key[warp] = key;
   __syncthreads();
+  __shared__ int s_last;
   if (threadIdx.x == 0) {
     unsigned long long k = s_key[0];
 #pragma unroll
     for (int w = 1; w < CS_SEARCH_WARPS; w++) k = min(k, s_key[w]);
     if (k != ~0ull) atomicMin(&S.key[a.parity], k);
+    int last = 0;
+    if (a.fuse_publish) {
+      __threadfence();
+      last = (atomicAdd(&S.search_done, 1u) == gridDim.x - 1) ? 1 : 0;
+      if (last) S.search_done = 0;
+    }
+    s_last = last;
   }
+  if (!a.fuse_publish) return;
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the last block to finish owns the complete arg-min: Update glue, pose out, rays ------------------
+  __threadfence();
+  CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
+  cs_publish_and_prepare<CS_SEARCH_WARPS * 32>(S, hdr, a, points, cand, result,
+                                               a.fuse_rays && a.step_mode != CS_STEP_SEARCH_ONLY);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// ray set-up (ClipRay :320-345 and the prologue of DrawLaserRayOnHoleMap :361-402)
+// set-up kernel: glue + ray preparation without a search kernel in front (map-only scans, cs_integrate,
+// multi-GPU searches whose arg-min is reduced between the kernels), or — rays_only, several blocks — the
+// ray preparation of scans too big for one block.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool cs_clip_ray(int size, int& xyc, int& yxc, int xy, int yx) {
-  if (xyc < 0) {
-    if (xyc == xy) return false;
-    yxc = cs_wadd(yxc, cs_wdiv(cs_wmul(cs_wsub(yxc, yx), cs_wsub(0, xyc)), cs_wsub(xyc, xy)));
-    xyc = 0;
-  }
-  if (xyc >= size) {
-    if (xyc == xy) return false;
-    yxc = cs_wadd(yxc, cs_wdiv(cs_wmul(cs_wsub(yxc, yx), cs_wsub(size - 1, xyc)), cs_wsub(xyc, xy)));
-    xyc = size - 1;
-  }
-  return true;
-}
+#define CS_SETUP_THREADS 256
 
-__device__ __forceinline__ CsRay cs_make_ray(int size, int x1, int y1, int x2, int y2, int xp, int yp) {
-  CsRay r;
-  r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
-  int x2c = x2, y2c = y2;
-  if (!cs_clip_ray(size, x2c, y2c, x1, y1)) return r;  // :365
-  if (!cs_clip_ray(size, y2c, x2c, y1, x1)) return r;  // :366
-  int dx = cs_wabs(cs_wsub(x2, x1)), dy = cs_wabs(cs_wsub(y2, y1));        // :368-369
-  int dxc = cs_wabs(cs_wsub(x2c, x1)), dyc = cs_wabs(cs_wsub(y2c, y1));    // :370-371
-  int sx = cs_sign(cs_wsub(x2, x1)), sy = cs_sign(cs_wsub(y2, y1));        // :372-373
-  int D, smaj, smin;
-  bool steep;
-  if (dx > dy) {  // :377
-    steep = false;
-    D = cs_wabs(cs_wsub(xp, x2));
-    smaj = sx; smin = sy;
-  } else {
-    steep = true;
-    dx = dy;
-    int t = dxc; dxc = dyc; dyc = t;
-    D = cs_wabs(cs_wsub(yp, y2));
-    smaj = sy; smin = sx;
-  }
-  if (D == 0) return r;  // :389-392
-  // the walk below never leaves the box [start, clipped end]; reject anything a wrapped clip produced
-  if (dxc >= size || dyc >= size || D < 0) return r;
-  const int value = CS_TS_OBSTACLE;
-  int incv = (value - CS_TS_NO_OBSTACLE) / D;                     // :398
-  int rem = -(value - CS_TS_NO_OBSTACLE - cs_wmul(D, incv));      // -incerrorv >= 0, :399
-  // zone thresholds in 64 bit: descending while t2 < x <= t1, ascending while x > t2 and x > t1 (:406-408)
-  long long t2 = (long long)cs_wsub(dx, cs_wmul(2, D)) + 1;       // first x with x > dx - 2*derrorv
-  long long t1 = (long long)cs_wsub(dx, D);
-  long long a0 = t2 > 0 ? t2 : 0;
-  long long lim = (long long)size + 1;                            // beyond any x <= dxc
-  if (a0 > lim) a0 = lim;
-  if (t1 > lim) t1 = lim;
-  if (t1 < -1) t1 = -1;
-  long long nd_total = t1 - a0 + 1;
-  if (nd_total < 0) nd_total = 0;
-  long long e0 = (long long)(D / 2) - nd_total * (long long)rem;  // errorv entering the ascending zone (:397, :411)
-  long long need = -e0 - (long long)rem;
-  long long kc = need > 0 ? (need + (long long)rem + (long long)D - 1) / ((long long)rem + (long long)D) : 0;
-  if (kc > lim) kc = lim;
-  r.dxc = dxc; r.dyc = dyc;
-  r.a0 = (int)a0; r.b0 = (int)t1;
-  r.incv = incv; r.kc = (int)kc; r.nd_total = (int)nd_total;
-  r.flags = 1 | (steep ? 2 : 0) | (smaj < 0 ? 4 : 0) | (smin < 0 ? 8 : 0);
-  return r;
-}
-
-// pixval written at major step x of ray r (closed form of :402-428)
-__device__ __forceinline__ int cs_ray_pixval(const CsRay& r, int x) {
-  if (x <= r.b0) {
-    int nd = x - r.a0 + 1;
-    nd = nd > 0 ? nd : 0;
-    return CS_TS_NO_OBSTACLE + nd * r.incv;
-  }
-  int c0 = max(r.a0, r.b0 + 1);
-  if (x < c0) return CS_TS_NO_OBSTACLE;
-  int j = x - c0 + 1;
-  return CS_TS_NO_OBSTACLE + (r.nd_total - j) * r.incv + min(j, r.kc);
-}
-
-// minor-axis offset after x major steps (closed form of the Bresenham error walk :394-396, 433-441)
-__device__ __forceinline__ int cs_ray_minor(const CsRay& r, int x) {
-  if (x == 0) return 0;
-  unsigned num = 2u * (unsigned)r.dyc * (unsigned)x + (unsigned)r.dxc - 1u;
-  unsigned m = num / (2u * (unsigned)r.dxc);
-  return min((int)m, x);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// finalize: one block per session
-// ---------------------------------------------------------------------------------------------------
-#define CS_FINALIZE_THREADS 512
-
-__global__ void __launch_bounds__(CS_FINALIZE_THREADS)
-cs_finalize_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  __shared__ float s_pose[3];
-  __shared__ float s_cs[2];
-  __shared__ int s_red_ring[CS_FINALIZE_THREADS / 32];
-  __shared__ long long s_red_vis[CS_FINALIZE_THREADS / 32];
-
-  const int sj = blockIdx.x;
+__global__ void __launch_bounds__(CS_SETUP_THREADS)
+cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
   const CsStepHeader& hdr = a.hdr[sj];
   const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
-
+  if (!a.rays_only) {  // single block: glue, publish, and (small scans) the rays
+    cs_publish_and_prepare<CS_SETUP_THREADS>(S, hdr, a, points, cand, result,
+                                             a.fuse_rays && a.step_mode != CS_STEP_SEARCH_ONLY);
+    return;
+  }
+  // rays only, any number of blocks: the pose was published by an earlier kernel (which also zeroed
+  // S.visits and left S.max_ring at "unknown")
+  __shared__ float sh_pose[3];
+  __shared__ float sh_cs[2];
   if (threadIdx.x == 0) {
-    float pose[3];
-    int dist = 2147483647, index = 0, searched = 0;
-    bool have_cs = false;
-    float ct = 0.f, st = 0.f;
-    if (a.step_mode == CS_STEP_INTEGRATE_ONLY) {
-      pose[0] = hdr.odo[0]; pose[1] = hdr.odo[1]; pose[2] = hdr.odo[2];
-      if (hdr.has_cs) { have_cs = true; ct = hdr.cs[0]; st = hdr.cs[1]; }
-    } else {
-      float sp[3];
-      cs_search_pose(S, hdr, a, sp);
-      if (a.do_search) {
-        unsigned long long key = S.key[a.parity];
-        dist = (int)(unsigned)(key >> 32);
-        index = (int)(unsigned)(key & 0xffffffffu);
-        searched = 1;
-        cs_candidate_pose(S, a, cand, sp, index, pose);
-      } else {
-        pose[0] = hdr.odo[0]; pose[1] = hdr.odo[1]; pose[2] = hdr.odo[2];  // :742
-      }
-      if (a.step_mode == CS_STEP_UPDATE) {
-        pose[2] = cs_normalize_angle(pose[2]);  // :746
-        // in place: kernels of one handle are stream ordered, and only this thread touches the state here
-        CsState& st1 = S.state[a.parity];
-        st1.pose[0] = pose[0]; st1.pose[1] = pose[1]; st1.pose[2] = pose[2];  // :747
-        st1.last_odo[0] = hdr.odo[0]; st1.last_odo[1] = hdr.odo[1]; st1.last_odo[2] = hdr.odo[2];  // :745
-        st1.scan_count += (a.do_search ? 0 : 1);  // :741
-      }
-    }
-    S.key[a.parity] = ~0ull;  // re-arm the arg-min for the next search
-    if (result) {
-      result->pose[0] = pose[0]; result->pose[1] = pose[1]; result->pose[2] = pose[2];
-      result->distance = dist;
-      result->index = index;
-      result->searched = searched;
-      if (a.seq_flag) {
-        __threadfence_system();
-        *a.seq_flag = a.seq_value;
-      }
-    }
-    if (!have_cs) { ct = cs_cosf(pose[2]); st = cs_sinf(pose[2]); }
-    s_pose[0] = pose[0]; s_pose[1] = pose[1]; s_pose[2] = pose[2];
-    s_cs[0] = ct; s_cs[1] = st;
+    sh_pose[0] = S.cur_pose[0]; sh_pose[1] = S.cur_pose[1]; sh_pose[2] = S.cur_pose[2];
+    sh_cs[0] = S.cur_cs[0]; sh_cs[1] = S.cur_cs[1];
   }
   __syncthreads();
-
+  const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
+  const float cs[2] = {sh_cs[0], sh_cs[1]};
   int max_ring = -1;
   long long visits = 0;
-  const int n = (a.step_mode == CS_STEP_SEARCH_ONLY) ? 0 : hdr.n_points;
-  const float scale = S.scale;
-  const int size = S.size;
-  const float px = __fadd_rn(__fmul_rn(s_pose[0], scale), 0.5f);  // :499
-  const float py = __fadd_rn(__fmul_rn(s_pose[1], scale), 0.5f);  // :500
-  const float c = __fmul_rn(s_cs[0], scale);                       // :501
-  const float s = __fmul_rn(s_cs[1], scale);                       // :502
-  const int x1 = cs_cvt_i32(px), y1 = cs_cvt_i32(py);              // :505-506
-  const bool on_map = !(x1 < 0 || x1 >= size || y1 < 0 || y1 >= size);  // :509-512
-  const float hw = S.hole_width;
-
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    CsRay r;
-    r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
-    int x2 = 0, y2 = 0, xp = 0, yp = 0;
-    if (on_map) {
-      const float2 p = points[i];
-      float x2p = __fsub_rn(__fmul_rn(c, p.x), __fmul_rn(s, p.y));  // :519
-      float y2p = __fadd_rn(__fmul_rn(s, p.x), __fmul_rn(c, p.y));  // :520
-      xp = cs_cvt_i32(__fadd_rn(px, x2p));                          // :521
-      yp = cs_cvt_i32(__fadd_rn(py, y2p));                          // :522
-      float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(x2p, x2p), __fmul_rn(y2p, y2p)));  // :524
-      float add = __fdiv_rn(__fdiv_rn(__fmul_rn(hw, scale), 2.0f), dist);            // :525
-      float k1 = __fadd_rn(1.0f, add);
-      x2p = __fmul_rn(x2p, k1);                                     // :527
-      y2p = __fmul_rn(y2p, k1);                                     // :528
-      x2 = cs_cvt_i32(__fadd_rn(px, x2p));                          // :529
-      y2 = cs_cvt_i32(__fadd_rn(py, y2p));                          // :530
-      r = cs_make_ray(size, x1, y1, x2, y2, xp, yp);
-      if (r.flags & 1) {
-        max_ring = max(max_ring, r.dxc);
-        visits += (long long)r.dxc + 1;
-      }
-    }
-    S.rays[i] = r;
-    if (S.ray_dbg) {
-      int* d = S.ray_dbg + 6 * (size_t)i;
-      d[0] = x1; d[1] = y1; d[2] = x2; d[3] = y2; d[4] = xp; d[5] = yp;
-    }
-  }
-
+  cs_prepare_rays(S, points, hdr.n_points, blockIdx.x * CS_SETUP_THREADS + threadIdx.x, gridDim.x * CS_SETUP_THREADS,
+                  pose, cs, true, max_ring, visits);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    max_ring = max(max_ring, __shfl_xor_sync(0xffffffffu, max_ring, o));
-    visits += __shfl_xor_sync(0xffffffffu, visits, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    s_red_ring[threadIdx.x >> 5] = max_ring;
-    s_red_vis[threadIdx.x >> 5] = visits;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < CS_FINALIZE_THREADS / 32; w++) {
-      max_ring = max(max_ring, s_red_ring[w]);
-      visits += s_red_vis[w];
-    }
-    S.x1 = x1; S.y1 = y1;
-    S.max_ring = max_ring;
-    S.n_rays = n;
-    S.visits = visits;
-    if (result) result->visits = visits;
+  for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
+  if ((threadIdx.x & 31) == 0 && visits) {
+    atomicAdd((unsigned long long*)&S.visits, (unsigned long long)visits);
+    if (a.visits_out) atomicAdd((unsigned long long*)a.visits_out, (unsigned long long)visits);
   }
 }
 
+
 // ---------------------------------------------------------------------------------------------------
-// integration by rings.
+// rings kernel: the draw loop (:404-442).
 //
 // Every ray starts in the same cell (x1,y1) and advances exactly one cell along its major axis per step,
 // so the cell written at step k lies on the square ring of Chebyshev radius k around the start.  Rings
-// are therefore independent of each other, and inside a ring the only ordering that matters is the
-// reference's ray order (foreach over cloud.Points, :517).  One warp owns one ring: it walks the rays
-// in index order 32 at a time, each lane evaluates its ray's cell and pixval at step k in closed form,
-// lanes that hit the same cell are applied in lane (= ray) order by the group's first lane, and
-// consecutive 32-ray batches are ordered by program order.  No atomics, no sort, bit-exact.
+// are independent of each other, and inside a ring the only ordering that matters is the reference's
+// ray order (foreach over cloud.Points, :517) among rays that hit the same cell.
+//
+// One block owns one ring.  Its warps take the rays in rounds of 256 per warp (eight 32-ray batches); every
+// lane evaluates its ray's cell, ring position and pixval at step k in closed form and leaves (position,
+// pixval).  Lanes of a batch that sit on the same cell form a group (match.any); the group's first lane
+// enters the cell into a shared-memory hash table keyed by ring position and sets its batch's bit in the
+// cell's mask.  Then, per cell, the batches of the mask are applied in ascending (= ray) order: the first
+// loads the cell from the map, each applies its lanes in lane order and hands the value to the next batch
+// through shared memory, the last stores the cell.  Cells are independent, so all map loads are in flight
+// together and nothing is serialised except the blends of one cell — which is exactly the reference's
+// dependency.  Batches whose rays all share one cell and pixval (the long runs of the inner rings) are
+// applied as a count, and a cell that has reached the fixed point of a pixval skips further identical
+// blends.  No global atomics, no sort, bit-exact for any ray order.
 // ---------------------------------------------------------------------------------------------------
-#define CS_INT_WARPS 8
-#define CS_INT_CHUNK 256  // rays staged per pass (8 KB)
+#define CS_RING_B 4                     // 32-ray batches per warp
+#define CS_RING_GROUP (32 * CS_RING_B)  // rays per warp and round
+#define CS_RING_MAX_WARPS 8
+#define CS_RING_UW ((CS_RING_MAX_WARPS * CS_RING_B + 31) / 32)  // mask words per slot
+#define CS_RING_SMEM_PER_WARP (CS_RING_GROUP * 4 * (2 + 6 + 2 * CS_RING_UW))  // pos, pix; per slot (2 per ray): key, value, seq, masks
+#define CS_POS_NONE (-1)
 
 __device__ __forceinline__ int cs_blend(int old, int pixval, int alpha) {
   return (int)(uint16_t)(((256 - alpha) * old + alpha * pixval) >> 8);  // :431
 }
 
-template <bool TILED>
-__global__ void __launch_bounds__(CS_INT_WARPS * 32)
-cs_integrate_kernel(CsSession* __restrict__ sessions) {
-  __shared__ CsRay s_rays[CS_INT_CHUNK];
-  const int sj = blockIdx.y;
-  CsSession& S = sessions[sj];
-  const int max_ring = S.max_ring;
-  if ((int)(blockIdx.x * CS_INT_WARPS) > max_ring) return;  // whole block beyond the longest ray
+// position of cell (x1+ox, y1+oy) along the ring of radius k = max(|ox|,|oy|): 0 .. 8k-1, counter-clockwise
+// from the corner (k,-k).  One value per cell.
+__device__ __forceinline__ int cs_ring_pos(int ox, int oy, int k) {
+  if (ox == k) return oy + k;
+  if (oy == k) return 3 * k - ox;
+  if (ox == -k) return 5 * k - oy;
+  return 7 * k + ox;
+}
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k = blockIdx.x * CS_INT_WARPS + warp;  // this warp's ring
-  const int n = S.n_rays;
-  const int size = S.size, pitch_tiles = S.pitch_tiles;
-  const int x1 = S.x1, y1 = S.y1;
-  const int alpha = S.quality;
-  uint16_t* __restrict__ map = S.map;
-  const CsRay* __restrict__ rays = S.rays;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const long long t_begin = S.ring_cycles ? clock64() : 0;
-
-  for (int base = 0; base < n; base += CS_INT_CHUNK) {
-    const int cn = min(CS_INT_CHUNK, n - base);
-    __syncthreads();
-    {
-      // 256 rays * 32 B, two 16-byte loads per thread
-      const int4* src = reinterpret_cast<const int4*>(rays + base);
-      int4* dst = reinterpret_cast<int4*>(s_rays);
-      for (int i = threadIdx.x; i < cn * 2; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    if (k > max_ring) continue;
-
-    for (int b = 0; b < cn; b += 32) {
-      const int ri = b + lane;
-      bool active = false;
-      uint32_t cell = 0;
-      int pixval = 0;
-      if (ri < cn) {
-        const CsRay r = s_rays[ri];
-        if ((r.flags & 1) && k <= r.dxc) {
-          int m = cs_ray_minor(r, k);
-          int dmaj = (r.flags & 4) ? -k : k;
-          int dmin = (r.flags & 8) ? -m : m;
-          int x = (r.flags & 2) ? x1 + dmin : x1 + dmaj;
-          int y = (r.flags & 2) ? y1 + dmaj : y1 + dmin;
-          if ((unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size) {
-            active = true;
-            cell = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
-            pixval = cs_ray_pixval(r, k);
-          }
-        }
-      }
-      const unsigned am = __ballot_sync(0xffffffffu, active);
-      if (am == 0) continue;
-      unsigned peers = 0;
-      if (active) peers = __match_any_sync(am, cell);
-      const bool leader = active && ((peers & lt_mask) == 0);
-      const int cnt = __popc(peers);
-      const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-      int v = 0;
-      if (leader) v = (int)__ldcg(map + cell);
-      if (maxcnt == 1) {
-        if (leader) v = cs_blend(v, pixval, alpha);
-      } else {
-        // ordered application inside each same-cell group: the leader pulls its peers' pixvals in
-        // lane order (= ray order)
-        unsigned rest = peers;
-        for (int t = 0; t < maxcnt; t++) {
-          int src = lane;
-          if (leader && rest) {
-            src = __ffs(rest) - 1;
-            rest &= rest - 1;
-          } else if (leader) {
-            src = -1;
-          }
-          int pv = __shfl_sync(0xffffffffu, pixval, src < 0 ? lane : src);
-          if (leader && src >= 0) v = cs_blend(v, pv, alpha);
-        }
-      }
-      if (leader) __stcg(map + cell, (uint16_t)v);
-      __syncwarp();
+struct CsBlendState {
+  int val, last_pv;
+  bool fixed;  // val is a fixed point of blending with last_pv: more of the same changes nothing (exact)
+  __device__ __forceinline__ void apply(int pv, int alpha) {
+    if (fixed && pv == last_pv) return;
+    const int nv = cs_blend(val, pv, alpha);
+    fixed = (nv == val);
+    last_pv = pv;
+    val = nv;
+  }
+  __device__ __forceinline__ void apply_n(int pv, int cnt, int alpha) {
+    while (cnt-- > 0 && !(fixed && pv == last_pv)) {
+      const int nv = cs_blend(val, pv, alpha);
+      fixed = (nv == val);
+      last_pv = pv;
+      val = nv;
     }
   }
-  if (S.ring_cycles && lane == 0 && k <= max_ring) S.ring_cycles[k] = clock64() - t_begin;
+};
+
+template <bool TILED>
+__global__ void __launch_bounds__(CS_RING_MAX_WARPS * 32)
+cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  extern __shared__ int cs_ring_smem[];  // blockDim.x/32 * CS_RING_SMEM_PER_WARP bytes
+  // per 32-ray batch of the round: x = active-lane mask, y = position and z = pixval of its first active
+  // lane, w = 1 when every active lane of the batch has that same position and pixval
+  __shared__ int4 s_batch[CS_RING_MAX_WARPS * CS_RING_B];
+
+  const long long t_begin = a.diag ? clock64() : 0;
+#define CS_STAMP(i) do { if (a.diag && threadIdx.x == 0) a.diag[(size_t)blockIdx.x * 8 + (i)] = clock64() - t_begin; } while (0)
+  const int sj = blockIdx.y;
+  CsSession& S = sessions[sj];
+  const int k = blockIdx.x;  // this block's ring
+  if (k > S.max_ring) return;
+  const int n = a.hdr[sj].n_points;
+  const int size = S.size, pitch_tiles = S.pitch_tiles;
+  const float scale = S.scale;
+  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(S.cur_pose[0], scale), 0.5f));  // :499, :505
+  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(S.cur_pose[1], scale), 0.5f));  // :500, :506
+  const int alpha = S.quality;
+  uint16_t* __restrict__ map = S.map;
+  const int4* __restrict__ rays = S.rays;
+  const int* __restrict__ batch_max = S.batch_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = blockDim.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int round_entries = W * CS_RING_GROUP;
+  const int tsize = 2 * round_entries;  // power of two (W is 1, 2, 4 or 8)
+  int* s_pos = cs_ring_smem;
+  int* s_pix = s_pos + round_entries;
+  int* s_keys = s_pix + round_entries;                             // slot -> ring position
+  volatile int* s_val = s_keys + tsize;                            // slot -> value handed from batch to batch
+  volatile int* s_seq = s_keys + 2 * tsize;                        // slot -> 1 + last batch that has been applied
+  unsigned* s_mask = reinterpret_cast<unsigned*>(s_keys + 3 * tsize);  // slot -> batches touching it (CS_RING_UW words)
+  CS_STAMP(4);
+
+  for (int round0 = 0; round0 < n; round0 += round_entries) {
+    const int g0 = round0 + warp * CS_RING_GROUP;
+    const int e0 = warp * CS_RING_GROUP;  // this warp's first entry in the round arrays
+    // the table is cleared while the rays are evaluated
+    for (int i = threadIdx.x; i < tsize; i += blockDim.x) {
+      s_keys[i] = CS_POS_NONE;
+      s_seq[i] = 0;
+#pragma unroll
+      for (int u = 0; u < CS_RING_UW; u++) s_mask[i * CS_RING_UW + u] = 0u;
+    }
+
+    // ---- every lane evaluates its eight rays at step k ---------------------------------------------------
+    uint32_t cell[CS_RING_B];
+    int pos[CS_RING_B];
+    unsigned peers[CS_RING_B];  // lanes of the same batch on the same cell (this lane included), 0: not on the ring
+    CS_STAMP(5);
+    // batches none of whose rays reaches this ring are skipped; the others' rays are all requested up front
+    int4 q[CS_RING_B];
+    unsigned live = 0;  // bit j: batch j has a ray on this ring
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {
+      const int b = (g0 >> 5) + j;
+      q[j] = make_int4(0, 0, 0, 0);
+      if (b * 32 < n && __ldg(batch_max + b) >= k) {
+        live |= 1u << j;
+        const int ri = g0 + j * 32 + lane;
+        if (ri < n) q[j] = __ldg(rays + ri);
+      }
+    }
+    CS_STAMP(6);
+    int pixv[CS_RING_B];
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {  // per-lane arithmetic only, so the eight rays interleave
+      cell[j] = 0; pos[j] = CS_POS_NONE; pixv[j] = 0;
+      const CsRay r = cs_unpack_ray(q[j]);
+      if ((r.flags & 1) && k <= r.dxc) {
+        const int m = cs_ray_minor(r, k);
+        const int dmaj = (r.flags & 4) ? -k : k;
+        const int dmin = (r.flags & 8) ? -m : m;
+        const int ox = (r.flags & 2) ? dmin : dmaj;
+        const int oy = (r.flags & 2) ? dmaj : dmin;
+        const int x = x1 + ox, y = y1 + oy;
+        if ((unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size) {
+          cell[j] = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
+          pixv[j] = cs_ray_pixval(r, k);
+          pos[j] = cs_ring_pos(ox, oy, k);
+        }
+      }
+    }
+    CS_STAMP(7);
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {  // warp-wide: batch summary and same-cell groups
+      peers[j] = 0;
+      int4 bi = make_int4(0, CS_POS_NONE, 0, 0);
+      if ((live >> j) & 1u) {  // warp-uniform
+        const bool active = pos[j] != CS_POS_NONE;
+        s_pix[e0 + j * 32 + lane] = pixv[j];
+        const unsigned actm = __ballot_sync(0xffffffffu, active);
+        bi.x = (int)actm;
+        if (actm) {
+          const int fl = __ffs(actm) - 1;
+          bi.y = __shfl_sync(0xffffffffu, pos[j], fl);
+          bi.z = __shfl_sync(0xffffffffu, pixv[j], fl);
+          const bool same_pos = __all_sync(0xffffffffu, !active || pos[j] == bi.y);
+          bi.w = (same_pos && __all_sync(0xffffffffu, !active || pixv[j] == bi.z)) ? 1 : 0;
+          if (active) peers[j] = same_pos ? actm : __match_any_sync(actm, pos[j]);
+        }
+      }
+      if (lane == 0) s_batch[warp * CS_RING_B + j] = bi;
+    }
+    CS_STAMP(1);
+    __syncthreads();
+
+    // ---- the first lane of every same-cell group enters the cell into the table with its batch number ----
+    int slot[CS_RING_B];
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {
+      slot[j] = -1;
+      if (peers[j] && (peers[j] & lt_mask) == 0) {
+        unsigned sl = (((unsigned)pos[j] * 2654435761u) >> 8) & (unsigned)(tsize - 1);
+        for (;;) {
+          const int old = atomicCAS(&s_keys[sl], CS_POS_NONE, pos[j]);
+          if (old == CS_POS_NONE || old == pos[j]) break;
+          sl = (sl + 1) & (unsigned)(tsize - 1);
+        }
+        slot[j] = (int)sl;
+        const int unit = warp * CS_RING_B + j;
+        atomicOr(&s_mask[sl * CS_RING_UW + (unit >> 5)], 1u << (unit & 31));
+      }
+    }
+    CS_STAMP(2);
+    __syncthreads();
+
+    // ---- per cell, the batches that touch it are applied in ascending (= ray) order: the first one loads the
+    // cell, each one applies its lanes in lane order and hands the value on through shared memory, the last
+    // one stores.  A batch only ever waits for batches of lower number, which are earlier in this warp's
+    // program order or belong to a lower warp, so the waits always resolve. ----------------------------------
+    int pred[CS_RING_B];   // batch to wait for (-1: this batch opens the cell)
+    bool last[CS_RING_B];  // this batch closes the cell
+    int v[CS_RING_B];
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {
+      pred[j] = -1; last[j] = false; v[j] = 0;
+      if (slot[j] >= 0) {
+        const int unit = warp * CS_RING_B + j;
+        bool later = false;
+#pragma unroll
+        for (int u = 0; u < CS_RING_UW; u++) {
+          const unsigned um = s_mask[slot[j] * CS_RING_UW + u];
+          const int base_u = u * 32;
+          unsigned below = um, above = um;
+          if (unit < base_u) below = 0;
+          else if (unit < base_u + 32) below = um & ((1u << (unit - base_u)) - 1u);
+          if (unit >= base_u + 32) above = 0;
+          else if (unit >= base_u) above = um & ~((2u << (unit - base_u)) - 1u);
+          if (below) pred[j] = base_u + 31 - __clz(below);
+          later = later || (above != 0);
+        }
+        last[j] = !later;
+        if (pred[j] < 0) v[j] = (int)__ldcg(map + cell[j]);  // all opening loads are issued before anything waits
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CS_RING_B; j++) {
+      if (slot[j] >= 0) {
+        CsBlendState st;
+        st.last_pv = -1; st.fixed = false;
+        if (pred[j] >= 0) {
+          while (s_seq[slot[j]] != pred[j] + 1) { }
+          __threadfence_block();
+          st.val = s_val[slot[j]];
+        } else {
+          st.val = v[j];
+        }
+        const int4 bi = s_batch[warp * CS_RING_B + j];
+        if (bi.w) {
+          st.apply_n(bi.z, __popc(peers[j]), alpha);  // the whole batch sits on this cell with one pixval
+        } else {
+          unsigned pm = peers[j];
+          while (pm) {
+            const int l = __ffs(pm) - 1;
+            pm &= pm - 1;
+            st.apply(s_pix[e0 + j * 32 + l], alpha);
+          }
+        }
+        if (last[j]) {
+          __stcg(map + cell[j], (uint16_t)st.val);
+        } else {
+          s_val[slot[j]] = st.val;
+          __threadfence_block();
+          s_seq[slot[j]] = warp * CS_RING_B + j + 1;
+        }
+      }
+    }
+    CS_STAMP(3);
+    if (round0 + round_entries < n) __syncthreads();  // rounds are ordered; the shared arrays are reused
+  }
+  CS_STAMP(0);
+#undef CS_STAMP
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -122,7 +122,7 @@ def test_search_philox_mode_matches_host_twin():
 # integration
 # ------------------------------------------------------------------------------------------------
 def test_integrate_kat_c():
-    p = _mk(32, 8.0, 1, 1)
+    p = _mk(32, 8.0, 1, 1, flags=N.FLAG_DEBUG_RAYS)
     pts = np.array([[2.0, 0.0]], dtype=np.float32)
     v = p.integrate(pts, [4.0, 4.0, 0.0])
     # default HoleWidth is 0.6; KAT-C uses 2.4
@@ -147,7 +147,7 @@ def test_integrate_kat_c():
 def test_integrate_map_bit_exact(flags, size, n_rays, hw, q):
     rng = np.random.default_rng(size + n_rays)
     phys = 8.0
-    p = _mk(size, phys, 1, 1, flags=flags, max_points=n_rays)
+    p = _mk(size, phys, 1, 1, flags=flags | N.FLAG_DEBUG_RAYS, max_points=n_rays)
     p.set_hole_width(hw)
     p.set_quality(q)
     m = orc.HoleMap(size, phys)

@@ -14,8 +14,9 @@ for k in range(12):
     p.sync()
     t = p.timing()
     rc = p.ring_cycles()
-    nz = np.nonzero(rc)[0]
-    print("scan %d search %.1fus fin %.1fus integ %.1fus visits %d rings %d max_cycles %d at ring %d; ring0 %d ring1 %d ring10 %d ring100 %d ring500 %d median %d" % (
-        k, t.search_ms*1e3, t.finalize_ms*1e3, t.integrate_ms*1e3, r.visits, len(nz), rc.max(), rc.argmax(), rc[0], rc[1], rc[10], rc[100], rc[500], np.median(rc[nz])))
-top = np.argsort(-rc)[:12]
-print("slowest rings:", [(int(i), int(rc[i])) for i in top])
+    tot = rc[:, 0]
+    nz = np.nonzero(tot)[0]
+    print("scan %d search %.1fus rings-kernel %.1fus visits %d rings %d max %d at ring %d median %d" % (
+        k, t.search_ms * 1e3, t.integrate_ms * 1e3, p.visits(), len(nz), tot.max(), tot.argmax(), np.median(tot[nz])))
+for ring in (0, 1, 2, 5, 10, 30, 100, 200, 300, 500, 800):
+    print("ring %4d: total %7d  sess-loads %d clear %d ray-loads %d compute %d collect %d table %d apply %d" % (ring, rc[ring, 0], rc[ring, 4], rc[ring, 5], rc[ring, 6], rc[ring, 7], rc[ring, 1], rc[ring, 2], rc[ring, 3]))
