@@ -1,0 +1,131 @@
+// CoreSLAMProcessor.B200.cs — drop-in for CoreSLAM/CoreSLAMProcessor.cs with the search and the HoleMap
+// integration running on a B200 through libcoreslam_b200.  Public surface identical to the reference
+// (ctor :119-120, Reset :167, Update :717, Dispose :757, properties :40-106); ObstacleMap handling is
+// unchanged C# and omitted here for brevity.  NOT COMPILED IN THIS REPOSITORY (no .NET SDK in the image).
+using System;
+using System.Collections.Generic;
+using System.Linq;
+using System.Numerics;
+using BaseSLAM;
+
+namespace CoreSLAM.B200
+{
+    public sealed unsafe class HoleMap
+    {
+        private readonly IntPtr handle;
+        internal HoleMap(IntPtr handle, int sizePixels, float sizeMeters)
+        {
+            this.handle = handle;
+            Size = sizePixels;
+            Scale = sizePixels / sizeMeters;                 // HoleMap.cs:20
+            Pixels = new ushort[sizePixels * sizePixels];    // host copy, refreshed by SyncToHost()
+        }
+        public readonly ushort[] Pixels;                      // HoleMap.cs:27 (public field, kept)
+        public int Size { get; }
+        public float Scale { get; }
+
+        /// Pull the device-resident map into Pixels (waits for the pending integration).
+        public void SyncToHost()
+        {
+            fixed (ushort* p = Pixels) Native.Check(Native.cs_map_download(handle, p), handle);
+        }
+
+        public byte[] GetPackedPixels()                       // HoleMap.cs:44-55, packed on the device
+        {
+            var packed = new byte[Pixels.Length / 2];
+            fixed (byte* p = packed) Native.Check(Native.cs_map_packed(handle, p), handle);
+            return packed;
+        }
+    }
+
+    public sealed unsafe class CoreSLAMProcessor : IDisposable
+    {
+        private IntPtr handle;
+        private readonly IntPtr staging;      // pinned float2[maxPoints]: ScanSegmentsToCloud writes here in place
+        private readonly int maxPoints;
+        private byte quality = 50;
+        private float holeWidth = 0.6f;
+        private int positionSearchBeginning = 5;
+
+        public float PhysicalMapSize { get; }
+        public HoleMap HoleMap { get; }
+        public float SigmaXY { get; }
+        public float SigmaTheta { get; }
+        public int SearchIterationsPerThread { get; }
+        public int NumSearchThreads { get; }
+        public Vector3 Pose { get; private set; }
+        /// true: HoleMap.Pixels is refreshed after every Update (reference semantics, costs a D2H copy)
+        public bool SyncMapAfterUpdate { get; set; } = false;
+
+        public byte Quality { get => quality; set { Native.Check(Native.cs_set_quality(handle, value), handle); quality = value; } }
+        public float HoleWidth { get => holeWidth; set { Native.Check(Native.cs_set_hole_width(handle, value), handle); holeWidth = value; } }
+        public int PositionSearchBeginning
+        {
+            get => positionSearchBeginning;
+            set { Native.Check(Native.cs_set_position_search_beginning(handle, value), handle); positionSearchBeginning = value; }
+        }
+
+        public CoreSLAMProcessor(float physicalMapSize, int holeMapSize, int obstacleMapSize, Vector3 startPose,
+            float sigmaXY, float sigmaTheta, int iterationsPerThread, int numSearchThreads,
+            int device = 0, ulong seed = 0x5EED, int maxPoints = 16384)
+        {
+            PhysicalMapSize = physicalMapSize; SigmaXY = sigmaXY; SigmaTheta = sigmaTheta;
+            SearchIterationsPerThread = iterationsPerThread; NumSearchThreads = numSearchThreads;
+            this.maxPoints = maxPoints;
+            var cfg = new CsConfig
+            {
+                PhysicalMapSize = physicalMapSize, HoleMapSize = holeMapSize, SigmaXY = sigmaXY, SigmaTheta = sigmaTheta,
+                IterationsPerThread = iterationsPerThread, NumSearchThreads = numSearchThreads,
+                Device = device, MaxPoints = maxPoints, Seed = seed
+            };
+            cfg.StartPose[0] = startPose.X; cfg.StartPose[1] = startPose.Y; cfg.StartPose[2] = startPose.Z;
+            Native.Check(Native.cs_create(ref cfg, out handle), IntPtr.Zero);
+            Native.Check(Native.cs_pinned_alloc(out staging, (ulong)maxPoints * 8), handle);
+            HoleMap = new HoleMap(handle, holeMapSize, physicalMapSize);
+            Pose = startPose;
+        }
+
+        public void Reset()
+        {
+            Native.Check(Native.cs_reset(handle), handle);
+            float* p = stackalloc float[3];
+            Native.Check(Native.cs_get_pose(handle, p), handle);
+            Pose = new Vector3(p[0], p[1], p[2]);
+        }
+
+        /// CoreSLAMProcessor.Update (:717-752).  ScanSegmentsToCloud (:187-207) stays here on the host and
+        /// writes straight into the pinned staging block; search + NormalizeAngle + HoleMap integration
+        /// run on the device.  Returns when the pose is known; the integration overlaps the caller.
+        public void Update(List<ScanSegment> segments)
+        {
+            Vector3 odoPose = segments.Last().Pose;
+            float* pts = (float*)staging;
+            int n = 0;
+            foreach (ScanSegment segment in segments)
+            {
+                Vector3 pose = segment.Pose - odoPose;
+                foreach (Ray r in segment.Rays)
+                {
+                    if (n >= maxPoints) throw new InvalidOperationException("scan larger than maxPoints");
+                    pts[2 * n] = pose.X + r.Radius * MathF.Cos(r.Angle + pose.Z);
+                    pts[2 * n + 1] = pose.Y + r.Radius * MathF.Sin(r.Angle + pose.Z);
+                    n++;
+                }
+            }
+            float* odo = stackalloc float[3] { odoPose.X, odoPose.Y, odoPose.Z };
+            Native.Check(Native.cs_update(handle, pts, n, odo, null, out CsResult res), handle);
+            Pose = new Vector3(res.Pose[0], res.Pose[1], res.Pose[2]);
+            if (SyncMapAfterUpdate) HoleMap.SyncToHost();
+            // UpdateObstacleMap(cloud) continues in C# exactly as in the reference (:751)
+        }
+
+        public void Dispose()
+        {
+            if (handle == IntPtr.Zero) return;
+            Native.cs_pinned_free(staging);
+            Native.cs_destroy(handle);
+            handle = IntPtr.Zero;
+            GC.SuppressFinalize(this);
+        }
+    }
+}

@@ -1,0 +1,82 @@
+// CoreSlamNative.cs — P/Invoke bindings for libcoreslam_b200 (include/coreslam_b200.h).
+// NOT COMPILED IN THIS REPOSITORY: the build image has no .NET SDK.  It is the binding a SLAM.NET
+// maintainer adds to CoreSLAM/CoreSLAM.csproj; struct layouts mirror the C header field for field.
+using System;
+using System.Runtime.InteropServices;
+
+namespace CoreSLAM.B200
+{
+    public enum CsStatus : int
+    {
+        Ok = 0, InvalidArgument = 1, NoDevice = 2, Cuda = 3, OutOfMemory = 4, Capacity = 5, State = 6, Nccl = 7
+    }
+
+    [Flags]
+    public enum CsFlags : uint
+    {
+        None = 0, RowMajorMap = 0x1, Timing = 0x2, KeepDistances = 0x4, NoHostSpin = 0x8, L2Persist = 0x10, DebugRays = 0x20
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct CsConfig          // cs_config, 72 bytes
+    {
+        public float PhysicalMapSize;
+        public int HoleMapSize;
+        public fixed float StartPose[3];
+        public float SigmaXY;
+        public float SigmaTheta;
+        public int IterationsPerThread;
+        public int NumSearchThreads;
+        public int Device;
+        public int MaxPoints;
+        public ulong Seed;
+        public IntPtr Stream;
+        public uint Flags;
+        public uint Reserved;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct CsResult          // cs_result, 32 bytes
+    {
+        public fixed float Pose[3];
+        public int Distance;
+        public int Index;
+        public int Searched;
+        public long Visits;
+    }
+
+    internal static unsafe class Native
+    {
+        private const string Lib = "coreslam_b200";   // libcoreslam_b200.so / coreslam_b200.dll
+
+        [DllImport(Lib)] public static extern int cs_abi_version();
+        [DllImport(Lib)] public static extern IntPtr cs_last_error(IntPtr h);
+        [DllImport(Lib)] public static extern int cs_device_count();
+        [DllImport(Lib)] public static extern CsStatus cs_create(ref CsConfig cfg, out IntPtr handle);
+        [DllImport(Lib)] public static extern CsStatus cs_destroy(IntPtr h);
+        [DllImport(Lib)] public static extern CsStatus cs_reset(IntPtr h);
+        [DllImport(Lib)] public static extern CsStatus cs_set_quality(IntPtr h, int quality);
+        [DllImport(Lib)] public static extern CsStatus cs_set_hole_width(IntPtr h, float metres);
+        [DllImport(Lib)] public static extern CsStatus cs_set_position_search_beginning(IntPtr h, int scans);
+        [DllImport(Lib)] public static extern CsStatus cs_get_pose(IntPtr h, float* pose3);
+        [DllImport(Lib)] public static extern CsStatus cs_update(IntPtr h, float* pointsXY, int nPoints, float* odometryPose3,
+                                                                 float* candOffsets /* T*I*3 or null */, out CsResult result);
+        [DllImport(Lib)] public static extern CsStatus cs_search(IntPtr h, float* pointsXY, int nPoints, float* searchPose3,
+                                                                 float* candPoses, float* candCosSin, int nCand, uint scanIndex,
+                                                                 out CsResult best, int* distances);
+        [DllImport(Lib)] public static extern CsStatus cs_integrate(IntPtr h, float* pointsXY, int nPoints, float* pose3,
+                                                                    float* poseCosSin, long* visits);
+        [DllImport(Lib)] public static extern CsStatus cs_sync(IntPtr h);
+        [DllImport(Lib)] public static extern CsStatus cs_map_download(IntPtr h, ushort* pixels);
+        [DllImport(Lib)] public static extern CsStatus cs_map_upload(IntPtr h, ushort* pixels);
+        [DllImport(Lib)] public static extern CsStatus cs_map_packed(IntPtr h, byte* packed);
+        [DllImport(Lib)] public static extern CsStatus cs_pinned_alloc(out IntPtr ptr, ulong bytes);
+        [DllImport(Lib)] public static extern CsStatus cs_pinned_free(IntPtr ptr);
+
+        public static void Check(CsStatus st, IntPtr h)
+        {
+            if (st != CsStatus.Ok)
+                throw new InvalidOperationException($"{st}: {Marshal.PtrToStringAnsi(cs_last_error(h))}");
+        }
+    }
+}

@@ -56,6 +56,18 @@ def test_normalize_angle_matches_libm_fmodf():
     assert np.array_equal(tail.view(np.uint32), want[-10:].view(np.uint32))
 
 
+def test_host_sincos_all_2_32_inputs(tmp_path):
+    """Every float bit pattern (2^32) against the host libm — the claim DESIGN.md section 2 rests on."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "trig_exhaustive")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-include", "stdlib.h", "-o", exe,
+                           os.path.join(root, "tests", "ctools_trig_exhaustive.c"), "-lm", "-lpthread"])
+    out = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "mismatches 0 " in out.stdout, out.stdout + out.stderr
+
+
 @pytest.mark.gpu
 def test_device_sincos_matches_libm():
     import ctypes as C
