@@ -132,6 +132,20 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
 cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
                     const float* cand_offsets, cs_result* out);
 
+/* Multi-GPU candidate split (very large candidate sets, BASELINE cfg4): the map is replicated, GPU g
+ * evaluates the flat candidate indices [cand_first, cand_first + cand_count) of the same scan, and ONE
+ * 8-byte exchange picks the winner: the packed key (uint32 distance << 32 | uint32 flat index) is
+ * min-reduced over the GPUs in place at *key_device between the two calls — on the handle's stream, e.g.
+ * ncclAllReduce(key, key, 1, ncclUint64, ncclMin, comm, stream) or torch.distributed.all_reduce(MIN) on an
+ * int64 view (the key is < 2^63).  cs_update_finish then decodes the same winner on every GPU, publishes
+ * the pose and integrates the scan into this GPU's replica (deterministic, so replicas stay identical
+ * without any map traffic).  In verification mode every GPU passes the full T*I offset table (the winner
+ * is looked up by flat index); in Philox mode (cand_offsets = NULL) nothing is uploaded.
+ * Replaces the cross-thread arg-min of ParallelMonteCarloSearch (:694-705) at GPU granularity. */
+cs_status cs_update_begin(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                          const float* cand_offsets, int32_t cand_first, int32_t cand_count, uint64_t** key_device);
+cs_status cs_update_finish(cs_processor* h, cs_result* out);
+
 /* Wait until everything enqueued on the handle (including the last integration) has finished. */
 cs_status cs_sync(cs_processor* h);
 
@@ -168,6 +182,28 @@ cs_status cs_scanlog_upload(cs_scanlog* log);
 cs_status cs_scanlog_destroy(cs_scanlog* log);
 /* Runs Update for scans [first, first+count) back to back on the device; results[count] optional. */
 cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);
+
+/* ---- batches of independent sessions on one GPU (parameter sweeps / scan-log replays, BASELINE cfg5) ----
+ * One launch per kernel for all sessions (grid.y = session); every session has its own HoleMap, pose,
+ * sigma_xy / sigma_theta / seed / start_pose (cfgs[j]), Quality and HoleWidth.  Map size, iterations,
+ * threads, device, max_points and flags must be equal across cfgs.  No communication between sessions. */
+cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** out);
+cs_status cs_batch_destroy(cs_batch* b);
+const char* cs_batch_last_error(const cs_batch* b);
+int32_t cs_batch_size(const cs_batch* b);
+cs_status cs_batch_set_params(cs_batch* b, int32_t session /* <0: all */, int32_t quality, float hole_width);
+/* Update for every session: points n_sessions*max_points*(x,y) (session j uses n_points[j]), odometry
+ * n_sessions*3, cand_offsets n_sessions*T*I*3 or NULL (Philox), results optional n_sessions records. */
+cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
+                          const float* cand_offsets, cs_result* results);
+/* Every session replays scans [first, first+count) of one shared device-resident log; results: optional
+ * n_sessions records of the last scan. */
+cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);
+cs_status cs_batch_sync(cs_batch* b);
+cs_status cs_batch_get_poses(cs_batch* b, float* poses /* n_sessions*3 */);
+cs_status cs_batch_map_download(cs_batch* b, int32_t session, uint16_t* pixels);
+cs_status cs_batch_map_checksums(cs_batch* b, uint64_t* checksums /* n_sessions */);
+cs_status cs_batch_get_launch_count(cs_batch* b, uint64_t* launches);
 
 /* ---- host twins of the device generators (for building verification tables; not a compute path) ----- */
 /* offsets[n*3] = the Philox deviates the device uses for candidates 0..n-1 of scan `scan_index`. */

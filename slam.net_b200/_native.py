@@ -123,6 +123,8 @@ SIGNATURES = {
     "cs_search": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_uint32, C.POINTER(Result), _ip]),
     "cs_integrate": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(C.c_int64)]),
     "cs_update": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(Result)]),
+    "cs_update_begin": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cs_update_finish": (C.c_int, [_vp, C.POINTER(Result)]),
     "cs_sync": (C.c_int, [_vp]),
     "cs_map_download": (C.c_int, [_vp, _vp]),
     "cs_map_upload": (C.c_int, [_vp, _vp]),
@@ -144,6 +146,18 @@ SIGNATURES = {
     "cs_scanlog_upload": (C.c_int, [_vp]),
     "cs_scanlog_destroy": (C.c_int, [_vp]),
     "cs_replay": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(Result)]),
+    "cs_batch_create": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(_vp)]),
+    "cs_batch_destroy": (C.c_int, [_vp]),
+    "cs_batch_last_error": (C.c_char_p, [_vp]),
+    "cs_batch_size": (C.c_int32, [_vp]),
+    "cs_batch_set_params": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_float]),
+    "cs_batch_update": (C.c_int, [_vp, _fp, _ip, _fp, _fp, C.POINTER(Result)]),
+    "cs_batch_replay": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(Result)]),
+    "cs_batch_sync": (C.c_int, [_vp]),
+    "cs_batch_get_poses": (C.c_int, [_vp, _fp]),
+    "cs_batch_map_download": (C.c_int, [_vp, C.c_int32, _vp]),
+    "cs_batch_map_checksums": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
+    "cs_batch_get_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_philox_offsets": (None, [C.c_uint64, C.c_uint32, C.c_int32, C.c_float, C.c_float, _fp]),
     "cs_host_sincos": (None, [_fp, C.c_int32, _fp, _fp]),
     "cs_device_sincos": (C.c_int, [C.c_int32, _fp, C.c_int32, _fp, _fp]),
@@ -177,7 +191,7 @@ class CoreSlamError(RuntimeError):
         self.status = status
 
 
-def check(status: int, handle=None):
+def check(status: int, handle=None, batch=None):
     if status != 0:
-        msg = lib().cs_last_error(handle)
+        msg = lib().cs_batch_last_error(batch) if batch is not None else lib().cs_last_error(handle)
         raise CoreSlamError(status, msg.decode() if msg else "")

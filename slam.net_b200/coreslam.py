@@ -236,6 +236,25 @@ class Processor:
         self._ck(N.lib().cs_update(self._h, _ptr(pts), pts.shape[0], _ptr(_f32(odometry_pose)), _ptr(off), C.byref(r)))
         return _result(r)
 
+    # -- multi-GPU candidate split (cs_update_begin / cs_update_finish) -----------------------------
+    def update_begin(self, points, odometry_pose, cand_offsets, cand_first: int, cand_count: int) -> int:
+        """Launches the search over flat candidate indices [cand_first, cand_first+cand_count) and returns
+        the DEVICE address of the 8-byte packed arg-min to be min-reduced over the GPUs before
+        update_finish()."""
+        pts = _f32(points).reshape(-1, 2)
+        off = None if cand_offsets is None else _f32(cand_offsets).reshape(-1, 3)
+        if off is not None and off.shape[0] != self.n_cand:
+            raise ValueError("cand_offsets needs T*I = %d rows (the full table on every GPU)" % self.n_cand)
+        key = C.c_void_p()
+        self._ck(N.lib().cs_update_begin(self._h, _ptr(pts), pts.shape[0], _ptr(_f32(odometry_pose)), _ptr(off),
+                                         int(cand_first), int(cand_count), C.byref(key)))
+        return int(key.value or 0)
+
+    def update_finish(self) -> SearchResult:
+        r = N.Result()
+        self._ck(N.lib().cs_update_finish(self._h, C.byref(r)))
+        return _result(r)
+
     def replay(self, log: ScanLog, first: int = 0, count: Optional[int] = None, want_results=True):
         count = log.n_scans - first if count is None else count
         res = (N.Result * count)() if want_results else None
@@ -302,6 +321,101 @@ class Processor:
     def launch_count(self) -> int:
         v = C.c_uint64()
         self._ck(N.lib().cs_get_launch_count(self._h, C.byref(v)))
+        return int(v.value)
+
+
+class Batch:
+    """N independent sessions on one GPU (cs_batch_*): a parameter sweep / many replays advanced in
+    lockstep, one kernel launch per stage for all of them."""
+
+    def __init__(self, n_sessions: int, physical_map_size: float, hole_map_size: int, start_poses, sigma_xy, sigma_theta,
+                 iterations_per_thread: int, num_search_threads: int, *, device: int = 0, max_points: int = 0,
+                 seeds=None, stream: int = 0, flags: int = 0):
+        cfgs = (N.Config * n_sessions)()
+        start_poses = np.broadcast_to(_f32(start_poses), (n_sessions, 3))
+        sxy = np.broadcast_to(np.asarray(sigma_xy, dtype=np.float32), (n_sessions,))
+        sth = np.broadcast_to(np.asarray(sigma_theta, dtype=np.float32), (n_sessions,))
+        seeds = np.arange(n_sessions, dtype=np.uint64) if seeds is None else np.asarray(seeds, dtype=np.uint64)
+        for j in range(n_sessions):
+            c = cfgs[j]
+            c.physical_map_size = physical_map_size
+            c.hole_map_size = hole_map_size
+            c.start_pose = (C.c_float * 3)(*[float(v) for v in start_poses[j]])
+            c.sigma_xy = float(sxy[j])
+            c.sigma_theta = float(sth[j])
+            c.iterations_per_thread = iterations_per_thread
+            c.num_search_threads = num_search_threads
+            c.device = device
+            c.max_points = max_points
+            c.seed = int(seeds[j])
+            c.stream = stream or None
+            c.flags = flags
+        self._h = C.c_void_p()
+        N.check(N.lib().cs_batch_create(cfgs, n_sessions, C.byref(self._h)))
+        self.n = n_sessions
+        self.size = hole_map_size
+        self.n_cand = max(num_search_threads, 1) * iterations_per_thread
+        self.max_points = ((max_points if max_points > 0 else 16384) + 1) & ~1
+        self.seeds, self.sigma_xy, self.sigma_theta = seeds, sxy, sth
+
+    def _ck(self, status):
+        N.check(status, batch=self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            N.lib().cs_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, session: int, quality: int, hole_width: float):
+        self._ck(N.lib().cs_batch_set_params(self._h, int(session), int(quality), float(hole_width)))
+
+    def update(self, points: Sequence[np.ndarray], odometry, cand_offsets=None, want_results=True):
+        """points: one (P_j, 2) array per session; odometry (n, 3); cand_offsets (n, T*I, 3) or None."""
+        buf = np.zeros((self.n, self.max_points, 2), dtype=np.float32)
+        npts = np.zeros(self.n, dtype=np.int32)
+        for j, p in enumerate(points):
+            p = _f32(p).reshape(-1, 2)
+            buf[j, :p.shape[0]] = p
+            npts[j] = p.shape[0]
+        odo = _f32(odometry).reshape(self.n, 3)
+        off = None if cand_offsets is None else _f32(cand_offsets).reshape(self.n, self.n_cand, 3)
+        res = (N.Result * self.n)() if want_results else None
+        self._ck(N.lib().cs_batch_update(self._h, _ptr(buf), npts.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(odo), _ptr(off), res))
+        return [_result(r) for r in res] if want_results else None
+
+    def replay(self, log: ScanLog, first: int = 0, count: Optional[int] = None, want_results=True):
+        count = log.n_scans - first if count is None else count
+        res = (N.Result * self.n)() if want_results else None
+        self._ck(N.lib().cs_batch_replay(self._h, log._h, first, count, res))
+        return [_result(r) for r in res] if want_results else None
+
+    def sync(self):
+        self._ck(N.lib().cs_batch_sync(self._h))
+
+    def poses(self) -> np.ndarray:
+        out = np.zeros((self.n, 3), dtype=np.float32)
+        self._ck(N.lib().cs_batch_get_poses(self._h, _ptr(out)))
+        return out
+
+    def map_download(self, session: int) -> np.ndarray:
+        px = np.empty(self.size * self.size, dtype=np.uint16)
+        self._ck(N.lib().cs_batch_map_download(self._h, int(session), px.ctypes.data))
+        return px
+
+    def map_checksums(self) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.uint64)
+        self._ck(N.lib().cs_batch_map_checksums(self._h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
+    def launch_count(self) -> int:
+        v = C.c_uint64()
+        self._ck(N.lib().cs_batch_get_launch_count(self._h, C.byref(v)))
         return int(v.value)
 
 

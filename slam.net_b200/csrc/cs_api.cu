@@ -77,6 +77,11 @@ struct cs_processor {
   int search_begin = 5;
   unsigned update_count = 0;  // Philox scan index
 
+  // split-phase update in flight (cs_update_begin ... cs_update_finish)
+  bool pending = false;
+  CsStepArgs pending_args{};
+  int pending_points = 0, pending_rings = 0;
+
   uint64_t launches = 0;
   Timing tm;
   cs_timing last_timing{};
@@ -169,12 +174,13 @@ StagePlan plan_stage(int n_points, int n_cand_floats3, bool with_cs) {
 }
 
 // Upper bound on the ring count of a scan: |rotated, scaled point| + half the hole width, plus rounding slack.
-int rings_hint(const cs_processor* h, double max_range) {
-  if (!(max_range == max_range) || max_range > 1e30) return h->size;
-  double cells = max_range * (double)h->scale * 1.00001 + 0.5 * (double)h->hs.hole_width * (double)h->scale + 4.0;
-  if (cells >= (double)h->size) return h->size;
+int rings_hint_of(int size, float scale, float hole_width, double max_range) {
+  if (!(max_range == max_range) || max_range > 1e30) return size;
+  double cells = max_range * (double)scale * 1.00001 + 0.5 * (double)hole_width * (double)scale + 4.0;
+  if (cells >= (double)size) return size;
   return (int)cells + 1;
 }
+int rings_hint(const cs_processor* h, double max_range) { return rings_hint_of(h->size, h->scale, h->hs.hole_width, max_range); }
 
 double max_range_of(const float* points, int n) {
   double m = 0.0;
@@ -186,50 +192,85 @@ double max_range_of(const float* points, int n) {
   return std::sqrt(m);
 }
 
-// One step on the handle's stream: [search kernel, whose last block publishes the pose and prepares the
-// rays] or [set-up kernel] -> (big scans: multi-block ray preparation) -> rings kernel.
-cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base) {
+// What a step is launched on: one processor (n_sessions = 1) or a batch of independent sessions
+// (grid.y = n_sessions; every kernel indexes its session by blockIdx.y).
+struct LaunchCtx {
+  cudaStream_t stream;
+  CsSession* d_sess;
+  bool tiled;
+  int n_sessions;
+  uint64_t* launches;
+  long long* diag;
+  cudaEvent_t ev_pose;   // optional: recorded once the pose is out
+  cudaEvent_t ev_done;   // optional: recorded after the rings kernel
+};
+
+enum { CS_PHASE_SEARCH = 1, CS_PHASE_FINISH = 2, CS_PHASE_ALL = 3 };
+
+// One step on the stream: [search kernel, whose last block publishes the pose and prepares the rays] or
+// [set-up kernel] -> (big scans: multi-block ray preparation) -> rings kernel.  Split phases (multi-GPU
+// candidate split): SEARCH launches only the search over this GPU's candidate slice and leaves the packed
+// arg-min in CsSession::key[parity]; FINISH — after the caller's 8-byte min exchange — launches the set-up
+// kernel (which decodes the reduced key) and the rings kernel.
+cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int rings, int phases) {
   const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
   const bool draws = a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0;
   const bool big = n_points > CS_FUSE_RAYS_MAX;
-  a.fuse_publish = 1;
+  const bool fused = searching && phases == CS_PHASE_ALL;
+  a.fuse_publish = fused ? 1 : 0;
   a.fuse_rays = (draws && !big) ? 1 : 0;
   a.rays_only = 0;
   a.max_ring_hint = rings - 1;
-  a.diag = h->d_ring_cycles;
-  if (searching) {
-    dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), 1);
-    dispatch_layout(h->tiled, [&](auto T) {
-      cs_search_kernel<decltype(T)::value><<<grid, CS_SEARCH_WARPS * 32, 0, h->stream>>>(h->d_sess, a);
+  a.diag = c.diag;
+  if ((phases & CS_PHASE_SEARCH) && searching) {
+    dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), (unsigned)c.n_sessions);
+    dispatch_layout(c.tiled, [&](auto T) {
+      cs_search_kernel<decltype(T)::value><<<grid, CS_SEARCH_WARPS * 32, 0, c.stream>>>(c.d_sess, a);
     });
-  } else {
-    cs_setup_kernel<<<dim3(1, 1), CS_SETUP_THREADS, 0, h->stream>>>(h->d_sess, a);
+    (*c.launches)++;
   }
-  h->launches++;
+  if (!(phases & CS_PHASE_FINISH)) return cudaGetLastError();
+  if (!fused) {
+    cs_setup_kernel<<<dim3(1, (unsigned)c.n_sessions), CS_SETUP_THREADS, 0, c.stream>>>(c.d_sess, a);
+    (*c.launches)++;
+  }
   // the pose is out once this kernel has finished
-  if (timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN))) cudaEventRecord(h->tm.ev[ev_base + 0], h->stream);
+  if (c.ev_pose) cudaEventRecord(c.ev_pose, c.stream);
   if (draws) {
     if (big) {
       CsStepArgs b = a;
       b.rays_only = 1;
-      cs_setup_kernel<<<dim3((unsigned)((n_points + 1023) / 1024), 1), CS_SETUP_THREADS, 0, h->stream>>>(h->d_sess, b);
-      h->launches++;
+      cs_setup_kernel<<<dim3((unsigned)((n_points + 1023) / 1024), (unsigned)c.n_sessions), CS_SETUP_THREADS, 0, c.stream>>>(c.d_sess, b);
+      (*c.launches)++;
     }
     int warps = (n_points + CS_RING_GROUP - 1) / CS_RING_GROUP;
     if (warps < 1) warps = 1;
     if (warps > CS_RING_MAX_WARPS) warps = CS_RING_MAX_WARPS;
     while (warps & (warps - 1)) warps++;  // the kernel's table size must be a power of two
     if (rings < 1) rings = 1;
-    dispatch_layout(h->tiled, [&](auto T) {
-      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)rings, 1), warps * 32, (size_t)warps * CS_RING_SMEM_PER_WARP, h->stream>>>(h->d_sess, a);
+    dispatch_layout(c.tiled, [&](auto T) {
+      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)rings, (unsigned)c.n_sessions), warps * 32, (size_t)warps * CS_RING_SMEM_PER_WARP, c.stream>>>(c.d_sess, a);
     });
-    h->launches++;
+    (*c.launches)++;
   }
-  if (timing) {
-    cudaEventRecord(h->tm.ev[ev_base + 1], h->stream);
-    cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
-  }
-  CS_CUDA(h, cudaGetLastError());
+  if (c.ev_done) cudaEventRecord(c.ev_done, c.stream);
+  return cudaGetLastError();
+}
+
+cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base, int phases = CS_PHASE_ALL) {
+  LaunchCtx c{};
+  c.stream = h->stream;
+  c.d_sess = h->d_sess;
+  c.tiled = h->tiled;
+  c.n_sessions = 1;
+  c.launches = &h->launches;
+  c.diag = h->d_ring_cycles;
+  a.hdr_stride = 1;
+  const bool want_pose_event = timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN));
+  c.ev_pose = (want_pose_event && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 0] : nullptr;
+  c.ev_done = (timing && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 1] : nullptr;
+  CS_CUDA(h, launch_step_ctx(c, a, n_points, rings, phases));
+  if (c.ev_done) cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
   return CS_OK;
 }
 
@@ -609,13 +650,13 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
   return CS_OK;
 }
 
-cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
-                    const float* cand_offsets, cs_result* out) {
-  CS_CHECK_HANDLE(h);
+// Stages one scan and fills the step arguments of an Update; shared by cs_update and cs_update_begin.
+static cs_status stage_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                              const float* cand_offsets, bool timing, CsStepArgs* out_args) {
   if (!points || !odometry_pose || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
   if (!finite3(odometry_pose)) return fail(h, CS_ERR_INVALID_ARGUMENT, "odometry pose is NaN");
-  const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
+  if (h->pending) return fail(h, CS_ERR_STATE, "a split-phase update is in flight: call cs_update_finish first");
 
   // The previous call's integration may still be running: the pinned block is free again (its H2D copy
   // finished before that call's pose flag), the device block is protected by stream order.
@@ -648,13 +689,16 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
   a.n_cand = h->n_cand;
   a.cand_first = 0;
   a.cand_count = h->n_cand + 1;
-  cs_status st = launch_step(h, a, n_points, rings_hint(h, max_range_of(points, n_points)), timing, 2);
-  if (st != CS_OK) return st;
+  *out_args = a;
+  return CS_OK;
+}
+
+// Host-side bookkeeping after an Update has been enqueued, the wait for the pose, and the result copy.
+static cs_status complete_update(cs_processor* h, const CsStepArgs& a, bool timing, cs_result* out) {
   h->parity ^= 1;
   h->update_count++;
-  if (!do_search) h->scan_count++;  // :741
-
-  st = wait_for_pose(h, a.seq_value, h->tm.ev[2]);
+  if (!a.do_search) h->scan_count++;  // :741
+  cs_status st = wait_for_pose(h, a.seq_value, h->tm.ev[2]);
   if (st != CS_OK) return st;
   if (timing) {
     st = collect_timing(h, true);
@@ -672,6 +716,57 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
     }
   }
   return CS_OK;
+}
+
+cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                    const float* cand_offsets, cs_result* out) {
+  CS_CHECK_HANDLE(h);
+  const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
+  CsStepArgs a{};
+  cs_status st = stage_update(h, points, n_points, odometry_pose, cand_offsets, timing, &a);
+  if (st != CS_OK) return st;
+  st = launch_step(h, a, n_points, rings_hint(h, max_range_of(points, n_points)), timing, 2);
+  if (st != CS_OK) return st;
+  return complete_update(h, a, timing, out);
+}
+
+// ---- multi-GPU candidate split (BASELINE cfg4) ---------------------------------------------
+cs_status cs_update_begin(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
+                          const float* cand_offsets, int32_t cand_first, int32_t cand_count, uint64_t** key_device) {
+  CS_CHECK_HANDLE(h);
+  if (cand_first < 0 || cand_count < 0 || (long long)cand_first + cand_count > (long long)h->n_cand + 1)
+    return fail(h, CS_ERR_INVALID_ARGUMENT, "candidate slice [%d, %d) outside [0, T*I+1 = %d)", cand_first,
+                cand_first + cand_count, h->n_cand + 1);
+  CsStepArgs a{};
+  cs_status st = stage_update(h, points, n_points, odometry_pose, cand_offsets, false, &a);
+  if (st != CS_OK) return st;
+  a.cand_first = cand_first;
+  a.cand_count = cand_count;
+  const int rings = rings_hint(h, max_range_of(points, n_points));
+  if (cand_count > 0) {
+    st = launch_step(h, a, n_points, rings, false, 2, CS_PHASE_SEARCH);
+    if (st != CS_OK) return st;
+  }
+  h->pending = true;
+  h->pending_args = a;
+  h->pending_points = n_points;
+  h->pending_rings = rings;
+  if (key_device)  // NULL when this scan runs no search (:726): nothing to exchange
+    *key_device = (a.do_search && cand_count > 0)
+                      ? reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, key) +
+                                                    sizeof(unsigned long long) * (size_t)a.parity)
+                      : nullptr;
+  return CS_OK;
+}
+
+cs_status cs_update_finish(cs_processor* h, cs_result* out) {
+  CS_CHECK_HANDLE(h);
+  if (!h->pending) return fail(h, CS_ERR_STATE, "cs_update_finish without cs_update_begin");
+  h->pending = false;
+  const CsStepArgs a = h->pending_args;
+  cs_status st = launch_step(h, a, h->pending_points, h->pending_rings, false, 2, CS_PHASE_FINISH);
+  if (st != CS_OK) return st;
+  return complete_update(h, a, false, out);
 }
 
 cs_status cs_sync(cs_processor* h) {
@@ -953,6 +1048,407 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     h->last_timing = cs_timing{};
     h->last_timing.total_device_ms = ms;
   }
+  return CS_OK;
+}
+
+// =====================================================================================================
+// Batches of independent sessions on one GPU (SURVEY 8e "sessions", BASELINE cfg5): one launch per
+// kernel for all sessions (grid.y = session), every session with its own map, pose, parameters and
+// Philox stream.  No data-path communication between sessions or GPUs.
+// =====================================================================================================
+}  // extern "C"
+
+struct cs_batch {
+  int device = 0, n = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false, tiled = true;
+  int size = 0, pitch_tiles = 0, max_points = 0, n_cand = 0;
+  float scale = 0.f;
+  size_t map_cells = 0;
+  std::vector<CsSession> hs;
+  CsSession* d_sess = nullptr;
+  uint16_t* d_maps = nullptr;
+  uint16_t* d_linear = nullptr;
+  int4* d_rays = nullptr;
+  int* d_batch_max = nullptr;
+  unsigned long long* d_checksum = nullptr;
+  // staging: [n headers][n * max_points points][n * n_cand offsets]
+  size_t off_points = 0, off_cand = 0, stage_bytes = 0;
+  uint8_t* h_stage = nullptr;
+  uint8_t* d_stage = nullptr;
+  CsDevResult* d_results = nullptr;
+  CsDevResult* h_results = nullptr;  // pinned
+  int parity = 0, scan_count = 0, search_begin = 5;
+  unsigned update_count = 0;
+  uint64_t launches = 0;
+  std::string error;
+  bool poisoned = false;
+};
+
+namespace {
+cs_status bfail(cs_batch* b, cs_status code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (b) {
+    b->error = buf;
+    if (code == CS_ERR_CUDA) b->poisoned = true;
+  } else {
+    g_create_error = buf;
+  }
+  return code;
+}
+#define CS_BCUDA(b, expr)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return bfail((b), CS_ERR_CUDA, "%s failed: %s (line %d)", #expr, cudaGetErrorString(_e), __LINE__); \
+  } while (0)
+#define CS_CHECK_BATCH(b)                                                           \
+  do {                                                                              \
+    if (!(b)) return CS_ERR_INVALID_ARGUMENT;                                       \
+    if ((b)->poisoned) return CS_ERR_CUDA;                                          \
+    if (cudaSetDevice((b)->device) != cudaSuccess) return bfail((b), CS_ERR_CUDA, "cudaSetDevice failed"); \
+  } while (0)
+
+LaunchCtx batch_ctx(cs_batch* b) {
+  LaunchCtx c{};
+  c.stream = b->stream;
+  c.d_sess = b->d_sess;
+  c.tiled = b->tiled;
+  c.n_sessions = b->n;
+  c.launches = &b->launches;
+  return c;
+}
+
+void batch_reset_host(cs_batch* b, const cs_config* cfgs) {
+  for (int j = 0; j < b->n; j++) {
+    CsSession& s = b->hs[j];
+    memset(s.state, 0, sizeof(s.state));
+    if (cfgs)
+      for (int k = 0; k < 3; k++) s.state[0].pose[k] = cfgs[j].start_pose[k];
+    s.key[0] = s.key[1] = ~0ull;
+    s.max_ring = -1;
+    s.search_done = 0;
+    s.visits = 0;
+  }
+  b->parity = 0;
+  b->scan_count = 0;
+  b->update_count = 0;
+}
+}  // namespace
+
+extern "C" {
+
+const char* cs_batch_last_error(const cs_batch* b) { return b ? b->error.c_str() : g_create_error.c_str(); }
+
+cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** out) {
+  if (!cfgs || !out || n_sessions <= 0 || n_sessions > 65535)
+    return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_batch_create: bad argument (1..65535 sessions)");
+  *out = nullptr;
+  const cs_config& c0 = cfgs[0];
+  if (c0.hole_map_size < 8 || c0.hole_map_size > 16384 || !(c0.physical_map_size > 0.f) || c0.iterations_per_thread < 0)
+    return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_batch_create: bad map size / iterations");
+  for (int j = 1; j < n_sessions; j++) {
+    const cs_config& c = cfgs[j];
+    if (c.hole_map_size != c0.hole_map_size || c.physical_map_size != c0.physical_map_size ||
+        c.iterations_per_thread != c0.iterations_per_thread || c.num_search_threads != c0.num_search_threads ||
+        c.device != c0.device || c.max_points != c0.max_points || c.flags != c0.flags)
+      return bfail(nullptr, CS_ERR_INVALID_ARGUMENT,
+                   "cs_batch_create: session %d differs in map size / iterations / threads / device / max_points / flags "
+                   "(only start_pose, sigma_xy, sigma_theta and seed may vary)", j);
+  }
+  const int threads = c0.num_search_threads > 0 ? c0.num_search_threads : 1;
+  const long long n_cand = (long long)threads * c0.iterations_per_thread;
+  if (n_cand > (1ll << 26)) return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "too many candidates per scan");
+  const int max_points = c0.max_points > 0 ? c0.max_points : 16384;
+  if (max_points > 65536) return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "max_points must be <= 65536");
+  int ndev = cs_device_count();
+  if (ndev <= 0) return bfail(nullptr, CS_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+  if (c0.device < 0 || c0.device >= ndev) return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "device %d out of range", c0.device);
+
+  cs_batch* b = new cs_batch();
+  b->device = c0.device;
+  b->n = n_sessions;
+  b->tiled = !(c0.flags & CS_FLAG_ROW_MAJOR_MAP);
+  b->size = c0.hole_map_size;
+  b->pitch_tiles = (b->size + 7) / 8;
+  b->max_points = (max_points + 1) & ~1;
+  b->n_cand = (int)n_cand;
+  b->scale = (float)c0.hole_map_size / c0.physical_map_size;
+  b->map_cells = b->tiled ? (size_t)b->pitch_tiles * b->pitch_tiles * 64 : (size_t)b->size * b->size;
+  b->hs.assign((size_t)n_sessions, CsSession{});
+  b->off_points = align_up(sizeof(CsStepHeader) * (size_t)n_sessions, 16);
+  b->off_cand = align_up(b->off_points + (size_t)n_sessions * b->max_points * 8, 16);
+  b->stage_bytes = align_up(b->off_cand + (size_t)n_sessions * (size_t)n_cand * 12, 16);
+
+  bool ok = cudaSetDevice(b->device) == cudaSuccess;
+  if (ok && c0.stream) b->stream = (cudaStream_t)c0.stream;
+  else if (ok) { ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess; b->own_stream = ok; }
+  ok = ok && cudaMalloc(&b->d_maps, b->map_cells * sizeof(uint16_t) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_sess, sizeof(CsSession) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_rays, (size_t)b->max_points * sizeof(int4) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_batch_max, ((size_t)b->max_points / 32 + 1) * sizeof(int) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaHostAlloc(&b->h_stage, b->stage_bytes, cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP) == cudaSuccess;
+  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP) == cudaSuccess;
+  if (!ok) {
+    cudaError_t e = cudaGetLastError();
+    bfail(nullptr, e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "cs_batch_create: %s", cudaGetErrorString(e));
+    cs_batch_destroy(b);
+    return e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA;
+  }
+  for (int j = 0; j < n_sessions; j++) {
+    CsSession& s = b->hs[j];
+    memset(&s, 0, sizeof(s));
+    s.map = b->d_maps + (size_t)j * b->map_cells;
+    s.size = b->size;
+    s.pitch_tiles = b->pitch_tiles;
+    s.scale = b->scale;
+    s.sigma_xy = cfgs[j].sigma_xy;
+    s.sigma_theta = cfgs[j].sigma_theta;
+    s.iters = c0.iterations_per_thread;
+    s.threads = c0.num_search_threads;
+    s.n_cand = b->n_cand;
+    s.quality = 50;
+    s.hole_width = 0.6f;
+    s.search_begin = 5;
+    s.seed = cfgs[j].seed;
+    s.rays = b->d_rays + (size_t)j * b->max_points;
+    s.batch_max = b->d_batch_max + (size_t)j * ((size_t)b->max_points / 32 + 1);
+  }
+  batch_reset_host(b, cfgs);
+  cs_fill_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_maps, b->map_cells * (size_t)n_sessions,
+                                                 (uint16_t)((CS_TS_OBSTACLE + CS_TS_NO_OBSTACLE) / 2));
+  b->launches++;
+  cudaMemcpyAsync(b->d_sess, b->hs.data(), sizeof(CsSession) * (size_t)n_sessions, cudaMemcpyHostToDevice, b->stream);
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    bfail(nullptr, CS_ERR_CUDA, "cs_batch_create: %s", cudaGetErrorString(cudaGetLastError()));
+    cs_batch_destroy(b);
+    return CS_ERR_CUDA;
+  }
+  *out = b;
+  return CS_OK;
+}
+
+cs_status cs_batch_destroy(cs_batch* b) {
+  if (!b) return CS_OK;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  cudaFree(b->d_maps);
+  cudaFree(b->d_linear);
+  cudaFree(b->d_sess);
+  cudaFree(b->d_rays);
+  cudaFree(b->d_batch_max);
+  cudaFree(b->d_checksum);
+  cudaFree(b->d_stage);
+  cudaFree(b->d_results);
+  if (b->h_stage) cudaFreeHost(b->h_stage);
+  if (b->h_results) cudaFreeHost(b->h_results);
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  cudaGetLastError();
+  delete b;
+  return CS_OK;
+}
+
+int32_t cs_batch_size(const cs_batch* b) { return b ? b->n : 0; }
+
+// session < 0: all sessions.  Quality 1..255 (:76-82), HoleWidth metres (:87).
+cs_status cs_batch_set_params(cs_batch* b, int32_t session, int32_t quality, float hole_width) {
+  CS_CHECK_BATCH(b);
+  if (session >= b->n) return bfail(b, CS_ERR_INVALID_ARGUMENT, "session %d out of range", session);
+  if (quality < 1 || quality > 255) return bfail(b, CS_ERR_INVALID_ARGUMENT, "Quality must be 1..255");
+  if (!(hole_width >= 0.f) || !(hole_width * b->scale < 60000.f)) return bfail(b, CS_ERR_INVALID_ARGUMENT, "HoleWidth out of range");
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  for (int j = (session < 0 ? 0 : session); j < (session < 0 ? b->n : session + 1); j++) {
+    b->hs[j].quality = quality;
+    b->hs[j].hole_width = hole_width;
+    CS_BCUDA(b, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(b->d_sess + j) + offsetof(CsSession, quality), &b->hs[j].quality,
+                                sizeof(int), cudaMemcpyHostToDevice, b->stream));
+    CS_BCUDA(b, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(b->d_sess + j) + offsetof(CsSession, hole_width), &b->hs[j].hole_width,
+                                sizeof(float), cudaMemcpyHostToDevice, b->stream));
+  }
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  return CS_OK;
+}
+
+static float batch_max_hole_width(const cs_batch* b) {
+  float w = 0.f;
+  for (const CsSession& s : b->hs) w = s.hole_width > w ? s.hole_width : w;
+  return w;
+}
+
+// One CoreSLAMProcessor.Update (:717-752) for every session of the batch.
+//   points        n_sessions * max_points * (x, y); session j uses the first n_points[j]
+//   odometry      n_sessions * (x, y, theta)
+//   cand_offsets  n_sessions * T*I * (dx, dy, dtheta) verification tables, or NULL: per-session Philox streams
+//   results       optional, n_sessions records (blocks until the poses are back)
+cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
+                          const float* cand_offsets, cs_result* results) {
+  CS_CHECK_BATCH(b);
+  if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_update: null argument");
+  const bool do_search = b->scan_count >= b->search_begin;
+  const bool with_offsets = cand_offsets != nullptr && do_search;
+  // the pinned block may still be the source of the previous call's copy
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  int max_n = 0;
+  double max_range = 0.0;
+  for (int j = 0; j < b->n; j++) {
+    const int np = n_points[j];
+    if (np <= 0 || np > b->max_points) return bfail(b, CS_ERR_CAPACITY, "session %d: n_points %d outside 1..%d", j, np, b->max_points);
+    const float* odo = odometry + 3 * (size_t)j;
+    if (!finite3(odo)) return bfail(b, CS_ERR_INVALID_ARGUMENT, "session %d: odometry pose is NaN", j);
+    CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(b->h_stage) + j;
+    memset(hdr, 0, sizeof(CsStepHeader));
+    hdr->odo[0] = odo[0]; hdr->odo[1] = odo[1]; hdr->odo[2] = odo[2];
+    hdr->n_points = np;
+    const float* src = points + (size_t)j * b->max_points * 2;
+    memcpy(b->h_stage + b->off_points + (size_t)j * b->max_points * 8, src, (size_t)np * 8);
+    const double r = max_range_of(src, np);
+    if (!(r <= max_range)) max_range = r;
+    if (np > max_n) max_n = np;
+  }
+  if (with_offsets) memcpy(b->h_stage + b->off_cand, cand_offsets, (size_t)b->n * b->n_cand * 12);
+  const size_t bytes = with_offsets ? b->stage_bytes : b->off_cand;
+  CS_BCUDA(b, cudaMemcpyAsync(b->d_stage, b->h_stage, bytes, cudaMemcpyHostToDevice, b->stream));
+
+  CsStepArgs a{};
+  a.hdr = reinterpret_cast<const CsStepHeader*>(b->d_stage);
+  a.hdr_stride = 1;
+  a.points = reinterpret_cast<const float2*>(b->d_stage + b->off_points);
+  a.points_stride = (size_t)b->max_points;
+  a.cand = with_offsets ? reinterpret_cast<const float*>(b->d_stage + b->off_cand) : nullptr;
+  a.cand_stride = (size_t)b->n_cand * 3;
+  a.result = b->d_results;
+  a.result_stride = 1;
+  a.scan_index = b->update_count;
+  a.cand_mode = with_offsets ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
+  a.step_mode = CS_STEP_UPDATE;
+  a.parity = b->parity;
+  a.do_search = do_search ? 1 : 0;
+  a.n_cand = b->n_cand;
+  a.cand_first = 0;
+  a.cand_count = b->n_cand + 1;
+  CS_BCUDA(b, launch_step_ctx(batch_ctx(b), a, max_n, rings_hint_of(b->size, b->scale, batch_max_hole_width(b), max_range), CS_PHASE_ALL));
+  b->parity ^= 1;
+  b->update_count++;
+  if (!do_search) b->scan_count++;
+  if (results) {
+    CS_BCUDA(b, cudaMemcpyAsync(b->h_results, b->d_results, sizeof(CsDevResult) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+    for (int j = 0; j < b->n; j++) {
+      copy_result(results + j, b->h_results + j);
+      results[j].visits = -1;
+    }
+  }
+  return CS_OK;
+}
+
+// Parameter sweep: every session consumes the same device-resident scan log (its own map, pose, parameters
+// and — when the log carries no candidate tables — its own Philox stream).  results: optional, the
+// n_sessions records of the LAST scan replayed.
+cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results) {
+  CS_CHECK_BATCH(b);
+  if (!log || !log->uploaded) return bfail(b, CS_ERR_STATE, "scan log not uploaded");
+  if (log->device != b->device) return bfail(b, CS_ERR_INVALID_ARGUMENT, "scan log lives on another device");
+  if (first < 0 || count < 0 || first + count > log->n_scans) return bfail(b, CS_ERR_INVALID_ARGUMENT, "scan range");
+  if (log->n_offsets > 0 && log->n_offsets != b->n_cand) return bfail(b, CS_ERR_INVALID_ARGUMENT, "scan log offsets != T*I");
+  if (log->max_points > b->max_points) return bfail(b, CS_ERR_CAPACITY, "scan log max_points exceeds the batch's");
+  const float hw = batch_max_hole_width(b);
+  for (int i = 0; i < count; i++) {
+    const int sidx = first + i;
+    const bool do_search = b->scan_count >= b->search_begin;
+    CsStepArgs a{};
+    a.hdr = log->d_hdr + sidx;
+    a.hdr_stride = 0;
+    a.points = log->d_points + (size_t)sidx * log->max_points;
+    a.points_stride = 0;
+    a.cand = log->n_offsets > 0 ? log->d_offsets + (size_t)sidx * log->n_offsets * 3 : nullptr;
+    a.cand_stride = 0;
+    a.result = b->d_results;
+    a.result_stride = 1;
+    a.scan_index = b->update_count;
+    a.cand_mode = log->n_offsets > 0 ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
+    a.step_mode = CS_STEP_UPDATE;
+    a.parity = b->parity;
+    a.do_search = do_search ? 1 : 0;
+    a.n_cand = b->n_cand;
+    a.cand_first = 0;
+    a.cand_count = b->n_cand + 1;
+    CS_BCUDA(b, launch_step_ctx(batch_ctx(b), a, log->h_hdr[sidx].n_points,
+                                rings_hint_of(b->size, b->scale, hw, log->h_max_range[sidx]), CS_PHASE_ALL));
+    b->parity ^= 1;
+    b->update_count++;
+    if (!do_search) b->scan_count++;
+  }
+  if (results && count > 0) {
+    CS_BCUDA(b, cudaMemcpyAsync(b->h_results, b->d_results, sizeof(CsDevResult) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+    CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+    for (int j = 0; j < b->n; j++) {
+      copy_result(results + j, b->h_results + j);
+      results[j].visits = -1;
+    }
+  } else {
+    CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  }
+  return CS_OK;
+}
+
+cs_status cs_batch_sync(cs_batch* b) {
+  CS_CHECK_BATCH(b);
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  return CS_OK;
+}
+
+cs_status cs_batch_get_poses(cs_batch* b, float* poses /* n_sessions * 3 */) {
+  CS_CHECK_BATCH(b);
+  if (!poses) return bfail(b, CS_ERR_INVALID_ARGUMENT, "null poses");
+  std::vector<CsSession> tmp((size_t)b->n);
+  CS_BCUDA(b, cudaMemcpyAsync(tmp.data(), b->d_sess, sizeof(CsSession) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  for (int j = 0; j < b->n; j++)
+    for (int k = 0; k < 3; k++) poses[3 * j + k] = tmp[j].state[b->parity].pose[k];
+  return CS_OK;
+}
+
+cs_status cs_batch_map_download(cs_batch* b, int32_t session, uint16_t* pixels) {
+  CS_CHECK_BATCH(b);
+  if (!pixels || session < 0 || session >= b->n) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_map_download: bad argument");
+  if (!b->d_linear) CS_BCUDA(b, cudaMalloc(&b->d_linear, (size_t)b->size * b->size * sizeof(uint16_t)));
+  dispatch_layout(b->tiled, [&](auto T) {
+    cs_relayout_kernel<decltype(T)::value><<<148 * 8, 256, 0, b->stream>>>(b->hs[session].map, b->d_linear, b->size, b->pitch_tiles, 0);
+  });
+  b->launches++;
+  CS_BCUDA(b, cudaMemcpyAsync(pixels, b->d_linear, (size_t)b->size * b->size * 2, cudaMemcpyDeviceToHost, b->stream));
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  return CS_OK;
+}
+
+cs_status cs_batch_map_checksums(cs_batch* b, uint64_t* checksums /* n_sessions */) {
+  CS_CHECK_BATCH(b);
+  if (!checksums) return bfail(b, CS_ERR_INVALID_ARGUMENT, "null checksums");
+  for (int j = 0; j < b->n; j++) {
+    CS_BCUDA(b, cudaMemsetAsync(b->d_checksum, 0, sizeof(unsigned long long), b->stream));
+    dispatch_layout(b->tiled, [&](auto T) {
+      cs_checksum_kernel<decltype(T)::value><<<148 * 4, 256, 0, b->stream>>>(b->hs[j].map, b->size, b->pitch_tiles, b->d_checksum);
+    });
+    b->launches++;
+    CS_BCUDA(b, cudaMemcpyAsync(checksums + j, b->d_checksum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+  }
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  return CS_OK;
+}
+
+cs_status cs_batch_get_launch_count(cs_batch* b, uint64_t* launches) {
+  if (!b || !launches) return CS_ERR_INVALID_ARGUMENT;
+  *launches = b->launches;
   return CS_OK;
 }
 

@@ -101,7 +101,7 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
-  const CsStepHeader* hdr;
+  const CsStepHeader* hdr; size_t hdr_stride;    // 1: one header per session, 0: every session reads hdr[0] (shared scan log)
   const float2* points;  size_t points_stride;   // stride in float2 between sessions
   const float* cand;     size_t cand_stride;     // offsets or absolute poses, 3 floats per candidate
   const float* cand_cs;                          // optional (n_cand+1)*2 host cos/sin
@@ -460,7 +460,7 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
-  const CsStepHeader& hdr = a.hdr[sj];
+  const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
   const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
 
@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(CS_SETUP_THREADS)
 cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
-  const CsStepHeader& hdr = a.hdr[sj];
+  const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
   const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
@@ -679,7 +679,7 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   CsSession& S = sessions[sj];
   const int k = blockIdx.x;  // this block's ring
   if (k > S.max_ring) return;
-  const int n = a.hdr[sj].n_points;
+  const int n = a.hdr[(size_t)sj * a.hdr_stride].n_points;
   const int size = S.size, pitch_tiles = S.pitch_tiles;
   const float scale = S.scale;
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(S.cur_pose[0], scale), 0.5f));  // :499, :505

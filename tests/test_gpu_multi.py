@@ -1,0 +1,161 @@
+"""Sharded paths on the GPU: batches of independent sessions (cfg5) and the candidate split
+with its 8-byte arg-min exchange (cfg4) — bit-exact against the CPU oracle / the single-handle path.
+
+The candidate split is exercised on ONE device with two handles playing two ranks (same kernels, same
+exchange code; the MIN runs through torch on the device keys), and, when the box has >= 2 GPUs, with two
+real processes over NCCL.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import slam.net_b200 as sn
+from slam.net_b200 import _native as N
+from slam.net_b200 import parallel as par
+from slam.net_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_batch_update_matches_oracle_per_session():
+    n_sess, n_scans, P, size, phys, iters, threads = 5, 12, 200, 256, 40.0, 48, 2
+    rps = [synth.make_replay(n_scans, P, phys, seed=50 + j) for j in range(n_sess)]
+    sxy = [0.05 + 0.02 * j for j in range(n_sess)]
+    sth = [0.10 + 0.01 * j for j in range(n_sess)]
+    b = sn.Batch(n_sess, phys, size, [rp.odometry[0] for rp in rps], sxy, sth, iters, threads, max_points=P)
+    os_ = [orc.Processor(phys, size, rps[j].odometry[0], sxy[j], sth[j], iters, threads) for j in range(n_sess)]
+    for j in range(n_sess):
+        b.set_params(j, 40 + 30 * j, 0.4 + 0.3 * j)
+        os_[j].quality = 40 + 30 * j
+        os_[j].hole_width = 0.4 + 0.3 * j
+    for k in range(n_scans):
+        offs = np.stack([synth.candidate_offsets(70 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        res = b.update([rps[j].points[k] for j in range(n_sess)], np.stack([rps[j].odometry[k] for j in range(n_sess)]), offs)
+        for j in range(n_sess):
+            os_[j].update(rps[j].points[k], rps[j].odometry[k], offs[j])
+            assert np.array_equal(res[j].pose, os_[j].pose), (k, j)
+            assert res[j].searched == (k >= 5)
+            if k >= 5:
+                assert (res[j].distance, res[j].index) == (os_[j].last_distance, os_[j].last_index)
+    assert np.array_equal(b.poses(), np.stack([o.pose for o in os_]))
+    sums = b.map_checksums()
+    for j in range(n_sess):
+        assert int(sums[j]) == sn.host_map_checksum(np.array(os_[j].map.pixels), size)
+    assert np.array_equal(b.map_download(3), np.array(os_[3].map.pixels))
+    b.close()
+
+
+def test_batch_replay_shared_log_philox_equals_single_handles():
+    """Parameter sweep: every session replays the same log with its own seed / sigmas / HoleWidth (production
+    mode, on-device Philox).  Must equal one cs_processor per session fed the same scans."""
+    n_sess, n_scans, P, size, phys, iters, threads = 4, 14, 180, 200, 40.0, 32, 4
+    rp = synth.make_replay(n_scans, P, phys, seed=9)
+    seeds = [11, 22, 33, 44]
+    sxy = [0.05, 0.1, 0.15, 0.2]
+    sth = [0.05, 0.1, 0.17, 0.25]
+    b = sn.Batch(n_sess, phys, size, rp.odometry[0], sxy, sth, iters, threads, max_points=P, seeds=seeds)
+    log = sn.ScanLog(n_scans, P, n_offsets=0)
+    for k in range(n_scans):
+        log.set(k, rp.points[k], rp.odometry[k])
+    log.upload()
+    for j in range(n_sess):
+        b.set_params(j, 50 + 10 * j, 0.6 + 0.2 * j)
+    res = b.replay(log, 0, 6)
+    res = b.replay(log, 6, n_scans - 6)
+    for j in range(n_sess):
+        p = sn.Processor(phys, size, rp.odometry[0], sxy[j], sth[j], iters, threads, max_points=P, seed=seeds[j])
+        p.set_quality(50 + 10 * j)
+        p.set_hole_width(0.6 + 0.2 * j)
+        o = orc.Processor(phys, size, rp.odometry[0], sxy[j], sth[j], iters, threads)
+        o.quality = 50 + 10 * j
+        o.hole_width = 0.6 + 0.2 * j
+        for k in range(n_scans):
+            r = p.update(rp.points[k], rp.odometry[k], None)
+            o.update(rp.points[k], rp.odometry[k], sn.philox_offsets(seeds[j], k, iters * threads, sxy[j], sth[j]))
+        assert np.array_equal(r.pose, res[j].pose) and (r.distance, r.index) == (res[j].distance, res[j].index)
+        assert np.array_equal(r.pose, o.pose)
+        assert np.array_equal(b.map_download(j), p.map_download())
+        assert np.array_equal(b.map_download(j), np.array(o.map.pixels))
+        p.close()
+    assert len(set(int(x) for x in b.map_checksums())) == n_sess  # the sweep really produced different maps
+    log.close()
+    b.close()
+
+
+def test_batch_rejects_mismatched_configs():
+    cfgs = (N.Config * 2)()
+    for j, c in enumerate(cfgs):
+        c.physical_map_size, c.hole_map_size = 10.0, 64 + 64 * j
+        c.iterations_per_thread, c.num_search_threads = 4, 1
+    h = N.C.c_void_p()
+    assert N.lib().cs_batch_create(cfgs, 2, N.C.byref(h)) == 1  # CS_ERR_INVALID_ARGUMENT
+
+
+@pytest.mark.parametrize("philox", [False, True])
+def test_candidate_split_two_handles_one_device(philox):
+    """Two 'ranks' on one GPU: each evaluates half of the flat candidate indices, the packed keys are
+    min-reduced on the device, both finish with the pose and map of the unsplit reference run."""
+    import torch
+    n_scans, P, size, phys, iters, threads = 16, 300, 320, 40.0, 61, 4  # T*I + 1 = 245: odd split
+    rp = synth.make_replay(n_scans, P, phys, seed=21)
+    seed = 0xABCDEF
+    ranks = [sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=seed) for _ in range(2)]
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    n_flat = iters * threads + 1
+    for k in range(n_scans):
+        off = (sn.philox_offsets(seed, k, iters * threads, 0.1, 0.17) if philox
+               else synth.candidate_offsets(4, k, iters * threads, 0.1, 0.17))
+        ptrs = []
+        for g, p in enumerate(ranks):
+            lo, cnt = par.candidate_slice(n_flat, 2, g)
+            ptrs.append(p.update_begin(rp.points[k], rp.odometry[k], None if philox else off, lo, cnt))
+        assert all(bool(x) == (k >= 5) for x in ptrs)
+        if k >= 5:
+            for p in ranks:
+                p.sync()
+            keys = [par.device_key_tensor(x, 0) for x in ptrs]
+            m = torch.minimum(keys[0], keys[1])  # the 8-byte exchange, played by one device
+            keys[0].copy_(m)
+            keys[1].copy_(m)
+            torch.cuda.synchronize()
+        res = [p.update_finish() for p in ranks]
+        o.update(rp.points[k], rp.odometry[k], off)
+        for r in res:
+            assert np.array_equal(r.pose, o.pose), k
+            if k >= 5:
+                assert (r.distance, r.index) == (o.last_distance, o.last_index)
+    for p in ranks:
+        assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+        p.close()
+
+
+def test_split_phase_state_errors():
+    p = sn.Processor(10.0, 64, (5, 5, 0), 0.1, 0.1, 8, 1, max_points=16)
+    pts = np.array([[1.0, 0.0]], dtype=np.float32)
+    with pytest.raises(sn.CoreSlamError):
+        p.update_finish()                      # finish without begin
+    with pytest.raises(sn.CoreSlamError):
+        p.update_begin(pts, (5, 5, 0), None, 5, 100)   # slice outside [0, T*I+1)
+    p.update_begin(pts, (5, 5, 0), None, 0, 9)
+    with pytest.raises(sn.CoreSlamError):
+        p.update(pts, (5, 5, 0), None)         # a split update is in flight
+    p.update_finish()
+    p.update(pts, (5, 5, 0), None)
+    p.close()
+
+
+def test_candidate_split_two_processes_nccl():
+    """Real thing: 2 ranks, 2 GPUs, NCCL MIN all-reduce of the in-session key."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "mp_split_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SPLIT_OK" in out.stdout
