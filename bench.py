@@ -44,7 +44,11 @@ WORKLOADS = {
     "cfg2": dict(points=1024, threads=4, iters=1024, size=2048, phys=40.0,
                  desc="CoreSLAM synthetic replay, 4096 candidates x 1024-point scans, HoleMap 2048x2048, verification mode"),
     "cfg4": dict(points=1024, threads=64, iters=1024, size=8192, phys=81.92,
-                 desc="Large-map regime: HoleMap 8192x8192 @1 cm (128 MB), 65536 candidates x 1024-point scans"),
+                 desc="Large-map HBM regime: HoleMap 8192x8192 @1 cm (128 MB), 65536 candidates x 1024-point scans, candidates split "
+                      "across the GPUs with one 8-byte arg-min exchange (NCCL MIN all-reduce) per scan"),
+    "cfg5": dict(points=360, threads=1, iters=1000, size=1600, phys=40.0, sessions=1024,
+                 desc="Batched independent sessions: 1024 CoreSLAM replays (parameter sweep over sigma_xy, sigma_theta, HoleWidth, "
+                      "Quality, seed; cfg1 geometry) sharded over the GPUs, no collective"),
 }
 PRIME_SCANS = 5  # PositionSearchBeginning: the first 5 scans only build the map (CoreSLAMProcessor.cs:92, :726)
 SIGMA_XY, SIGMA_THETA = 0.1, 0.17453292  # 0.1 m, 10 degrees (Simulation/MainWindow.xaml.cs:69)
@@ -142,6 +146,130 @@ def run_cpu(wl, rp, offs, n_cand, first, count, budget_s=25.0):
     return lookups / dt, done, T, dt, pose
 
 
+def run_sharded(args, wl, metric, config, rank, world, local, K, W):
+    """cfg4 (candidate split, strong scaling, one 8-byte exchange per scan) and cfg5 (session batches, strong
+    scaling over a fixed set of 1024 sessions, no collective)."""
+    import torch
+    import torch.distributed as dist
+    import slam.net_b200 as sn
+    from slam.net_b200 import parallel as par
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P = wl["points"]
+    n_cand = wl["threads"] * wl["iters"]
+    n_total = PRIME_SCANS + W + K
+    from slam.net_b200 import synth
+    rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed)  # same scans on every rank
+    stream = torch.cuda.Stream()
+    sampler = ClockSampler(local)
+    extra = {}
+    with torch.cuda.stream(stream):
+        if args.workload == "cfg4":
+            proc = sn.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"],
+                                device=local, max_points=P, seed=args.seed, stream=stream.cuda_stream)
+            ss = par.SplitSearch(proc, rank, world, local, torch_stream=stream)
+            for k in range(PRIME_SCANS + W):
+                ss.update(rp.points[k], rp.odometry[k], None)
+            proc.sync()
+            launches0 = proc.launch_count()
+            lat = np.zeros(K)
+            barrier()
+            sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            t0 = time.perf_counter()
+            for i in range(K):
+                k = PRIME_SCANS + W + i
+                ta = time.perf_counter()
+                r = ss.update(rp.points[k], rp.odometry[k], None)
+                lat[i] = time.perf_counter() - ta
+            e1.record(stream)
+            proc.sync()
+            barrier()
+            wall = time.perf_counter() - t0
+            dev_ms = e0.elapsed_time(e1)
+            launches = proc.launch_count() - launches0
+            lookups_per_step = (n_cand + 1) * P  # whole job: all ranks together evaluate every candidate once
+            work_scale = 1
+            scaling = "strong"
+            extra = {"scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3)},
+                     "final_pose": [float(x) for x in r.pose], "map_checksum": int(proc.map_checksum()),
+                     "exchange": "torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world,
+                     "mode": "production (on-device Philox candidates; nothing but the scan is uploaded)"}
+            h2d, d2h = 64 + 8 * P, 32
+            proc.close()
+        else:
+            n_sessions = wl["sessions"]
+            mine = par.session_shard(n_sessions, world, rank)
+            # parameter grid over sigma_xy, sigma_theta, HoleWidth, Quality, seed (SURVEY 8d)
+            sxy = np.array([0.05 + 0.025 * (s % 5) for s in mine], dtype=np.float32)
+            sth = np.array([0.0873 + 0.0436 * ((s // 5) % 4) for s in mine], dtype=np.float32)
+            batch = sn.Batch(len(mine), wl["phys"], wl["size"], rp.odometry[0], sxy, sth, wl["iters"], wl["threads"], device=local,
+                             max_points=P, seeds=[args.seed + s for s in mine], stream=stream.cuda_stream)
+            for j, s in enumerate(mine):
+                batch.set_params(j, 30 + 20 * ((s // 20) % 6), 0.4 + 0.2 * ((s // 120) % 4))
+            log = sn.ScanLog(n_total, P, n_offsets=0, device=local)
+            for k in range(n_total):
+                log.set(k, rp.points[k], rp.odometry[k])
+            log.upload()
+            batch.replay(log, 0, PRIME_SCANS + W, want_results=False)
+            launches0 = batch.launch_count()
+            barrier()
+            sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            e0.record(stream)
+            batch.replay(log, PRIME_SCANS + W, K, want_results=False)
+            e1.record(stream)
+            barrier()
+            wall = time.perf_counter() - t0
+            dev_ms = e0.elapsed_time(e1)
+            launches = batch.launch_count() - launches0
+            lookups_per_step = (n_cand + 1) * P * n_sessions  # whole job per step: every session advances one scan
+            scaling = "strong"
+            poses = batch.poses()
+            extra = {"sessions": n_sessions, "sessions_this_rank": len(mine),
+                     "mode": "production (on-device Philox candidates), shared device-resident scan log",
+                     "pose_spread_m": float(np.ptp(poses[:, 0]) + np.ptp(poses[:, 1])),
+                     "l2": "per-rank working set %d maps x %.1f MB >> L2" % (len(mine), wl["size"] ** 2 * 2 / 1e6)}
+            h2d, d2h = 0, 0
+            log.close()
+            batch.close()
+    clocks = sampler.stop()
+    t_all = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = (float(x) for x in t_all.tolist())
+    if rank == 0:
+        value = lookups_per_step * K / (dev_ms_max * 1e-3)
+        line = {"metric": metric, "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "dtype": "f32 transform -> u16 gather -> i64 sum", "data": "synthetic",
+                "config": dict(config, mode=extra.pop("mode"), timing="CUDA events on the launching stream around the K steps; max over ranks"),
+                "candidate_poses_per_s": value / P, "clocks": clocks,
+                "e2e": {"value": lookups_per_step * K / (wall_ms_max * 1e-3), "unit": "lookups/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms_max / K},
+                "gpu_launches": int(launches)}
+        if args.workload == "cfg5":
+            line["sessions_per_s"] = wl["sessions"] * K / (dev_ms_max * 1e-3)
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -161,7 +289,9 @@ def main():
     config = {"workload": args.workload + ": " + wl["desc"], "points_per_scan": P,
               "candidates_per_scan": wl["threads"] * wl["iters"] + 1, "map": "%dx%d u16" % (wl["size"], wl["size"]),
               "prime_scans": PRIME_SCANS, "mode": "verification (uploaded candidate tables)",
-              "sharding": "one independent replay per GPU, no collective" if world > 1 else "single session"}
+              "sharding": {"cfg4": "candidate slices [g*C/G, (g+1)*C/G) per GPU, replicated map, one 8-byte MIN exchange per scan",
+                           "cfg5": "sessions i mod G per GPU, no collective"}.get(
+                               args.workload, "one independent replay per GPU, no collective" if world > 1 else "single session")}
 
     # ------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -183,6 +313,9 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
+
+    if args.workload in ("cfg4", "cfg5"):
+        return run_sharded(args, wl, metric, config, rank, world, local, K, W)
 
     # ------------------------------------------------------------------------------------ our arm
     import torch
