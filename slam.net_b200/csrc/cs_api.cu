@@ -243,13 +243,18 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
       cs_setup_kernel<<<dim3((unsigned)((n_points + 1023) / 1024), (unsigned)c.n_sessions), CS_SETUP_THREADS, 0, c.stream>>>(c.d_sess, b);
       (*c.launches)++;
     }
-    int warps = (n_points + CS_RING_GROUP - 1) / CS_RING_GROUP;
-    if (warps < 1) warps = 1;
-    if (warps > CS_RING_MAX_WARPS) warps = CS_RING_MAX_WARPS;
-    while (warps & (warps - 1)) warps++;  // the kernel's table size must be a power of two
+    int threads = ((n_points + CS_RING_RPT - 1) / CS_RING_RPT + 31) / 32 * 32;
+    if (threads < 32) threads = 32;
+    if (threads > CS_RING_MAX_THREADS) threads = CS_RING_MAX_THREADS;
     if (rings < 1) rings = 1;
+    // rings per block: enough blocks to fill the chip about twice when one session runs alone
+    int span = c.n_sessions > 1 ? 8 : (rings + 2 * 296 - 1) / (2 * 296);
+    if (span < 1) span = 1;
+    if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
+    a.ring_span = span;
     dispatch_layout(c.tiled, [&](auto T) {
-      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)rings, (unsigned)c.n_sessions), warps * 32, (size_t)warps * CS_RING_SMEM_PER_WARP, c.stream>>>(c.d_sess, a);
+      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)((rings + span - 1) / span), (unsigned)c.n_sessions), threads,
+                                            CS_RING_SMEM(threads), c.stream>>>(c.d_sess, a);
     });
     (*c.launches)++;
   }
@@ -400,9 +405,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)max_points * sizeof(int4)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, ((size_t)max_points / 32 + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP));
+                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP));
+                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total;
@@ -1196,9 +1201,9 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP) == cudaSuccess;
+                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS)) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  CS_RING_MAX_WARPS * CS_RING_SMEM_PER_WARP) == cudaSuccess;
+                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS)) == cudaSuccess;
   if (!ok) {
     cudaError_t e = cudaGetLastError();
     bfail(nullptr, e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "cs_batch_create: %s", cudaGetErrorString(e));

@@ -120,6 +120,7 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int fuse_rays;     // ... and prepares the rays (scans of up to CS_FUSE_RAYS_MAX points)
   int rays_only;     // set-up kernel: the pose was already published, only prepare rays from cur_pose
   int max_ring_hint; // rings the host launched blocks for, minus one
+  int ring_span;     // rings per block of the rings kernel
   long long* visits_out;  // optional device slot that receives the visit count
   long long* diag;        // optional diagnostics buffer (8 values per ring), see cs_get_ring_cycles
 };
@@ -611,38 +612,33 @@ cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 // Every ray starts in the same cell (x1,y1) and advances exactly one cell along its major axis per step,
 // so the cell written at step k lies on the square ring of Chebyshev radius k around the start.  Rings
 // are independent of each other, and inside a ring the only ordering that matters is the reference's
-// ray order (foreach over cloud.Points, :517) among rays that hit the same cell.
+// ray order (foreach over cloud.Points, :517) among rays that hit the same cell WITH DIFFERENT pixvals:
+// blends of one pixval commute with themselves, so a cell visited n times with one pixval just needs n.
 //
-// One block owns one ring.  Its warps take the rays in rounds of 256 per warp (eight 32-ray batches); every
-// lane evaluates its ray's cell, ring position and pixval at step k in closed form and leaves (position,
-// pixval).  Lanes of a batch that sit on the same cell form a group (match.any); the group's first lane
-// enters the cell into a shared-memory hash table keyed by ring position and sets its batch's bit in the
-// cell's mask.  Then, per cell, the batches of the mask are applied in ascending (= ray) order: the first
-// loads the cell from the map, each applies its lanes in lane order and hands the value to the next batch
-// through shared memory, the last stores the cell.  Cells are independent, so all map loads are in flight
-// together and nothing is serialised except the blends of one cell — which is exactly the reference's
-// dependency.  Batches whose rays all share one cell and pixval (the long runs of the inner rings) are
-// applied as a count, and a cell that has reached the fixed point of a pixval skips further identical
-// blends.  No global atomics, no sort, bit-exact for any ray order.
+// One block owns a span of rings; one lane evaluates one (ray, ring) visit in closed form.  Per ring:
+//   1. every live lane stores (ray, pixval) into a shared slot indexed by the cell's position on the ring
+//      (plain store; one writer survives and becomes the cell's owner);
+//   2. the others — the cell is contested — add 1 to the slot's counter, plus a "mixed" mark if their
+//      pixval differs from the owner's;
+//   3. owners of uncontested cells do the read-modify-write directly (the overwhelming majority of
+//      visits outside the dense disc around the robot); owners of contested uniform cells apply the blend
+//      count+1 times (with the exact fixed-point early-out); for mixed cells the 32-ray batches that visit
+//      the cell are chained in ascending order through the slot (mask of batches + a hand-off word), each
+//      batch applying its lanes in lane order.
+// Rings with more than CS_RING_SLOTS positions (k > 1024) go through the table in windows of positions.
+// No global atomics, no sort, bit-exact for any ray order; shared-memory atomics only on contested visits.
+// Scans with more rays than one round (threads x CS_RING_RPT) are processed in consecutive rounds; a
+// round starts after the previous round's stores, which keeps the ray order across rounds.
 // ---------------------------------------------------------------------------------------------------
-#define CS_RING_B 4                     // 32-ray batches per warp
-#define CS_RING_GROUP (32 * CS_RING_B)  // rays per warp and round
-#define CS_RING_MAX_WARPS 8
-#define CS_RING_UW ((CS_RING_MAX_WARPS * CS_RING_B + 31) / 32)  // mask words per slot
-#define CS_RING_SMEM_PER_WARP (CS_RING_GROUP * 4 * (2 + 6 + 2 * CS_RING_UW))  // pos, pix; per slot (2 per ray): key, value, seq, masks
-#define CS_POS_NONE (-1)
+#define CS_RING_MAX_THREADS 512
+#define CS_RING_RPT 2                  // rays per lane and round
+#define CS_RING_SLOTS 8192             // slot table entries: rings up to k = 1024 are indexed directly, longer ones hashed
+#define CS_RING_MAX_SPAN 16
+// dynamic shared memory for a block of `threads` threads
+#define CS_RING_SMEM(threads) ((size_t)CS_RING_SLOTS * 8 + (size_t)(threads) * CS_RING_RPT * (16 + 4))
 
 __device__ __forceinline__ int cs_blend(int old, int pixval, int alpha) {
   return (int)(uint16_t)(((256 - alpha) * old + alpha * pixval) >> 8);  // :431
-}
-
-// position of cell (x1+ox, y1+oy) along the ring of radius k = max(|ox|,|oy|): 0 .. 8k-1, counter-clockwise
-// from the corner (k,-k).  One value per cell.
-__device__ __forceinline__ int cs_ring_pos(int ox, int oy, int k) {
-  if (ox == k) return oy + k;
-  if (oy == k) return 3 * k - ox;
-  if (ox == -k) return 5 * k - oy;
-  return 7 * k + ox;
 }
 
 struct CsBlendState {
@@ -656,29 +652,50 @@ struct CsBlendState {
     val = nv;
   }
   __device__ __forceinline__ void apply_n(int pv, int cnt, int alpha) {
-    while (cnt-- > 0 && !(fixed && pv == last_pv)) {
+    while (cnt-- > 0) {
       const int nv = cs_blend(val, pv, alpha);
-      fixed = (nv == val);
-      last_pv = pv;
+      if (nv == val) break;  // fixed point of this pixval
       val = nv;
     }
   }
 };
 
+// One visit: ray r at ring k.  pos = the cell's index along the ring (0 .. 8k-1, one value per cell:
+// side s of the square contributes (2s+1)k +- minor, the corner 8k wraps to 0).
 template <bool TILED>
-__global__ void __launch_bounds__(CS_RING_MAX_WARPS * 32)
+__device__ __forceinline__ bool cs_ring_visit(const CsRay& r, int k, int x1, int y1, int size, int pitch_tiles, int& pos,
+                                              uint32_t& cell, int& pv) {
+  if (!(r.flags & 1) || k > r.dxc) return false;
+  const int m = cs_ray_minor(r, k);
+  const int dmaj = (r.flags & 4) ? -k : k;
+  const int dmin = (r.flags & 8) ? -m : m;
+  const bool steep = (r.flags & 2) != 0;
+  const int ox = steep ? dmin : dmaj;
+  const int oy = steep ? dmaj : dmin;
+  const int x = x1 + ox, y = y1 + oy;
+  if ((unsigned)x >= (unsigned)size || (unsigned)y >= (unsigned)size) return false;  // cannot happen for a clipped ray
+  int p;
+  if (!steep) p = (r.flags & 4) ? 5 * k - oy : k + oy;
+  else p = (r.flags & 4) ? 7 * k + ox : 3 * k - ox;
+  pos = (p == 8 * k) ? 0 : p;
+  cell = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
+  pv = cs_ray_pixval(r, k);
+  return true;
+}
+
+template <bool TILED>
+__global__ void __launch_bounds__(CS_RING_MAX_THREADS, 2)
 cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  extern __shared__ int cs_ring_smem[];  // blockDim.x/32 * CS_RING_SMEM_PER_WARP bytes
-  // per 32-ray batch of the round: x = active-lane mask, y = position and z = pixval of its first active
-  // lane, w = 1 when every active lane of the batch has that same position and pixval
-  __shared__ int4 s_batch[CS_RING_MAX_WARPS * CS_RING_B];
+  extern __shared__ int4 cs_ring_smem[];
 
   const long long t_begin = a.diag ? clock64() : 0;
-#define CS_STAMP(i) do { if (a.diag && threadIdx.x == 0) a.diag[(size_t)blockIdx.x * 8 + (i)] = clock64() - t_begin; } while (0)
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
-  const int k = blockIdx.x;  // this block's ring
-  if (k > S.max_ring) return;
+  const int span = a.ring_span;
+  const int k_begin = blockIdx.x * span;
+  const int max_ring = S.max_ring;
+  if (k_begin > max_ring) return;
+  const int k_end = min(k_begin + span - 1, max_ring);
   const int n = a.hdr[(size_t)sj * a.hdr_stride].n_points;
   const int size = S.size, pitch_tiles = S.pitch_tiles;
   const float scale = S.scale;
@@ -688,178 +705,188 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   uint16_t* __restrict__ map = S.map;
   const int4* __restrict__ rays = S.rays;
   const int* __restrict__ batch_max = S.batch_max;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int W = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthreads = blockDim.x;
+  const int round_cap = nthreads * CS_RING_RPT;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int round_entries = W * CS_RING_GROUP;
-  const int tsize = 2 * round_entries;  // power of two (W is 1, 2, 4 or 8)
-  int* s_pos = cs_ring_smem;
-  int* s_pix = s_pos + round_entries;
-  int* s_keys = s_pix + round_entries;                             // slot -> ring position
-  volatile int* s_val = s_keys + tsize;                            // slot -> value handed from batch to batch
-  volatile int* s_seq = s_keys + 2 * tsize;                        // slot -> 1 + last batch that has been applied
-  unsigned* s_mask = reinterpret_cast<unsigned*>(s_keys + 3 * tsize);  // slot -> batches touching it (CS_RING_UW words)
-  CS_STAMP(4);
 
-  for (int round0 = 0; round0 < n; round0 += round_entries) {
-    const int g0 = round0 + warp * CS_RING_GROUP;
-    const int e0 = warp * CS_RING_GROUP;  // this warp's first entry in the round arrays
-    // the table is cleared while the rays are evaluated
-    for (int i = threadIdx.x; i < tsize; i += blockDim.x) {
-      s_keys[i] = CS_POS_NONE;
-      s_seq[i] = 0;
-#pragma unroll
-      for (int u = 0; u < CS_RING_UW; u++) s_mask[i * CS_RING_UW + u] = 0u;
-    }
+  unsigned* s_w = reinterpret_cast<unsigned*>(cs_ring_smem);            // slot -> local ray << 18 | pixval (0 .. 2*65500 + carries: 18 bits); later: batch mask
+  unsigned* s_c = s_w + CS_RING_SLOTS;                                   // slot -> contested visits | mixed marks << 16; later: hand-off word
+  int4* s_rays = reinterpret_cast<int4*>(s_c + CS_RING_SLOTS);           // this round's packed rays
+  int* s_lpv = reinterpret_cast<int*>(s_rays + round_cap);               // pixvals of the visits of mixed cells
 
-    // ---- every lane evaluates its eight rays at step k ---------------------------------------------------
-    uint32_t cell[CS_RING_B];
-    int pos[CS_RING_B];
-    unsigned peers[CS_RING_B];  // lanes of the same batch on the same cell (this lane included), 0: not on the ring
-    CS_STAMP(5);
-    // batches none of whose rays reaches this ring are skipped; the others' rays are all requested up front
-    int4 q[CS_RING_B];
-    unsigned live = 0;  // bit j: batch j has a ray on this ring
+  for (int i = tid; i < CS_RING_SLOTS; i += nthreads) s_c[i] = 0u;
+
+  for (int round0 = 0; round0 < n; round0 += round_cap) {
+    const int round_n = min(round_cap, n - round0);
+    if (round0 > 0) __syncthreads();  // previous round: stores done, shared arrays free
+    for (int i = tid; i < round_n; i += nthreads) s_rays[i] = __ldg(rays + round0 + i);
+    int bmax[CS_RING_RPT];
 #pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {
-      const int b = (g0 >> 5) + j;
-      q[j] = make_int4(0, 0, 0, 0);
-      if (b * 32 < n && __ldg(batch_max + b) >= k) {
-        live |= 1u << j;
-        const int ri = g0 + j * 32 + lane;
-        if (ri < n) q[j] = __ldg(rays + ri);
-      }
+    for (int j = 0; j < CS_RING_RPT; j++) {
+      const int unit = warp * CS_RING_RPT + j;
+      bmax[j] = (unit * 32 < round_n) ? __ldg(batch_max + (round0 >> 5) + unit) : -1;
     }
-    CS_STAMP(6);
-    int pixv[CS_RING_B];
-#pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {  // per-lane arithmetic only, so the eight rays interleave
-      cell[j] = 0; pos[j] = CS_POS_NONE; pixv[j] = 0;
-      const CsRay r = cs_unpack_ray(q[j]);
-      if ((r.flags & 1) && k <= r.dxc) {
-        const int m = cs_ray_minor(r, k);
-        const int dmaj = (r.flags & 4) ? -k : k;
-        const int dmin = (r.flags & 8) ? -m : m;
-        const int ox = (r.flags & 2) ? dmin : dmaj;
-        const int oy = (r.flags & 2) ? dmaj : dmin;
-        const int x = x1 + ox, y = y1 + oy;
-        if ((unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size) {
-          cell[j] = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
-          pixv[j] = cs_ray_pixval(r, k);
-          pos[j] = cs_ring_pos(ox, oy, k);
-        }
-      }
-    }
-    CS_STAMP(7);
-#pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {  // warp-wide: batch summary and same-cell groups
-      peers[j] = 0;
-      int4 bi = make_int4(0, CS_POS_NONE, 0, 0);
-      if ((live >> j) & 1u) {  // warp-uniform
-        const bool active = pos[j] != CS_POS_NONE;
-        s_pix[e0 + j * 32 + lane] = pixv[j];
-        const unsigned actm = __ballot_sync(0xffffffffu, active);
-        bi.x = (int)actm;
-        if (actm) {
-          const int fl = __ffs(actm) - 1;
-          bi.y = __shfl_sync(0xffffffffu, pos[j], fl);
-          bi.z = __shfl_sync(0xffffffffu, pixv[j], fl);
-          const bool same_pos = __all_sync(0xffffffffu, !active || pos[j] == bi.y);
-          bi.w = (same_pos && __all_sync(0xffffffffu, !active || pixv[j] == bi.z)) ? 1 : 0;
-          if (active) peers[j] = same_pos ? actm : __match_any_sync(actm, pos[j]);
-        }
-      }
-      if (lane == 0) s_batch[warp * CS_RING_B + j] = bi;
-    }
-    CS_STAMP(1);
     __syncthreads();
 
-    // ---- the first lane of every same-cell group enters the cell into the table with its batch number ----
-    int slot[CS_RING_B];
+    for (int k = k_begin; k <= k_end; k++) {
+      int pos[CS_RING_RPT], pv[CS_RING_RPT];
+      uint32_t cell[CS_RING_RPT];
+      bool live[CS_RING_RPT];
+      // ---- evaluate this lane's visits of ring k ------------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {
-      slot[j] = -1;
-      if (peers[j] && (peers[j] & lt_mask) == 0) {
-        unsigned sl = (((unsigned)pos[j] * 2654435761u) >> 8) & (unsigned)(tsize - 1);
-        for (;;) {
-          const int old = atomicCAS(&s_keys[sl], CS_POS_NONE, pos[j]);
-          if (old == CS_POS_NONE || old == pos[j]) break;
-          sl = (sl + 1) & (unsigned)(tsize - 1);
+      for (int j = 0; j < CS_RING_RPT; j++) {
+        live[j] = false;
+        const int li = (warp * CS_RING_RPT + j) * 32 + lane;
+        if (bmax[j] >= k && li < round_n) {  // bmax: warp-uniform skip of batches that do not reach this ring
+          const CsRay r = cs_unpack_ray(s_rays[li]);
+          live[j] = cs_ring_visit<TILED>(r, k, x1, y1, size, pitch_tiles, pos[j], cell[j], pv[j]);
         }
-        slot[j] = (int)sl;
-        const int unit = warp * CS_RING_B + j;
-        atomicOr(&s_mask[sl * CS_RING_UW + (unit >> 5)], 1u << (unit & 31));
       }
-    }
-    CS_STAMP(2);
-    __syncthreads();
-
-    // ---- per cell, the batches that touch it are applied in ascending (= ray) order: the first one loads the
-    // cell, each one applies its lanes in lane order and hands the value on through shared memory, the last
-    // one stores.  A batch only ever waits for batches of lower number, which are earlier in this warp's
-    // program order or belong to a lower warp, so the waits always resolve. ----------------------------------
-    int pred[CS_RING_B];   // batch to wait for (-1: this batch opens the cell)
-    bool last[CS_RING_B];  // this batch closes the cell
-    int v[CS_RING_B];
+      // rings longer than the slot table (k > 1024) are handled in windows of CS_RING_SLOTS positions
+      const int nwin = (8 * k + CS_RING_SLOTS - 1) / CS_RING_SLOTS;
+      for (int win = 0; win < max(nwin, 1); win++) {
+        bool act[CS_RING_RPT], owner[CS_RING_RPT];
+        unsigned word[CS_RING_RPT];
+        int h[CS_RING_RPT];
+        // ---- 1. claim the slots ------------------------------------------------------------------------------
 #pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {
-      pred[j] = -1; last[j] = false; v[j] = 0;
-      if (slot[j] >= 0) {
-        const int unit = warp * CS_RING_B + j;
-        bool later = false;
-#pragma unroll
-        for (int u = 0; u < CS_RING_UW; u++) {
-          const unsigned um = s_mask[slot[j] * CS_RING_UW + u];
-          const int base_u = u * 32;
-          unsigned below = um, above = um;
-          if (unit < base_u) below = 0;
-          else if (unit < base_u + 32) below = um & ((1u << (unit - base_u)) - 1u);
-          if (unit >= base_u + 32) above = 0;
-          else if (unit >= base_u) above = um & ~((2u << (unit - base_u)) - 1u);
-          if (below) pred[j] = base_u + 31 - __clz(below);
-          later = later || (above != 0);
-        }
-        last[j] = !later;
-        if (pred[j] < 0) v[j] = (int)__ldcg(map + cell[j]);  // all opening loads are issued before anything waits
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < CS_RING_B; j++) {
-      if (slot[j] >= 0) {
-        CsBlendState st;
-        st.last_pv = -1; st.fixed = false;
-        if (pred[j] >= 0) {
-          while (s_seq[slot[j]] != pred[j] + 1) { }
-          __threadfence_block();
-          st.val = s_val[slot[j]];
-        } else {
-          st.val = v[j];
-        }
-        const int4 bi = s_batch[warp * CS_RING_B + j];
-        if (bi.w) {
-          st.apply_n(bi.z, __popc(peers[j]), alpha);  // the whole batch sits on this cell with one pixval
-        } else {
-          unsigned pm = peers[j];
-          while (pm) {
-            const int l = __ffs(pm) - 1;
-            pm &= pm - 1;
-            st.apply(s_pix[e0 + j * 32 + l], alpha);
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          act[j] = live[j] && (pos[j] >> 13) == win;
+          h[j] = pos[j] & (CS_RING_SLOTS - 1);
+          if (act[j]) {
+            const int li = (warp * CS_RING_RPT + j) * 32 + lane;
+            word[j] = ((unsigned)li << 18) | ((unsigned)pv[j] & 0x3ffffu);
+            s_w[h[j]] = word[j];
           }
         }
-        if (last[j]) {
-          __stcg(map + cell[j], (uint16_t)st.val);
-        } else {
-          s_val[slot[j]] = st.val;
-          __threadfence_block();
-          s_seq[slot[j]] = warp * CS_RING_B + j + 1;
+        __syncthreads();
+        // ---- 2. owners are the lanes that read their own word back; the others mark the slot ---------------
+        bool contested = false;
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          owner[j] = false;
+          if (act[j]) {
+            const unsigned w = s_w[h[j]];
+            owner[j] = (w == word[j]);
+            if (!owner[j]) {
+              atomicAdd(&s_c[h[j]], 1u + ((((w ^ word[j]) & 0x3ffffu) != 0u) ? 0x10000u : 0u));
+              contested = true;
+            }
+          }
+        }
+        if (!__syncthreads_or(contested)) {
+          // ---- 3a. no cell is visited twice in this round: plain read-modify-write --------------------------
+          int v[CS_RING_RPT];
+#pragma unroll
+          for (int j = 0; j < CS_RING_RPT; j++)
+            if (act[j]) v[j] = (int)__ldcg(map + cell[j]);
+#pragma unroll
+          for (int j = 0; j < CS_RING_RPT; j++)
+            if (act[j]) __stcg(map + cell[j], (uint16_t)cs_blend(v[j], pv[j], alpha));
+          continue;
+        }
+        // ---- 3b. contested cells with one pixval: the owner applies it count+1 times -------------------------
+        unsigned cnt[CS_RING_RPT];
+        bool slow[CS_RING_RPT];
+        bool any_slow_l = false;
+        int v[CS_RING_RPT];
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          cnt[j] = 0u; slow[j] = false; v[j] = 0;
+          if (act[j]) {
+            cnt[j] = s_c[h[j]];
+            slow[j] = (cnt[j] >> 16) != 0u;
+            any_slow_l = any_slow_l || slow[j];
+            if (owner[j] && !slow[j]) v[j] = (int)__ldcg(map + cell[j]);
+          }
+        }
+        const int any_slow = __syncthreads_or(any_slow_l);
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          if (act[j] && owner[j]) {
+            if (cnt[j]) s_c[h[j]] = 0u;  // everybody has read it (barrier above): re-arm / hand-off word "empty"
+            if (!slow[j]) {
+              CsBlendState st;
+              st.val = v[j]; st.last_pv = -1; st.fixed = false;
+              st.apply_n(pv[j], (int)(cnt[j] & 0xffffu) + 1, alpha);
+              __stcg(map + cell[j], (uint16_t)st.val);
+            } else {
+              s_w[h[j]] = 0u;  // becomes the mask of the 32-ray batches that visit this cell
+            }
+          }
+        }
+        if (!any_slow) continue;
+        // ---- 3c. cells visited with different pixvals: per cell, the batches that visit it are applied in
+        // ascending (= ray) order.  Lanes of a batch on the same cell form a group; its first lane sets the
+        // batch's bit in the cell's mask, then — in mask order — loads the cell or takes it from the
+        // previous batch through the slot's hand-off word, applies the group's pixvals in lane order and
+        // stores the cell or hands it on.  A batch only waits for lower batches: lower warps, or this
+        // warp's earlier j.
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++)
+          if (act[j] && slow[j]) s_lpv[(warp * CS_RING_RPT + j) * 32 + lane] = pv[j];
+        __syncthreads();
+        unsigned peers[CS_RING_RPT];
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          peers[j] = 0u;
+          const bool sl = act[j] && slow[j];
+          const unsigned bal = __ballot_sync(0xffffffffu, sl);
+          if (sl) {
+            peers[j] = __match_any_sync(bal, pos[j]);
+            if ((peers[j] & lt_mask) == 0u) atomicOr(&s_w[h[j]], 1u << (warp * CS_RING_RPT + j));
+          }
+        }
+        __syncthreads();
+        int pred[CS_RING_RPT];
+        bool lead[CS_RING_RPT], last[CS_RING_RPT];
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          const int unit = warp * CS_RING_RPT + j;
+          lead[j] = peers[j] != 0u && (peers[j] & lt_mask) == 0u;
+          pred[j] = -1; last[j] = true;
+          if (lead[j]) {
+            const unsigned m = s_w[h[j]];
+            const unsigned below = m & ((1u << unit) - 1u);
+            if (below) pred[j] = 31 - __clz(below);
+            last[j] = unit == 31 || (m >> (unit + 1)) == 0u;
+            if (pred[j] < 0) v[j] = (int)__ldcg(map + cell[j]);  // all opening loads are in flight before anything waits
+          }
+        }
+        __syncthreads();  // every mask has been read: s_w may be claimed again by the lanes that run ahead
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          if (lead[j]) {
+            const int unit = warp * CS_RING_RPT + j;
+            volatile unsigned* hand = s_c + h[j];
+            CsBlendState st;
+            st.last_pv = -1; st.fixed = false;
+            if (pred[j] >= 0) {
+              unsigned w;
+              do { w = *hand; } while ((w >> 16) != (unsigned)(pred[j] + 1));
+              st.val = (int)(w & 0xffffu);
+            } else {
+              st.val = v[j];
+            }
+            unsigned pm = peers[j];
+            while (pm) {
+              const int l = __ffs(pm) - 1;
+              pm &= pm - 1;
+              st.apply(s_lpv[unit * 32 + l], alpha);
+            }
+            if (last[j]) {
+              __stcg(map + cell[j], (uint16_t)st.val);
+              if (pred[j] >= 0) *hand = 0u;  // re-arm the slot's counter
+            } else {
+              *hand = ((unsigned)(unit + 1) << 16) | (unsigned)st.val;
+            }
+          }
         }
       }
     }
-    CS_STAMP(3);
-    if (round0 + round_entries < n) __syncthreads();  // rounds are ordered; the shared arrays are reused
   }
-  CS_STAMP(0);
-#undef CS_STAMP
+  if (a.diag && tid == 0) a.diag[(size_t)blockIdx.x * 8] = clock64() - t_begin;
 }
 
 // ---------------------------------------------------------------------------------------------------
