@@ -180,7 +180,8 @@ cs_status cs_scanlog_set(cs_scanlog* log, int32_t scan, const float* points, int
                          const float odometry_pose[3], const float* cand_offsets /* n_offsets*3 or NULL */);
 cs_status cs_scanlog_upload(cs_scanlog* log);
 cs_status cs_scanlog_destroy(cs_scanlog* log);
-/* Runs Update for scans [first, first+count) back to back on the device; results[count] optional. */
+/* Runs Update for scans [first, first+count) back to back on the device; results[count] optional.
+ * With results == NULL the call only enqueues the work and returns (cs_sync waits for it). */
 cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);
 
 /* ---- batches of independent sessions on one GPU (parameter sweeps / scan-log replays, BASELINE cfg5) ----

@@ -212,37 +212,49 @@ enum { CS_PHASE_SEARCH = 1, CS_PHASE_FINISH = 2, CS_PHASE_ALL = 3 };
 // candidate split): SEARCH launches only the search over this GPU's candidate slice and leaves the packed
 // arg-min in CsSession::key[parity]; FINISH — after the caller's 8-byte min exchange — launches the set-up
 // kernel (which decodes the reduced key) and the rings kernel.
+// Launch with the programmatic-stream-serialization attribute: the kernel may become resident while its
+// predecessor in the stream drains; every kernel here calls cs_pdl_wait() before it reads anything the
+// predecessor wrote.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int rings, int phases) {
   const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
   const bool draws = a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0;
-  const bool big = n_points > CS_FUSE_RAYS_MAX;
   const bool fused = searching && phases == CS_PHASE_ALL;
   a.fuse_publish = fused ? 1 : 0;
-  a.fuse_rays = (draws && !big) ? 1 : 0;
-  a.rays_only = 0;
   a.max_ring_hint = rings - 1;
   a.diag = c.diag;
+  cudaError_t e = cudaSuccess;
   if ((phases & CS_PHASE_SEARCH) && searching) {
     dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), (unsigned)c.n_sessions);
     dispatch_layout(c.tiled, [&](auto T) {
-      cs_search_kernel<decltype(T)::value><<<grid, CS_SEARCH_WARPS * 32, 0, c.stream>>>(c.d_sess, a);
+      e = launch_pdl(cs_search_kernel<decltype(T)::value>, grid, dim3(CS_SEARCH_WARPS * 32), 0, c.stream, c.d_sess, a);
     });
+    if (e != cudaSuccess) return e;
     (*c.launches)++;
   }
   if (!(phases & CS_PHASE_FINISH)) return cudaGetLastError();
   if (!fused) {
-    cs_setup_kernel<<<dim3(1, (unsigned)c.n_sessions), CS_SETUP_THREADS, 0, c.stream>>>(c.d_sess, a);
+    e = launch_pdl(cs_setup_kernel, dim3(1, (unsigned)c.n_sessions), dim3(CS_SETUP_THREADS), 0, c.stream, c.d_sess, a);
+    if (e != cudaSuccess) return e;
     (*c.launches)++;
   }
   // the pose is out once this kernel has finished
   if (c.ev_pose) cudaEventRecord(c.ev_pose, c.stream);
   if (draws) {
-    if (big) {
-      CsStepArgs b = a;
-      b.rays_only = 1;
-      cs_setup_kernel<<<dim3((unsigned)((n_points + 1023) / 1024), (unsigned)c.n_sessions), CS_SETUP_THREADS, 0, c.stream>>>(c.d_sess, b);
-      (*c.launches)++;
-    }
     int threads = ((n_points + CS_RING_RPT - 1) / CS_RING_RPT + 31) / 32 * 32;
     if (threads < 32) threads = 32;
     if (threads > CS_RING_MAX_THREADS) threads = CS_RING_MAX_THREADS;
@@ -252,10 +264,14 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
     a.ring_span = span;
+    int blocks = (rings + span - 1) / span;
+    const int nprep = (n_points + threads - 1) / threads;  // the first blocks also prepare the rays
+    if (blocks < nprep) blocks = nprep;
     dispatch_layout(c.tiled, [&](auto T) {
-      cs_rings_kernel<decltype(T)::value><<<dim3((unsigned)((rings + span - 1) / span), (unsigned)c.n_sessions), threads,
-                                            CS_RING_SMEM(threads), c.stream>>>(c.d_sess, a);
+      e = launch_pdl(cs_rings_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
+                     CS_RING_SMEM(threads), c.stream, c.d_sess, a);
     });
+    if (e != cudaSuccess) return e;
     (*c.launches)++;
   }
   if (c.ev_done) cudaEventRecord(c.ev_done, c.stream);
@@ -498,7 +514,7 @@ cs_status cs_reset(cs_processor* h) {  // CoreSLAMProcessor.cs:167-175
   for (int k = 0; k < 3; k++) s.state[0].pose[k] = h->cfg.start_pose[k];  // :172
   s.state[0].scan_count = 0;                                               // :174 (lastOdometryPose = 0, :173)
   s.key[0] = s.key[1] = ~0ull;
-  s.max_ring = -1;
+  s.prep_word = 0ull;
   s.search_done = 0;
   s.visits = 0;
   h->parity = 0;
@@ -1043,7 +1059,8 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     static_assert(sizeof(cs_result) == sizeof(CsDevResult), "");
     CS_CUDA(h, cudaMemcpyAsync(results, log->d_results + first, sizeof(CsDevResult) * count, cudaMemcpyDeviceToHost, h->stream));
   }
-  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  // results == NULL: fire and forget — the scans stay queued on the stream (cs_sync / cs_get_pose wait for them)
+  if (results || timing) CS_CUDA(h, cudaStreamSynchronize(h->stream));
   if (per_kernel) {
     cs_status st = collect_timing(h, false);
     if (st != CS_OK) return st;
@@ -1134,7 +1151,7 @@ void batch_reset_host(cs_batch* b, const cs_config* cfgs) {
     if (cfgs)
       for (int k = 0; k < 3; k++) s.state[0].pose[k] = cfgs[j].start_pose[k];
     s.key[0] = s.key[1] = ~0ull;
-    s.max_ring = -1;
+    s.prep_word = 0ull;
     s.search_done = 0;
     s.visits = 0;
   }
@@ -1400,9 +1417,7 @@ cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int
       copy_result(results + j, b->h_results + j);
       results[j].visits = -1;
     }
-  } else {
-    CS_BCUDA(b, cudaStreamSynchronize(b->stream));
-  }
+  }  // results == NULL: fire and forget (cs_batch_sync waits)
   return CS_OK;
 }
 

@@ -95,8 +95,11 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   long long* ring_cycles;      // optional diagnostics: cycles each ring's block spent in the rings kernel
   float cur_pose[3];           // pose the current integration draws from (Pose after :745-747)
   float cur_cs[2];             // its (cos, sin), unscaled
-  int max_ring;                // largest dxc of a valid ray, -1: nothing to draw, INT_MAX: unknown (multi-block set-up)
   unsigned search_done;        // blocks of the running search kernel that have finished
+  int pad0;
+  // one 8-byte word, read with a single load by the rings kernel's blocks: {prep_done, max_ring}
+  unsigned long long prep_word;  // low 32: blocks of the rings kernel that have prepared their rays; high 32: max_ring + 1
+                                 // (max_ring = largest dxc of a valid ray, -1: nothing to draw)
   long long visits;            // cells written by the current integration = sum over valid rays of dxc+1
 };
 
@@ -117,8 +120,6 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int cand_first;  // first flat index evaluated by this GPU (multi-GPU candidate split), normally 0
   int cand_count;  // number of flat indices evaluated by this GPU, normally n_cand+1
   int fuse_publish;  // search kernel: its last block runs the Update glue and publishes the pose
-  int fuse_rays;     // ... and prepares the rays (scans of up to CS_FUSE_RAYS_MAX points)
-  int rays_only;     // set-up kernel: the pose was already published, only prepare rays from cur_pose
   int max_ring_hint; // rings the host launched blocks for, minus one
   int ring_span;     // rings per block of the rings kernel
   long long* visits_out;  // optional device slot that receives the visit count
@@ -138,6 +139,11 @@ __device__ __forceinline__ uint32_t cs_cell_offset(int x, int y, int size, int p
     return (uint32_t)y * (uint32_t)size + (uint32_t)x;
   }
 }
+
+// programmatic dependent launch: a kernel launched with the stream-serialization attribute may start while its
+// predecessor drains; it must not touch the predecessor's results before cs_pdl_wait()
+__device__ __forceinline__ void cs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void cs_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // wrapping int32 arithmetic (C# unchecked)
 __device__ __forceinline__ int cs_wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
@@ -333,7 +339,7 @@ __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader
   }
   S.cur_pose[0] = g.pose[0]; S.cur_pose[1] = g.pose[1]; S.cur_pose[2] = g.pose[2];
   S.cur_cs[0] = g.cs[0]; S.cur_cs[1] = g.cs[1];
-  S.max_ring = 2147483647;  // unknown until the rays are prepared (a multi-block set-up leaves it there)
+  S.prep_word = 0ull;  // raised by the rings kernel's ray preparation
   S.visits = 0;
   if (result) {
     result->pose[0] = g.pose[0]; result->pose[1] = g.pose[1]; result->pose[2] = g.pose[2];
@@ -366,8 +372,8 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
     CsRay r;
     r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
     int x2 = 0, y2 = 0, xp = 0, yp = 0;
+    const float2 p = points[i];  // issued before anything that depends on the pose
     if (on_map) {
-      const float2 p = points[i];
       float x2p = __fsub_rn(__fmul_rn(c, p.x), __fmul_rn(s, p.y));  // :519
       float y2p = __fadd_rn(__fmul_rn(s, p.x), __fmul_rn(c, p.y));  // :520
       xp = cs_cvt_i32(__fadd_rn(px, x2p));                          // :521
@@ -398,53 +404,12 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
   }
 }
 
-// Block-wide: glue by thread 0 (publish), then all threads prepare the n rays; exact max_ring / visits.
-#define CS_FUSE_RAYS_MAX 2048
-template <int THREADS>
-__device__ __forceinline__ void cs_publish_and_prepare(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a,
-                                                       const float2* __restrict__ points, const float* cand,
-                                                       CsDevResult* result, bool with_rays) {
-  __shared__ float sh_pose[3];
-  __shared__ float sh_cs[2];
-  __shared__ int sh_ring[THREADS / 32];
-  __shared__ long long sh_vis[THREADS / 32];
+// Glue + publish by one thread (the rays are prepared by the first blocks of the rings kernel).
+__device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
+                                           CsDevResult* result) {
   CsGlue g;
-  if (threadIdx.x == 0) {
-    cs_glue_pose(S, hdr, a, cand, g);
-    sh_pose[0] = g.pose[0]; sh_pose[1] = g.pose[1]; sh_pose[2] = g.pose[2];
-    sh_cs[0] = g.cs[0]; sh_cs[1] = g.cs[1];
-  }
-  if (!with_rays) {
-    if (threadIdx.x == 0) cs_glue_publish(S, hdr, a, result, g);
-    return;
-  }
-  __syncthreads();
-  // the other threads start on the rays while thread 0 publishes (system-scope fence + flag for the host)
-  if (threadIdx.x == 0) cs_glue_publish(S, hdr, a, result, g);
-  const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
-  const float cs[2] = {sh_cs[0], sh_cs[1]};
-  int max_ring = -1;
-  long long visits = 0;
-  cs_prepare_rays(S, points, hdr.n_points, threadIdx.x, THREADS, pose, cs, true, max_ring, visits);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    max_ring = max(max_ring, __shfl_xor_sync(0xffffffffu, max_ring, o));
-    visits += __shfl_xor_sync(0xffffffffu, visits, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    sh_ring[threadIdx.x >> 5] = max_ring;
-    sh_vis[threadIdx.x >> 5] = visits;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < THREADS / 32; w++) {
-      max_ring = max(max_ring, sh_ring[w]);
-      visits += sh_vis[w];
-    }
-    S.max_ring = max_ring;
-    S.visits = visits;
-    if (a.visits_out) *a.visits_out = visits;
-  }
+  cs_glue_pose(S, hdr, a, cand, g);
+  cs_glue_publish(S, hdr, a, result, g);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -459,6 +424,10 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ float2 s_pts[CS_SEARCH_CHUNK];
   __shared__ unsigned long long s_key[CS_SEARCH_WARPS];
 
+  // the next kernel of the step may become resident as soon as every block of this grid has started; it
+  // waits (cs_pdl_wait) for this grid's results.  This grid itself depends on the previous step's rings kernel.
+  cs_pdl_launch_dependents();
+  cs_pdl_wait();
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
   const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
@@ -555,56 +524,32 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   if (!a.fuse_publish) return;
   __syncthreads();
   if (!s_last) return;
-  // ---- the last block to finish owns the complete arg-min: Update glue, pose out, rays ------------------
+  // ---- the last block to finish owns the complete arg-min: Update glue, pose out ---------------------------
   __threadfence();
-  CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
-  cs_publish_and_prepare<CS_SEARCH_WARPS * 32>(S, hdr, a, points, cand, result,
-                                               a.fuse_rays && a.step_mode != CS_STEP_SEARCH_ONLY);
+  if (threadIdx.x == 0) {
+    CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
+    cs_publish(S, hdr, a, cand, result);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// set-up kernel: glue + ray preparation without a search kernel in front (map-only scans, cs_integrate,
-// multi-GPU searches whose arg-min is reduced between the kernels), or — rays_only, several blocks — the
-// ray preparation of scans too big for one block.
+// set-up kernel: the Update glue without a search kernel in front (map-only scans, cs_integrate, multi-GPU
+// searches whose arg-min is reduced between the kernels).  One thread per session.
 // ---------------------------------------------------------------------------------------------------
-#define CS_SETUP_THREADS 256
+#define CS_SETUP_THREADS 32
 
 __global__ void __launch_bounds__(CS_SETUP_THREADS)
 cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  cs_pdl_launch_dependents();
+  cs_pdl_wait();
   const int sj = blockIdx.y;
+  if (threadIdx.x != 0) return;
   CsSession& S = sessions[sj];
   const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
-  const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
-  if (!a.rays_only) {  // single block: glue, publish, and (small scans) the rays
-    cs_publish_and_prepare<CS_SETUP_THREADS>(S, hdr, a, points, cand, result,
-                                             a.fuse_rays && a.step_mode != CS_STEP_SEARCH_ONLY);
-    return;
-  }
-  // rays only, any number of blocks: the pose was published by an earlier kernel (which also zeroed
-  // S.visits and left S.max_ring at "unknown")
-  __shared__ float sh_pose[3];
-  __shared__ float sh_cs[2];
-  if (threadIdx.x == 0) {
-    sh_pose[0] = S.cur_pose[0]; sh_pose[1] = S.cur_pose[1]; sh_pose[2] = S.cur_pose[2];
-    sh_cs[0] = S.cur_cs[0]; sh_cs[1] = S.cur_cs[1];
-  }
-  __syncthreads();
-  const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
-  const float cs[2] = {sh_cs[0], sh_cs[1]};
-  int max_ring = -1;
-  long long visits = 0;
-  cs_prepare_rays(S, points, hdr.n_points, blockIdx.x * CS_SETUP_THREADS + threadIdx.x, gridDim.x * CS_SETUP_THREADS,
-                  pose, cs, true, max_ring, visits);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) visits += __shfl_xor_sync(0xffffffffu, visits, o);
-  if ((threadIdx.x & 31) == 0 && visits) {
-    atomicAdd((unsigned long long*)&S.visits, (unsigned long long)visits);
-    if (a.visits_out) atomicAdd((unsigned long long*)a.visits_out, (unsigned long long)visits);
-  }
+  cs_publish(S, hdr, a, cand, result);
 }
-
 
 // ---------------------------------------------------------------------------------------------------
 // rings kernel: the draw loop (:404-442).
@@ -689,45 +634,102 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   extern __shared__ int4 cs_ring_smem[];
 
   const long long t_begin = a.diag ? clock64() : 0;
-  const int sj = blockIdx.y;
-  CsSession& S = sessions[sj];
-  const int span = a.ring_span;
-  const int k_begin = blockIdx.x * span;
-  const int max_ring = S.max_ring;
-  if (k_begin > max_ring) return;
-  const int k_end = min(k_begin + span - 1, max_ring);
-  const int n = a.hdr[(size_t)sj * a.hdr_stride].n_points;
-  const int size = S.size, pitch_tiles = S.pitch_tiles;
-  const float scale = S.scale;
-  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(S.cur_pose[0], scale), 0.5f));  // :499, :505
-  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(S.cur_pose[1], scale), 0.5f));  // :500, :506
-  const int alpha = S.quality;
-  uint16_t* __restrict__ map = S.map;
-  const int4* __restrict__ rays = S.rays;
-  const int* __restrict__ batch_max = S.batch_max;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nthreads = blockDim.x;
   const int round_cap = nthreads * CS_RING_RPT;
   const unsigned lt_mask = (1u << lane) - 1u;
-
   unsigned* s_w = reinterpret_cast<unsigned*>(cs_ring_smem);            // slot -> local ray << 18 | pixval (0 .. 2*65500 + carries: 18 bits); later: batch mask
   unsigned* s_c = s_w + CS_RING_SLOTS;                                   // slot -> contested visits | mixed marks << 16; later: hand-off word
   int4* s_rays = reinterpret_cast<int4*>(s_c + CS_RING_SLOTS);           // this round's packed rays
   int* s_lpv = reinterpret_cast<int*>(s_rays + round_cap);               // pixvals of the visits of mixed cells
+  {  // the counters start at zero; done before the dependency wait, so it overlaps the previous kernel's tail
+    uint4* c4 = reinterpret_cast<uint4*>(s_c);
+    for (int i = tid; i < CS_RING_SLOTS / 4; i += nthreads) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  cs_pdl_launch_dependents();  // the next step's search may become resident once every block here has started
+  cs_pdl_wait();               // the pose (search / set-up kernel) is final from here on
 
-  for (int i = tid; i < CS_RING_SLOTS; i += nthreads) s_c[i] = 0u;
+  const int sj = blockIdx.y;
+  CsSession& S = sessions[sj];
+  const int span = a.ring_span;
+  const int k_begin = blockIdx.x * span;
+  const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
+  const int n = hdr.n_points;
+  const int size = S.size, pitch_tiles = S.pitch_tiles;
+  const float scale = S.scale;
+  const float pose_x = S.cur_pose[0], pose_y = S.cur_pose[1];
+  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
+  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
+  const int alpha = S.quality;
+  uint16_t* __restrict__ map = S.map;
+  const int4* rays = S.rays;
+  const int* batch_max = S.batch_max;
+
+  // ---- ray preparation (UpdateHoleMap :517-530, ClipRay, the prologue of DrawLaserRayOnHoleMap): the first
+  // blocks of the grid take one ray per thread, publish max_ring / visits, and raise prep_done; every block
+  // waits for all of them.  Blocks are dispatched in index order, so the preparing blocks are resident before
+  // any block can wait on them.
+  const int nprep = (n + nthreads - 1) / nthreads;
+  if ((int)blockIdx.x < nprep) {
+    __shared__ int sh_ring[CS_RING_MAX_THREADS / 32];
+    __shared__ long long sh_vis[CS_RING_MAX_THREADS / 32];
+    const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
+    const float pose[3] = {pose_x, pose_y, S.cur_pose[2]};
+    const float cs[2] = {S.cur_cs[0], S.cur_cs[1]};
+    int mr = -1;
+    long long vis = 0;
+    cs_prepare_rays(S, points, n, blockIdx.x * nthreads + tid, nprep * nthreads, pose, cs, true, mr, vis);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+      vis += __shfl_xor_sync(0xffffffffu, vis, o);
+    }
+    if (lane == 0) { sh_ring[warp] = mr; sh_vis[warp] = vis; }
+    __threadfence();  // this thread's ray stores are visible device-wide before the block's arrival is counted
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < (nthreads >> 5); w++) { mr = max(mr, sh_ring[w]); vis += sh_vis[w]; }
+      unsigned* pw = reinterpret_cast<unsigned*>(&S.prep_word);  // little endian: [0] = count, [1] = max_ring + 1
+      atomicMax(pw + 1, (unsigned)(mr + 1));
+      if (vis) {
+        atomicAdd((unsigned long long*)&S.visits, (unsigned long long)vis);
+        if (a.visits_out) atomicAdd((unsigned long long*)a.visits_out, (unsigned long long)vis);
+      }
+      __threadfence();
+      atomicAdd(pw, 1u);
+    }
+  }
+  __shared__ int sh_max_ring;
+  if (tid == 0) {
+    volatile unsigned long long* pw = &S.prep_word;
+    unsigned long long w;
+    while ((unsigned)((w = *pw) & 0xffffffffull) < (unsigned)nprep) __nanosleep(20);
+    __threadfence();
+    sh_max_ring = (int)(unsigned)(w >> 32) - 1;  // every block's max was merged before its count
+  }
+  __syncthreads();
+  const int max_ring = sh_max_ring;
+  if (k_begin > max_ring) return;
+  const int k_end = min(k_begin + span - 1, max_ring);
 
   for (int round0 = 0; round0 < n; round0 += round_cap) {
     const int round_n = min(round_cap, n - round0);
     if (round0 > 0) __syncthreads();  // previous round: stores done, shared arrays free
-    for (int i = tid; i < round_n; i += nthreads) s_rays[i] = __ldg(rays + round0 + i);
+    for (int i = tid; i < round_n; i += nthreads) s_rays[i] = __ldcg(rays + round0 + i);  // written during this kernel: L2
     int bmax[CS_RING_RPT];
 #pragma unroll
     for (int j = 0; j < CS_RING_RPT; j++) {
       const int unit = warp * CS_RING_RPT + j;
-      bmax[j] = (unit * 32 < round_n) ? __ldg(batch_max + (round0 >> 5) + unit) : -1;
+      bmax[j] = (unit * 32 < round_n) ? __ldcg(batch_max + (round0 >> 5) + unit) : -1;
     }
     __syncthreads();
+
+    // read-modify-writes whose load is in flight (see 3a)
+    bool pend[CS_RING_RPT];
+    uint32_t pend_cell[CS_RING_RPT];
+    int pend_v[CS_RING_RPT], pend_pv[CS_RING_RPT];
+#pragma unroll
+    for (int j = 0; j < CS_RING_RPT; j++) { pend[j] = false; pend_cell[j] = 0; pend_v[j] = 0; pend_pv[j] = 0; }
 
     for (int k = k_begin; k <= k_end; k++) {
       int pos[CS_RING_RPT], pv[CS_RING_RPT];
@@ -744,8 +746,29 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         }
       }
       // rings longer than the slot table (k > 1024) are handled in windows of CS_RING_SLOTS positions
-      const int nwin = (8 * k + CS_RING_SLOTS - 1) / CS_RING_SLOTS;
-      for (int win = 0; win < max(nwin, 1); win++) {
+      const int nwin = max((8 * k + CS_RING_SLOTS - 1) / CS_RING_SLOTS, 1);
+      bool warp_dead = true;
+#pragma unroll
+      for (int j = 0; j < CS_RING_RPT; j++) warp_dead = warp_dead && (bmax[j] < k);
+      if (warp_dead) {
+        // none of this warp's rays reaches ring k (nor any later ring): it only keeps the block's barrier
+        // sequence — A, B(or), then C(or) on contested rings, then D, E, F on rings with mixed cells
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          if (pend[j]) __stcg(map + pend_cell[j], (uint16_t)cs_blend(pend_v[j], pend_pv[j], alpha));
+          pend[j] = false;
+        }
+        for (int win = 0; win < nwin; win++) {
+          __syncthreads();
+          if (!__syncthreads_or(0)) continue;
+          if (!__syncthreads_or(0)) continue;
+          __syncthreads();
+          __syncthreads();
+          __syncthreads();
+        }
+        continue;
+      }
+      for (int win = 0; win < nwin; win++) {
         bool act[CS_RING_RPT], owner[CS_RING_RPT];
         unsigned word[CS_RING_RPT];
         int h[CS_RING_RPT];
@@ -759,6 +782,12 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
             word[j] = ((unsigned)li << 18) | ((unsigned)pv[j] & 0x3ffffu);
             s_w[h[j]] = word[j];
           }
+        }
+        // the previous fast ring's loads have had this ring's evaluation to arrive: blend and store them
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          if (pend[j]) __stcg(map + pend_cell[j], (uint16_t)cs_blend(pend_v[j], pend_pv[j], alpha));
+          pend[j] = false;
         }
         __syncthreads();
         // ---- 2. owners are the lanes that read their own word back; the others mark the slot ---------------
@@ -776,14 +805,18 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
           }
         }
         if (!__syncthreads_or(contested)) {
-          // ---- 3a. no cell is visited twice in this round: plain read-modify-write --------------------------
-          int v[CS_RING_RPT];
+          // ---- 3a. no cell is visited twice in this round: plain read-modify-write.  The loads are issued
+          // now; the blend and the store follow after the next ring's evaluation (different rings never
+          // share a cell), so the L2 / HBM latency overlaps it.
 #pragma unroll
-          for (int j = 0; j < CS_RING_RPT; j++)
-            if (act[j]) v[j] = (int)__ldcg(map + cell[j]);
-#pragma unroll
-          for (int j = 0; j < CS_RING_RPT; j++)
-            if (act[j]) __stcg(map + cell[j], (uint16_t)cs_blend(v[j], pv[j], alpha));
+          for (int j = 0; j < CS_RING_RPT; j++) {
+            pend[j] = act[j];
+            if (act[j]) {
+              pend_v[j] = (int)__ldcg(map + cell[j]);
+              pend_cell[j] = cell[j];
+              pend_pv[j] = pv[j];
+            }
+          }
           continue;
         }
         // ---- 3b. contested cells with one pixval: the owner applies it count+1 times -------------------------
@@ -885,6 +918,10 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         }
       }
     }
+    // complete the deferred read-modify-writes before the next round may touch the same cells
+#pragma unroll
+    for (int j = 0; j < CS_RING_RPT; j++)
+      if (pend[j]) __stcg(map + pend_cell[j], (uint16_t)cs_blend(pend_v[j], pend_pv[j], alpha));
   }
   if (a.diag && tid == 0) a.diag[(size_t)blockIdx.x * 8] = clock64() - t_begin;
 }
