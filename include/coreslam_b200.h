@@ -163,10 +163,14 @@ cs_status cs_get_timing(cs_processor* h, cs_timing* t);
 cs_status cs_get_distances(cs_processor* h, int32_t* distances, int32_t count); /* needs CS_FLAG_KEEP_DISTANCES */
 cs_status cs_get_rays(cs_processor* h, int32_t* rays, int32_t n_points);         /* x1,y1,x2,y2,xp,yp of the last integration (CS_FLAG_DEBUG_RAYS) */
 cs_status cs_get_visits(cs_processor* h, int64_t* visits);   /* cells written by the last integration (waits for it) */
-/* Diagnostics: per ring of the last rings kernel, 8 cycle stamps since the ring's block started:
- * [0] end, [4] session loaded, [5] table cleared, [6] rays loaded, [7] cells evaluated, [1] groups formed,
- * [2] table built, [3] blends applied.  The first call enables the recording (and returns nothing);
- * later calls copy `count` values (ring r at 8*r). */
+/* Diagnostics (timeline of the last step; the first call enables the recording and returns nothing, later calls
+ * copy `count` values).  Records of 8 int64 each:
+ *   record b < Size             block b of the rings kernel: [0] cycles start->end, [1] SM id, then %globaltimer
+ *                               (ns) at [2] start, [3] dependency wait over, [4] ray preparation seen, [5] rays in
+ *                               shared memory, [6] end
+ *   record Size + b, b < 8192   block b of the search kernel: [0] SM id, %globaltimer at [1] start, [2] dependency
+ *                               wait over, [3] scan staged, [4] warp 0 done, [5] block done, [6] pose published
+ *                               (last block only), [7] 1 for the block that published */
 cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count);
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches);              /* kernels launched so far by this handle */
 

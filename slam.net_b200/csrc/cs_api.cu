@@ -29,6 +29,7 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr size_t kHdrBytes = 64;
+constexpr int kRayCopies = 8;  // copies of the per-ray draw parameters of a stand-alone session (see CsSession::rays)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -54,8 +55,10 @@ struct cs_processor {
   uint16_t* d_map = nullptr;
   uint16_t* d_linear = nullptr;  // lazily allocated row-major scratch for upload/download
   uint8_t* d_packed = nullptr;
-  int4* d_rays = nullptr;
-  int* d_batch_max = nullptr;
+  int4* d_rays = nullptr;       // kRayCopies copies of ray_stride entries
+  int* d_batch_max = nullptr;   // kRayCopies copies of batch_stride entries
+  unsigned long long* d_prep_words = nullptr;
+  int ray_stride = 0, batch_stride = 0;
   int* d_ray_dbg = nullptr;
   int* d_distances = nullptr;
   long long* d_ring_cycles = nullptr;
@@ -83,6 +86,7 @@ struct cs_processor {
   int pending_points = 0, pending_rings = 0;
 
   uint64_t launches = 0;
+  unsigned step_counter = 0;
   Timing tm;
   cs_timing last_timing{};
   std::string error;
@@ -194,13 +198,61 @@ double max_range_of(const float* points, int n) {
 
 // What a step is launched on: one processor (n_sessions = 1) or a batch of independent sessions
 // (grid.y = n_sessions; every kernel indexes its session by blockIdx.y).
+// Experiment knobs (environment, read once): CS_TUNE_SEARCH_WARPS (2/4/8), CS_TUNE_RING_SPAN, CS_TUNE_RING_THREADS.
+// Unset = the built-in choice.  They change launch shapes only, never results.
+struct Tune {
+  int search_warps = 0, ring_span = 0, ring_threads = 0;
+  Tune() {
+    auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
+    search_warps = geti("CS_TUNE_SEARCH_WARPS");
+    ring_span = geti("CS_TUNE_RING_SPAN");
+    ring_threads = geti("CS_TUNE_RING_THREADS");
+  }
+};
+const Tune& tune() { static Tune t; return t; }
+
+int device_sm_count(int device) {
+  static int cache[64] = {0};
+  if (device < 0 || device >= 64) return 148;
+  if (!cache[device]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    cache[device] = n;
+  }
+  return cache[device];
+}
+
+// Warps (= candidates) per block of the search kernel.  All blocks of one scan are resident at once, and a
+// warp's run time is fixed by the scan, so the kernel ends when the SM with the most warps ends: pick the
+// block size whose busiest SM carries the fewest warps (4097 candidates on 148 SMs: 8 warps -> 4 blocks = 32
+// warps on some SMs against 27.7 on average; 4 warps -> 7 blocks = 28).  Bigger blocks win ties (the scan is
+// staged once per block).
+int cs_search_warps(long long cand_count, int n_sessions, int num_sms) {
+  if (tune().search_warps == 2 || tune().search_warps == 4 || tune().search_warps == 8) return tune().search_warps;
+  const long long total = cand_count * (long long)n_sessions;
+  if (total > (long long)num_sms * 40) return CS_SEARCH_WARPS;  // more than one wave anyway
+  int best = CS_SEARCH_WARPS;
+  long long best_cost = -1;
+  for (int w = CS_SEARCH_WARPS; w >= 2; w >>= 1) {
+    const long long blocks = ((cand_count + w - 1) / w) * n_sessions;
+    const long long per_sm = (blocks + num_sms - 1) / num_sms;
+    if (per_sm > 16) continue;  // keep the whole grid resident (shared memory: 16 x 16 KB)
+    const long long cost = per_sm * w;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = w; }
+  }
+  return best;
+}
+
 struct LaunchCtx {
+  int num_sms;
   cudaStream_t stream;
   CsSession* d_sess;
   bool tiled;
   int n_sessions;
   uint64_t* launches;
+  unsigned* step_counter;  // source of CsStepArgs::step_id
   long long* diag;
+  int diag_rings;
   cudaEvent_t ev_pose;   // optional: recorded once the pose is out
   cudaEvent_t ev_done;   // optional: recorded after the rings kernel
 };
@@ -237,11 +289,22 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   a.fuse_publish = fused ? 1 : 0;
   a.max_ring_hint = rings - 1;
   a.diag = c.diag;
+  a.diag_rings = c.diag_rings;
+  if (phases & CS_PHASE_FINISH) {  // a call that publishes a pose takes the next step id: never 0, alternating parity
+    if (++(*c.step_counter) == 0) *c.step_counter = 2;
+    a.step_id = *c.step_counter;
+  }
   cudaError_t e = cudaSuccess;
   if ((phases & CS_PHASE_SEARCH) && searching) {
-    dim3 grid((unsigned)((a.cand_count + CS_SEARCH_WARPS - 1) / CS_SEARCH_WARPS), (unsigned)c.n_sessions);
+    const int warps = cs_search_warps(a.cand_count, c.n_sessions, c.num_sms);
+    dim3 grid((unsigned)((a.cand_count + warps - 1) / warps), (unsigned)c.n_sessions);
+    int chunk = (n_points + 1) & ~1;  // even: the staging loop moves two points per 16-byte load
+    if (chunk > CS_SEARCH_CHUNK) chunk = CS_SEARCH_CHUNK;
+    if (chunk < 2) chunk = 2;
+    a.search_chunk = chunk;
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(cs_search_kernel<decltype(T)::value>, grid, dim3(CS_SEARCH_WARPS * 32), 0, c.stream, c.d_sess, a);
+      e = launch_pdl(cs_search_kernel<decltype(T)::value>, grid, dim3(warps * 32), (size_t)chunk * sizeof(float2), c.stream,
+                     c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -256,16 +319,27 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   if (c.ev_pose) cudaEventRecord(c.ev_pose, c.stream);
   if (draws) {
     int threads = ((n_points + CS_RING_RPT - 1) / CS_RING_RPT + 31) / 32 * 32;
+    if (tune().ring_threads >= 32) threads = tune().ring_threads / 32 * 32;
     if (threads < 32) threads = 32;
     if (threads > CS_RING_MAX_THREADS) threads = CS_RING_MAX_THREADS;
     if (rings < 1) rings = 1;
-    // rings per block: enough blocks to fill the chip about twice when one session runs alone
-    int span = c.n_sessions > 1 ? 8 : (rings + 2 * 296 - 1) / (2 * 296);
+    // One session alone: a grid of at most one resident wave (2 blocks per SM) whose blocks draw work units of
+    // `span` rings from a ticket counter.  A batch of sessions: one unit of 8 rings per block, grid.y = sessions.
+    const bool dynamic = c.n_sessions == 1;
+    int span = dynamic ? 1 : 8;
+    if (tune().ring_span > 0) span = tune().ring_span;
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
     a.ring_span = span;
+    a.ring_dynamic = dynamic ? 1 : 0;
     int blocks = (rings + span - 1) / span;
-    const int nprep = (n_points + threads - 1) / threads;  // the first blocks also prepare the rays
+    if (dynamic && blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
+    // the first blocks also prepare the rays, 128 each (one warp per SM sub-partition: the preparation is a
+    // latency chain, not throughput); big scans use bigger groups so that at most 64 blocks prepare
+    int group = (((n_points + 63) / 64) + 31) / 32 * 32;
+    if (group < 128) group = 128;
+    a.prep_group = group;
+    const int nprep = (n_points + group - 1) / group;
     if (blocks < nprep) blocks = nprep;
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_rings_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
@@ -280,12 +354,15 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
 
 cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base, int phases = CS_PHASE_ALL) {
   LaunchCtx c{};
+  c.num_sms = device_sm_count(h->device);
   c.stream = h->stream;
   c.d_sess = h->d_sess;
   c.tiled = h->tiled;
   c.n_sessions = 1;
   c.launches = &h->launches;
+  c.step_counter = &h->step_counter;
   c.diag = h->d_ring_cycles;
+  c.diag_rings = h->size;
   a.hdr_stride = 1;
   const bool want_pose_event = timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN));
   c.ev_pose = (want_pose_event && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 0] : nullptr;
@@ -418,8 +495,12 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_map, h->map_cells * sizeof(uint16_t)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_sess, sizeof(CsSession)));
   if (cfg->flags & CS_FLAG_DEBUG_RAYS) CS_CREATE_CUDA(cudaMalloc(&h->d_ray_dbg, (size_t)max_points * 6 * sizeof(int)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)max_points * sizeof(int4)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, ((size_t)max_points / 32 + 1) * sizeof(int)));
+  h->ray_stride = (max_points + 31) / 32 * 32;
+  h->batch_stride = (h->ray_stride / 32 + 31) / 32 * 32;  // whole 128-byte lines per copy
+  CS_CREATE_CUDA(cudaMalloc(&h->d_rays, (size_t)kRayCopies * h->ray_stride * sizeof(int4)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, (size_t)kRayCopies * h->batch_stride * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_prep_words, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
+  CS_CREATE_CUDA(cudaMemset(h->d_prep_words, 0, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -473,6 +554,10 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   s.seed = cfg->seed;
   s.rays = h->d_rays;
   s.batch_max = h->d_batch_max;
+  s.ray_copies = kRayCopies;
+  s.ray_stride = h->ray_stride;
+  s.batch_stride = h->batch_stride;
+  s.prep_words = h->d_prep_words;
   s.ray_dbg = h->d_ray_dbg;
   s.distances = (cfg->flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
   cs_status st = cs_reset(h);
@@ -494,6 +579,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_sess);
   cudaFree(h->d_rays);
   cudaFree(h->d_batch_max);
+  cudaFree(h->d_prep_words);
   cudaFree(h->d_ray_dbg);
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
@@ -514,9 +600,10 @@ cs_status cs_reset(cs_processor* h) {  // CoreSLAMProcessor.cs:167-175
   for (int k = 0; k < 3; k++) s.state[0].pose[k] = h->cfg.start_pose[k];  // :172
   s.state[0].scan_count = 0;                                               // :174 (lastOdometryPose = 0, :173)
   s.key[0] = s.key[1] = ~0ull;
-  s.prep_word = 0ull;
   s.search_done = 0;
-  s.visits = 0;
+  s.visits_slot[0] = s.visits_slot[1] = 0;
+  s.ring_ticket[0] = s.ring_ticket[1] = 0;
+  memset(s.ll_pose, 0, sizeof(s.ll_pose));
   h->parity = 0;
   h->scan_count = 0;
   h->update_count = 0;
@@ -663,7 +750,7 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
   if (st != CS_OK) return st;
   if (visits) {
     long long v = 0;
-    CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+    CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits_slot) + (h->step_counter & 1u) * sizeof(long long), sizeof(v),
                                cudaMemcpyDeviceToHost, h->stream));
     CS_CUDA(h, cudaStreamSynchronize(h->stream));
     *visits = v;
@@ -730,7 +817,7 @@ static cs_status complete_update(cs_processor* h, const CsStepArgs& a, bool timi
     out->visits = -1;  // counted on the device while the integration runs; cs_get_visits() after cs_sync()
     if (timing) {
       long long v = 0;
-      CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+      CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits_slot) + (h->step_counter & 1u) * sizeof(long long), sizeof(v),
                                  cudaMemcpyDeviceToHost, h->stream));
       CS_CUDA(h, cudaStreamSynchronize(h->stream));
       out->visits = v;
@@ -903,7 +990,7 @@ cs_status cs_get_visits(cs_processor* h, int64_t* visits) {
   CS_CHECK_HANDLE(h);
   if (!visits) return fail(h, CS_ERR_INVALID_ARGUMENT, "null visits");
   long long v = 0;
-  CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits), sizeof(v),
+  CS_CUDA(h, cudaMemcpyAsync(&v, reinterpret_cast<uint8_t*>(h->d_sess) + offsetof(CsSession, visits_slot) + (h->step_counter & 1u) * sizeof(long long), sizeof(v),
                              cudaMemcpyDeviceToHost, h->stream));
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
   *visits = v;
@@ -912,10 +999,11 @@ cs_status cs_get_visits(cs_processor* h, int64_t* visits) {
 
 cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count) {
   CS_CHECK_HANDLE(h);
-  if (count < 0 || count > h->size * 8) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
+  const size_t slots = ((size_t)h->size + CS_DIAG_SEARCH_BLOCKS) * 8;
+  if (count < 0 || (size_t)count > slots) return fail(h, CS_ERR_INVALID_ARGUMENT, "bad count");
   if (!h->d_ring_cycles) {  // first call switches the diagnostics on
-    CS_CUDA(h, cudaMalloc(&h->d_ring_cycles, (size_t)h->size * 8 * sizeof(long long)));
-    CS_CUDA(h, cudaMemsetAsync(h->d_ring_cycles, 0, (size_t)h->size * 8 * sizeof(long long), h->stream));
+    CS_CUDA(h, cudaMalloc(&h->d_ring_cycles, slots * sizeof(long long)));
+    CS_CUDA(h, cudaMemsetAsync(h->d_ring_cycles, 0, slots * sizeof(long long), h->stream));
     h->hs.ring_cycles = h->d_ring_cycles;
     return patch_session(h, offsetof(CsSession, ring_cycles), &h->hs.ring_cycles, sizeof(long long*));
   }
@@ -1093,6 +1181,7 @@ struct cs_batch {
   uint16_t* d_linear = nullptr;
   int4* d_rays = nullptr;
   int* d_batch_max = nullptr;
+  unsigned long long* d_prep_words = nullptr;
   unsigned long long* d_checksum = nullptr;
   // staging: [n headers][n * max_points points][n * n_cand offsets]
   size_t off_points = 0, off_cand = 0, stage_bytes = 0;
@@ -1103,6 +1192,7 @@ struct cs_batch {
   int parity = 0, scan_count = 0, search_begin = 5;
   unsigned update_count = 0;
   uint64_t launches = 0;
+  unsigned step_counter = 0;
   std::string error;
   bool poisoned = false;
 };
@@ -1136,11 +1226,13 @@ cs_status bfail(cs_batch* b, cs_status code, const char* fmt, ...) {
 
 LaunchCtx batch_ctx(cs_batch* b) {
   LaunchCtx c{};
+  c.num_sms = device_sm_count(b->device);
   c.stream = b->stream;
   c.d_sess = b->d_sess;
   c.tiled = b->tiled;
   c.n_sessions = b->n;
   c.launches = &b->launches;
+  c.step_counter = &b->step_counter;
   return c;
 }
 
@@ -1151,9 +1243,10 @@ void batch_reset_host(cs_batch* b, const cs_config* cfgs) {
     if (cfgs)
       for (int k = 0; k < 3; k++) s.state[0].pose[k] = cfgs[j].start_pose[k];
     s.key[0] = s.key[1] = ~0ull;
-    s.prep_word = 0ull;
     s.search_done = 0;
-    s.visits = 0;
+    s.visits_slot[0] = s.visits_slot[1] = 0;
+    s.ring_ticket[0] = s.ring_ticket[1] = 0;
+    memset(s.ll_pose, 0, sizeof(s.ll_pose));
   }
   b->parity = 0;
   b->scan_count = 0;
@@ -1212,6 +1305,8 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_sess, sizeof(CsSession) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_rays, (size_t)b->max_points * sizeof(int4) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_batch_max, ((size_t)b->max_points / 32 + 1) * sizeof(int) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_prep_words, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemset(b->d_prep_words, 0, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_stage, b->stage_bytes, cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
@@ -1245,6 +1340,10 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
     s.seed = cfgs[j].seed;
     s.rays = b->d_rays + (size_t)j * b->max_points;
     s.batch_max = b->d_batch_max + (size_t)j * ((size_t)b->max_points / 32 + 1);
+    s.ray_copies = 1;  // a session of a batch has few blocks: nothing to spread
+    s.ray_stride = b->max_points;
+    s.batch_stride = b->max_points / 32 + 1;
+    s.prep_words = b->d_prep_words + (size_t)j * 2 * 16;
   }
   batch_reset_host(b, cfgs);
   cs_fill_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_maps, b->map_cells * (size_t)n_sessions,
@@ -1269,6 +1368,7 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_sess);
   cudaFree(b->d_rays);
   cudaFree(b->d_batch_max);
+  cudaFree(b->d_prep_words);
   cudaFree(b->d_checksum);
   cudaFree(b->d_stage);
   cudaFree(b->d_results);

@@ -88,19 +88,29 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   unsigned long long seed;
   CsState state[2];            // state[parity] is current; an Update writes state[parity^1] and the host flips parity
   unsigned long long key[2];   // packed (distance << 32 | flat index) arg-min; key[parity] belongs to the current step
-  int4* rays;                  // packed per-ray draw parameters of the current integration (capacity max_points)
-  int* batch_max;              // per 32 consecutive rays: largest dxc of a valid ray, -1 if none
+  int4* rays;                  // packed per-ray draw parameters of the current integration: ray_copies copies of
+                               // ray_stride entries each (every SM reads the copy smid % ray_copies, so the lines the
+                               // whole grid wants at the same instant are spread over several L2 slices)
+  int* batch_max;              // per 32 consecutive rays: largest dxc of a valid ray, -1 if none; ray_copies copies of
+                               // batch_stride entries
+  int ray_copies, ray_stride, batch_stride, pad1;
+  unsigned long long* prep_words;  // [2 slots][ray_copies] words, 128 B apart: preparing blocks of the rings kernel that are
+                                   // done; slot = step id & 1, re-armed for the next step by this step's publishing thread
   int* ray_dbg;                // optional 6 ints per ray (x1,y1,x2,y2,xp,yp), CS_FLAG_DEBUG_RAYS
   int* distances;              // optional n_cand+1
   long long* ring_cycles;      // optional diagnostics: cycles each ring's block spent in the rings kernel
   float cur_pose[3];           // pose the current integration draws from (Pose after :745-747)
   float cur_cs[2];             // its (cos, sin), unscaled
   unsigned search_done;        // blocks of the running search kernel that have finished
-  int pad0;
-  // one 8-byte word, read with a single load by the rings kernel's blocks: {prep_done, max_ring}
-  unsigned long long prep_word;  // low 32: blocks of the rings kernel that have prepared their rays; high 32: max_ring + 1
-                                 // (max_ring = largest dxc of a valid ray, -1: nothing to draw)
-  long long visits;            // cells written by the current integration = sum over valid rays of dxc+1
+  unsigned pad0;
+  // The pose the current integration draws from, published without a fence: five 8-byte words {float bits, step id},
+  // each single-copy atomic — x, y, theta (Pose after :745-747), cos, sin (unscaled).  The rings kernel's blocks are
+  // resident before the search ends and poll the words for their step id.
+  unsigned long long ll_pose[5];
+  unsigned long long pad2;
+  long long visits_slot[2];    // cells written by the integration of step id & 1 = sum over valid rays of dxc+1
+  unsigned ring_ticket[2];     // work-unit tickets of the rings kernel; slot = step id & 1, re-armed for the next step by
+                               // the publishing thread of this step
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
@@ -121,9 +131,15 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int cand_count;  // number of flat indices evaluated by this GPU, normally n_cand+1
   int fuse_publish;  // search kernel: its last block runs the Update glue and publishes the pose
   int max_ring_hint; // rings the host launched blocks for, minus one
-  int ring_span;     // rings per block of the rings kernel
+  int ring_span;     // rings per work unit of the rings kernel
+  int prep_group;    // rays prepared by each of the first blocks of the rings kernel (multiple of 32)
+  int ring_dynamic;  // 1: blocks draw further units from CsSession::ring_ticket (one session, grid <= one wave)
+  int search_chunk;  // points staged in shared memory per pass of the search kernel (<= CS_SEARCH_CHUNK)
+  unsigned step_id;  // nonzero, different for consecutive steps on the same session(s): tags ll_pose, selects the counter slots
   long long* visits_out;  // optional device slot that receives the visit count
-  long long* diag;        // optional diagnostics buffer (8 values per ring), see cs_get_ring_cycles
+  long long* diag;        // optional diagnostics buffer (8 values per block of the rings kernel, then 8 per block of
+                          // the search kernel), see cs_get_ring_cycles
+  int diag_rings;         // records reserved for the rings kernel in diag
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -144,6 +160,11 @@ __device__ __forceinline__ uint32_t cs_cell_offset(int x, int y, int size, int p
 // predecessor drains; it must not touch the predecessor's results before cs_pdl_wait()
 __device__ __forceinline__ void cs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void cs_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// diagnostics only (a.diag != nullptr): wall-clock stamps and the SM a block ran on
+__device__ __forceinline__ long long cs_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+#define CS_DIAG_SEARCH_BLOCKS 8192  // search-kernel timeline records kept after the per-ring records
 
 // wrapping int32 arithmetic (C# unchecked)
 __device__ __forceinline__ int cs_wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
@@ -301,7 +322,7 @@ struct CsGlue {
 
 // pure part: which pose does this step end on (no side effects)
 __device__ __forceinline__ void cs_glue_pose(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
-                                             CsGlue& g) {
+                                             unsigned long long key, CsGlue& g) {
   g.dist = 2147483647; g.index = 0; g.searched = 0;
   bool have_cs = false;
   if (a.step_mode == CS_STEP_INTEGRATE_ONLY) {
@@ -311,7 +332,6 @@ __device__ __forceinline__ void cs_glue_pose(CsSession& S, const CsStepHeader& h
     float sp[3];
     cs_search_pose(S, hdr, a, sp);
     if (a.do_search) {
-      const unsigned long long key = atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
       g.dist = (int)(unsigned)(key >> 32);
       g.index = (int)(unsigned)(key & 0xffffffffu);
       g.searched = 1;
@@ -326,7 +346,7 @@ __device__ __forceinline__ void cs_glue_pose(CsSession& S, const CsStepHeader& h
 
 // side effects: processor state, arg-min re-arm, result record + flag, session scratch for the integration
 __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a,
-                                                CsDevResult* result, const CsGlue& g) {
+                                                CsDevResult* result, const CsGlue& g, long long* d = nullptr) {
   if (a.step_mode == CS_STEP_UPDATE) {
     const CsState& st0 = S.state[a.parity];
     CsState& st1 = S.state[a.parity ^ 1];
@@ -337,10 +357,27 @@ __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader
   } else if (a.step_mode == CS_STEP_SEARCH_ONLY) {
     S.key[a.parity] = ~0ull;  // re-arm in place
   }
+  // device-side consumers first: the rings kernel of this step is already resident and polls these words
+  {
+    const unsigned long long tag = (unsigned long long)a.step_id << 32;
+    volatile unsigned long long* ll = S.ll_pose;
+    ll[0] = tag | __float_as_uint(g.pose[0]);
+    ll[1] = tag | __float_as_uint(g.pose[1]);
+    ll[2] = tag | __float_as_uint(g.pose[2]);
+    ll[3] = tag | __float_as_uint(g.cs[0]);
+    ll[4] = tag | __float_as_uint(g.cs[1]);
+  }
+  if (d) d[2] = cs_globaltimer();
   S.cur_pose[0] = g.pose[0]; S.cur_pose[1] = g.pose[1]; S.cur_pose[2] = g.pose[2];
   S.cur_cs[0] = g.cs[0]; S.cur_cs[1] = g.cs[1];
-  S.prep_word = 0ull;  // raised by the rings kernel's ray preparation
-  S.visits = 0;
+  // re-arm the NEXT step's counters (kernel boundaries order this before that step's rings kernel; this step's
+  // were re-armed by the previous step's publisher, or are zero from the start)
+  {
+    const unsigned nslot = (a.step_id + 1u) & 1u;
+    S.ring_ticket[nslot] = 0u;
+    S.visits_slot[nslot] = 0;
+    for (int c = 0; c < S.ray_copies; c++) S.prep_words[((size_t)nslot * S.ray_copies + c) * 16] = 0ull;
+  }
   if (result) {
     result->pose[0] = g.pose[0]; result->pose[1] = g.pose[1]; result->pose[2] = g.pose[2];
     result->distance = g.dist;
@@ -356,9 +393,9 @@ __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader
 
 // Per-ray part of UpdateHoleMap (:517-530) + ClipRay + the prologue of DrawLaserRayOnHoleMap for rays
 // first, first+stride, ... < n.  Returns this thread's (max dxc, visits) contribution.
-__device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __restrict__ points, int n, int first, int stride,
-                                                const float pose[3], const float cs[2], bool write_dbg,
-                                                int& max_ring, long long& visits) {
+__device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __restrict__ points, float2 p_first, int n, int first,
+                                                int stride, const float pose[3], const float cs[2], bool write_dbg,
+                                                long long& visits) {
   const float scale = S.scale;
   const int size = S.size;
   const float px = __fadd_rn(__fmul_rn(pose[0], scale), 0.5f);  // :499
@@ -372,7 +409,7 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
     CsRay r;
     r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
     int x2 = 0, y2 = 0, xp = 0, yp = 0;
-    const float2 p = points[i];  // issued before anything that depends on the pose
+    const float2 p = (i == first) ? p_first : points[i];  // the first one was loaded while the pose was awaited
     if (on_map) {
       float x2p = __fsub_rn(__fmul_rn(c, p.x), __fmul_rn(s, p.y));  // :519
       float y2p = __fadd_rn(__fmul_rn(s, p.x), __fmul_rn(c, p.y));  // :520
@@ -386,16 +423,17 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
       x2 = cs_cvt_i32(__fadd_rn(px, x2p));                          // :529
       y2 = cs_cvt_i32(__fadd_rn(py, y2p));                          // :530
       r = cs_make_ray(size, x1, y1, x2, y2, xp, yp);
-      if (r.flags & 1) {
-        max_ring = max(max_ring, r.dxc);
-        visits += (long long)r.dxc + 1;
-      }
+      if (r.flags & 1) visits += (long long)r.dxc + 1;
     }
-    S.rays[i] = cs_pack_ray(r);
+    {
+      const int4 q = cs_pack_ray(r);
+      for (int c = 0; c < S.ray_copies; c++) S.rays[(size_t)c * S.ray_stride + i] = q;
+    }
     {  // the 32 lanes of a warp hold 32 consecutive rays (first and stride are multiples of 32 apart)
       int bm = (r.flags & 1) ? r.dxc : -1;
       bm = __reduce_max_sync(__activemask(), bm);
-      if ((i & 31) == 0) S.batch_max[i >> 5] = bm;
+      if ((i & 31) == 0)
+        for (int c = 0; c < S.ray_copies; c++) S.batch_max[(size_t)c * S.batch_stride + (i >> 5)] = bm;
     }
     if (write_dbg && S.ray_dbg) {
       int* d = S.ray_dbg + 6 * (size_t)i;
@@ -406,28 +444,48 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
 
 // Glue + publish by one thread (the rays are prepared by the first blocks of the rings kernel).
 __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
-                                           CsDevResult* result) {
+                                           CsDevResult* result, bool have_guess = false, unsigned long long guess = 0ull) {
+  long long* d = (a.diag && blockIdx.y == 0) ? a.diag + ((size_t)a.diag_rings + CS_DIAG_SEARCH_BLOCKS - 1) * 8 : nullptr;
+  if (d) d[0] = cs_globaltimer();
+  const bool need_key = a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search;
+  unsigned long long key = 0ull;
+  if (need_key) key = atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
   CsGlue g;
-  cs_glue_pose(S, hdr, a, cand, g);
-  cs_glue_publish(S, hdr, a, result, g);
+  if (have_guess && need_key) {
+    // The arg-min as this thread last saw it is almost always the final one: the glue arithmetic runs on it while
+    // the read above is in flight, and is redone only if the final key differs.
+    cs_glue_pose(S, hdr, a, cand, guess, g);
+    if (key != guess) cs_glue_pose(S, hdr, a, cand, key, g);
+  } else {
+    cs_glue_pose(S, hdr, a, cand, key, g);
+  }
+  if (d) d[1] = cs_globaltimer();
+  cs_glue_publish(S, hdr, a, result, g, d);
+  if (d) d[3] = cs_globaltimer();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // search: one warp per candidate pose, lanes stride over the scan in 32-point strips
 // ---------------------------------------------------------------------------------------------------
-#define CS_SEARCH_WARPS 8
-#define CS_SEARCH_CHUNK 2048  // points staged in shared memory per pass (16 KB)
+#define CS_SEARCH_WARPS 8     // most warps (= candidates) per block; the host picks 2, 4 or 8 (see cs_search_warps)
+#define CS_SEARCH_CHUNK 2048  // most points staged in shared memory per pass (16 KB); dynamic: 8 B x min(P, chunk)
 
 template <bool TILED>
 __global__ void __launch_bounds__(CS_SEARCH_WARPS * 32)
 cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  __shared__ float2 s_pts[CS_SEARCH_CHUNK];
+  extern __shared__ float4 cs_search_smem[];
+  float2* s_pts = reinterpret_cast<float2*>(cs_search_smem);  // a.search_chunk points
   __shared__ unsigned long long s_key[CS_SEARCH_WARPS];
+  const int nwarps = blockDim.x >> 5;
+  const int chunk = a.search_chunk;
 
-  // the next kernel of the step may become resident as soon as every block of this grid has started; it
-  // waits (cs_pdl_wait) for this grid's results.  This grid itself depends on the previous step's rings kernel.
-  cs_pdl_launch_dependents();
-  cs_pdl_wait();
+  // This grid depends on the previous step's rings kernel (cs_pdl_wait below); the next kernel of this step may
+  // become resident once every block here is past that wait.
+  long long* tl = nullptr;  // timeline record of this block (diagnostics)
+  if (a.diag && blockIdx.y == 0 && blockIdx.x < CS_DIAG_SEARCH_BLOCKS && threadIdx.x == 0) {
+    tl = a.diag + ((size_t)a.diag_rings + blockIdx.x) * 8;
+    tl[0] = cs_smid(); tl[1] = cs_globaltimer(); tl[7] = 0;
+  }
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
   const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
@@ -435,24 +493,65 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int local = blockIdx.x * CS_SEARCH_WARPS + warp;
+  const int local = blockIdx.x * nwarps + warp;
   const int idx = a.cand_first + local;  // flat candidate index
   const bool valid = local < a.cand_count;
+
+  // ---- everything that does not depend on the previous step goes first: the step's inputs (scan, header,
+  // candidate table) were uploaded before the kernels in front, and size / scale / seed / sigmas are host-owned
+  // constants.  When this grid becomes resident early (programmatic dependent launch) all of it overlaps the tail
+  // of the previous step's rings kernel.
   const int P = hdr.n_points;
   const int size = S.size, pitch_tiles = S.pitch_tiles;
   const uint16_t* __restrict__ map = S.map;
   const float scale = S.scale;
+  {  // first chunk of the scan -> shared memory, asynchronously (two points per 16-byte copy).  Through L1 (.ca):
+     // every block of the grid reads the same few KB, and the blocks of one SM should share one L2 fetch.
+    const int n0 = min(chunk, P);
+    const float4* src4 = reinterpret_cast<const float4*>(points);
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(s_pts);
+    for (int i = threadIdx.x; i < (n0 >> 1); i += blockDim.x)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * (unsigned)i), "l"(src4 + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if ((n0 & 1) && threadIdx.x == 0) s_pts[n0 - 1] = points[n0 - 1];
+  }
+  float off[3] = {0.f, 0.f, 0.f};  // candidate offset (or absolute pose) of this warp
+  float ct = 0.f, st = 0.f;
+  if (valid) {
+    if (idx > 0) {
+      if (a.cand_mode == CS_CAND_PHILOX) {
+        cs_gauss3(S.seed, a.scan_index, (uint32_t)(idx - 1), S.sigma_xy, S.sigma_theta, off);
+      } else {
+        const float* p = cand + 3 * (size_t)(idx - 1);
+        off[0] = p[0]; off[1] = p[1]; off[2] = p[2];
+      }
+    }
+    if (a.cand_cs) {
+      ct = a.cand_cs[2 * (size_t)idx];
+      st = a.cand_cs[2 * (size_t)idx + 1];
+    }
+  }
+
+  cs_pdl_wait();  // the previous step (its rings kernel: map, and through it the search kernel: state) is complete
+  // Only now may this step's rings kernel become resident: it does not wait for this grid as a whole but polls
+  // counters that the previous step's publishing thread re-armed, so it must not run ahead of that step's end.
+  cs_pdl_launch_dependents();
+  if (tl) tl[2] = cs_globaltimer();
 
   float px = 0.f, py = 0.f, c = 0.f, s = 0.f;
   if (valid) {
     float sp[3], pose[3];
     cs_search_pose(S, hdr, a, sp);
-    cs_candidate_pose(S, a, cand, sp, idx, pose);
-    float ct, st;
-    if (a.cand_cs) {
-      ct = a.cand_cs[2 * (size_t)idx];
-      st = a.cand_cs[2 * (size_t)idx + 1];
+    if (idx == 0) {
+      pose[0] = sp[0]; pose[1] = sp[1]; pose[2] = sp[2];
+    } else if (a.cand_mode == CS_CAND_ABSOLUTE) {
+      pose[0] = off[0]; pose[1] = off[1]; pose[2] = off[2];
     } else {
+      pose[0] = __fadd_rn(sp[0], off[0]);  // :635-637
+      pose[1] = __fadd_rn(sp[1], off[1]);
+      pose[2] = __fadd_rn(sp[2], off[2]);
+    }
+    if (!a.cand_cs) {
       ct = cs_cosf(pose[2]);
       st = cs_sinf(pose[2]);
     }
@@ -464,15 +563,21 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
   unsigned sum = 0;  // <= 65535 * 65536 < 2^32 (max_points <= 65536)
   unsigned nb = 0;
-  for (int base = 0; base < P; base += CS_SEARCH_CHUNK) {
-    const int n = min(CS_SEARCH_CHUNK, P - base);
-    __syncthreads();
-    // vectorised staging: two points per 16-byte load
-    const float4* src4 = reinterpret_cast<const float4*>(points + base);
-    float4* dst4 = reinterpret_cast<float4*>(s_pts);
-    for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) dst4[i] = __ldg(src4 + i);
-    if ((n & 1) && threadIdx.x == 0) s_pts[n - 1] = points[base + n - 1];
-    __syncthreads();
+  for (int base = 0; base < P; base += chunk) {
+    const int n = min(chunk, P - base);
+    if (base == 0) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+    } else {
+      __syncthreads();
+      // vectorised staging: two points per 16-byte load
+      const float4* src4 = reinterpret_cast<const float4*>(points + base);
+      float4* dst4 = reinterpret_cast<float4*>(s_pts);
+      for (int i = threadIdx.x; i < (n >> 1); i += blockDim.x) dst4[i] = __ldg(src4 + i);
+      if ((n & 1) && threadIdx.x == 0) s_pts[n - 1] = points[base + n - 1];
+      __syncthreads();
+    }
+    if (tl && base == 0) tl[3] = cs_globaltimer();
     if (valid) {
 #pragma unroll 8
       for (int i = lane; i < n; i += 32) {
@@ -505,31 +610,26 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     key = ((unsigned long long)(unsigned)d << 32) | (unsigned)idx;
     if (lane == 0 && S.distances) S.distances[idx] = d;
   }
+  if (tl) tl[4] = cs_globaltimer();  // warp 0 is through its candidate
   if (lane == 0) s_key[warp] = key;
   __syncthreads();
-  __shared__ int s_last;
-  if (threadIdx.x == 0) {
-    unsigned long long k = s_key[0];
-#pragma unroll
-    for (int w = 1; w < CS_SEARCH_WARPS; w++) k = min(k, s_key[w]);
-    if (k != ~0ull) atomicMin(&S.key[a.parity], k);
-    int last = 0;
-    if (a.fuse_publish) {
-      __threadfence();
-      last = (atomicAdd(&S.search_done, 1u) == gridDim.x - 1) ? 1 : 0;
-      if (last) S.search_done = 0;
-    }
-    s_last = last;
-  }
+  if (tl) tl[5] = cs_globaltimer();    // every warp of the block is
+  if (threadIdx.x != 0) return;
+  unsigned long long k = s_key[0];
+  for (int w = 1; w < nwarps; w++) k = min(k, s_key[w]);
+  unsigned long long seen = ~0ull;
+  if (k != ~0ull) seen = atomicMin(&S.key[a.parity], k);
   if (!a.fuse_publish) return;
-  __syncthreads();
-  if (!s_last) return;
-  // ---- the last block to finish owns the complete arg-min: Update glue, pose out ---------------------------
+  // ---- the last block to finish owns the complete arg-min: Update glue, pose out.  Every block counts itself
+  // after its atomicMin is performed (fence); the one that sees the full count reads the final key.
+  const unsigned long long guess = min(seen, k);  // the arg-min as of this block's own contribution
   __threadfence();
-  if (threadIdx.x == 0) {
-    CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
-    cs_publish(S, hdr, a, cand, result);
-  }
+  const bool last = atomicAdd(&S.search_done, 1u) == gridDim.x - 1;
+  if (!last) return;
+  S.search_done = 0;
+  CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
+  cs_publish(S, hdr, a, cand, result, guess != ~0ull, guess);
+  if (tl) { tl[6] = cs_globaltimer(); tl[7] = 1; }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -540,8 +640,8 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
 __global__ void __launch_bounds__(CS_SETUP_THREADS)
 cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  cs_pdl_launch_dependents();
   cs_pdl_wait();
+  cs_pdl_launch_dependents();  // after the wait: see cs_search_kernel
   const int sj = blockIdx.y;
   if (threadIdx.x != 0) return;
   CsSession& S = sessions[sj];
@@ -635,6 +735,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
   const long long t_begin = a.diag ? clock64() : 0;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tl = (a.diag && blockIdx.y == 0 && (int)blockIdx.x < a.diag_rings && tid == 0) ? a.diag + (size_t)blockIdx.x * 8 : nullptr;
+  if (tl) { tl[1] = cs_smid(); tl[2] = cs_globaltimer(); tl[4] = 0; tl[5] = 0; tl[6] = 0; }
   const int nthreads = blockDim.x;
   const int round_cap = nthreads * CS_RING_RPT;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -647,82 +749,129 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     for (int i = tid; i < CS_RING_SLOTS / 4; i += nthreads) c4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   cs_pdl_launch_dependents();  // the next step's search may become resident once every block here has started
-  cs_pdl_wait();               // the pose (search / set-up kernel) is final from here on
+  // No griddepcontrol.wait here: the kernel in front (search / set-up) is not awaited as a whole.  Its publishing
+  // thread writes CsSession::ll_pose as soon as the pose is final; this kernel's preparing blocks poll that, the
+  // others poll the preparing blocks' count.  (The wait is executed at the very end, to keep completion
+  // transitive for the next kernel in the stream.)  Nothing the search kernel writes is read before the polls.
 
   const int sj = blockIdx.y;
   CsSession& S = sessions[sj];
   const int span = a.ring_span;
-  const int k_begin = blockIdx.x * span;
   const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
-  const int n = hdr.n_points;
-  const int size = S.size, pitch_tiles = S.pitch_tiles;
+  const int n = hdr.n_points;                      // input of the step: uploaded before the kernels in front
+  const int size = S.size, pitch_tiles = S.pitch_tiles;  // host-owned constants
   const float scale = S.scale;
-  const float pose_x = S.cur_pose[0], pose_y = S.cur_pose[1];
-  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
-  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
   const int alpha = S.quality;
   uint16_t* __restrict__ map = S.map;
-  const int4* rays = S.rays;
-  const int* batch_max = S.batch_max;
+  const int copies = S.ray_copies;
+  const int copy = cs_smid() % copies;  // the blocks of one SM share a copy (and its L1 lines)
+  const int4* rays = S.rays + (size_t)copy * S.ray_stride;
+  const int* batch_max = S.batch_max + (size_t)copy * S.batch_stride;
+  const unsigned slot = a.step_id & 1u;
+  unsigned long long* prep_words = S.prep_words + (size_t)slot * copies * 16;
+  const unsigned long long ll_tag = (unsigned long long)a.step_id << 32;
 
-  // ---- ray preparation (UpdateHoleMap :517-530, ClipRay, the prologue of DrawLaserRayOnHoleMap): the first
-  // blocks of the grid take one ray per thread, publish max_ring / visits, and raise prep_done; every block
-  // waits for all of them.  Blocks are dispatched in index order, so the preparing blocks are resident before
-  // any block can wait on them.
-  const int nprep = (n + nthreads - 1) / nthreads;
+  // ---- ray preparation (UpdateHoleMap :517-530, ClipRay, the prologue of DrawLaserRayOnHoleMap): the first nprep
+  // blocks of the grid each take a group of `a.prep_group` rays (a multiple of 32, one ray per lane and pass), write
+  // them to every copy and raise the copies' counts; every block waits for the count of its copy.  Blocks are
+  // dispatched in index order, so the preparing blocks are resident before any block can wait on them.
+  const int group = a.prep_group;
+  const int nprep = (n + group - 1) / group;
   if ((int)blockIdx.x < nprep) {
-    __shared__ int sh_ring[CS_RING_MAX_THREADS / 32];
     __shared__ long long sh_vis[CS_RING_MAX_THREADS / 32];
+    __shared__ float sh_pose[5];
     const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
-    const float pose[3] = {pose_x, pose_y, S.cur_pose[2]};
-    const float cs[2] = {S.cur_cs[0], S.cur_cs[1]};
-    int mr = -1;
-    long long vis = 0;
-    cs_prepare_rays(S, points, n, blockIdx.x * nthreads + tid, nprep * nthreads, pose, cs, true, mr, vis);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
-      vis += __shfl_xor_sync(0xffffffffu, vis, o);
+    const int g_begin = blockIdx.x * group, g_end = min(n, g_begin + group);
+    const int i0 = g_begin + tid;
+    const float2 p0 = (i0 < g_end) ? __ldg(points + i0) : make_float2(1.f, 0.f);  // in flight while the pose is awaited
+    if (tid < 5) {
+      volatile unsigned long long* ll = S.ll_pose + tid;
+      unsigned long long w;
+      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag) {}
+      sh_pose[tid] = __uint_as_float((unsigned)w);
+      if (tl) tl[3] = cs_globaltimer();
     }
-    if (lane == 0) { sh_ring[warp] = mr; sh_vis[warp] = vis; }
-    __threadfence();  // this thread's ray stores are visible device-wide before the block's arrival is counted
     __syncthreads();
+    const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
+    const float cs[2] = {sh_pose[3], sh_pose[4]};
+    long long vis = 0;
+    long long* pd = (tl && blockIdx.x == 0) ? a.diag + ((size_t)a.diag_rings + CS_DIAG_SEARCH_BLOCKS - 2) * 8 : nullptr;
+    if (pd) { pd[0] = tl[3]; pd[1] = cs_globaltimer(); }
+    if (tid < group) cs_prepare_rays(S, points, p0, g_end, i0, nthreads, pose, cs, true, vis);
+    if (pd) pd[2] = cs_globaltimer();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(0xffffffffu, vis, o);
+    if (lane == 0) sh_vis[warp] = vis;
+    __threadfence();  // this thread's ray stores are visible device-wide before the block's arrival is counted
+    if (pd) pd[3] = cs_globaltimer();
+    __syncthreads();
+    if (tid < copies) atomicAdd(S.prep_words + ((size_t)slot * copies + tid) * 16, 1ull);
     if (tid == 0) {
-      for (int w = 1; w < (nthreads >> 5); w++) { mr = max(mr, sh_ring[w]); vis += sh_vis[w]; }
-      unsigned* pw = reinterpret_cast<unsigned*>(&S.prep_word);  // little endian: [0] = count, [1] = max_ring + 1
-      atomicMax(pw + 1, (unsigned)(mr + 1));
+      if (pd) pd[4] = cs_globaltimer();
+      for (int w = 1; w < (nthreads >> 5); w++) vis += sh_vis[w];
       if (vis) {
-        atomicAdd((unsigned long long*)&S.visits, (unsigned long long)vis);
+        atomicAdd((unsigned long long*)&S.visits_slot[slot], (unsigned long long)vis);
         if (a.visits_out) atomicAdd((unsigned long long*)a.visits_out, (unsigned long long)vis);
       }
-      __threadfence();
-      atomicAdd(pw, 1u);
     }
   }
   __shared__ int sh_max_ring;
   if (tid == 0) {
-    volatile unsigned long long* pw = &S.prep_word;
-    unsigned long long w;
-    while ((unsigned)((w = *pw) & 0xffffffffull) < (unsigned)nprep) __nanosleep(20);
+    sh_max_ring = -1;
+    volatile unsigned long long* pw = prep_words + (size_t)copy * 16;
+    while (*pw != (unsigned long long)nprep) {}
     __threadfence();
-    sh_max_ring = (int)(unsigned)(w >> 32) - 1;  // every block's max was merged before its count
+    if (tl) tl[4] = cs_globaltimer();
+  }
+  __syncthreads();
+  // the pose words are final: the preparing blocks saw them before they counted themselves
+  const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
+  const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
+  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
+  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
+  {  // max_ring = largest dxc of a valid ray (-1: nothing to draw), from the per-batch maxima
+    int m = -1;
+    for (int i = tid; i < (n + 31) / 32; i += nthreads) m = max(m, batch_max[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if (lane == 0 && m >= 0) atomicMax(&sh_max_ring, m);
   }
   __syncthreads();
   const int max_ring = sh_max_ring;
-  if (k_begin > max_ring) return;
+  // ---- work units: unit u = rings [u*span, (u+1)*span).  Block b starts on unit b; when the rings kernel runs one
+  // session alone (a.ring_dynamic) the grid is at most one resident wave and every further unit is drawn from a
+  // ticket counter in ascending ring order, so the dense inner rings start first and the blocks stay busy until the
+  // rings run out.  In a batch of sessions every block owns exactly one unit.
+  const int nrounds = (n + round_cap - 1) / round_cap;
+  unsigned* ticket = &S.ring_ticket[a.step_id & 1u];
+  __shared__ int sh_next_unit;
+  bool rays_resident = false;
+  int bmax[CS_RING_RPT];
+#pragma unroll
+  for (int j = 0; j < CS_RING_RPT; j++) bmax[j] = -1;
+  for (int unit = blockIdx.x;;) {
+  const int k_begin = unit * span;
+  if (k_begin > max_ring) break;
   const int k_end = min(k_begin + span - 1, max_ring);
+  unsigned next_ticket = 0u;  // requested now, consumed after the unit: the L2 round trip hides behind the rings
+  if (a.ring_dynamic && tid == 0) next_ticket = atomicAdd(ticket, 1u);
 
   for (int round0 = 0; round0 < n; round0 += round_cap) {
     const int round_n = min(round_cap, n - round0);
-    if (round0 > 0) __syncthreads();  // previous round: stores done, shared arrays free
-    for (int i = tid; i < round_n; i += nthreads) s_rays[i] = __ldcg(rays + round0 + i);  // written during this kernel: L2
-    int bmax[CS_RING_RPT];
+    if (nrounds > 1 || !rays_resident) {
+      if (rays_resident) __syncthreads();  // previous round: stores done, shared arrays free
+      // Written during this kernel by the preparing blocks, and not read by anybody before their count was seen
+      // (L1 is invalidated at kernel start), so the default L1-allocating load is coherent here — and the blocks
+      // of one SM share one L2 fetch of lines that every block of the grid wants at the same moment.
+      for (int i = tid; i < round_n; i += nthreads) s_rays[i] = rays[round0 + i];
 #pragma unroll
-    for (int j = 0; j < CS_RING_RPT; j++) {
-      const int unit = warp * CS_RING_RPT + j;
-      bmax[j] = (unit * 32 < round_n) ? __ldcg(batch_max + (round0 >> 5) + unit) : -1;
+      for (int j = 0; j < CS_RING_RPT; j++) {
+        const int bu = warp * CS_RING_RPT + j;
+        bmax[j] = (bu * 32 < round_n) ? batch_max[(round0 >> 5) + bu] : -1;
+      }
+      rays_resident = true;
     }
     __syncthreads();
+    if (tl && round0 == 0 && unit == (int)blockIdx.x) tl[5] = cs_globaltimer();
 
     // read-modify-writes whose load is in flight (see 3a)
     bool pend[CS_RING_RPT];
@@ -923,7 +1072,13 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     for (int j = 0; j < CS_RING_RPT; j++)
       if (pend[j]) __stcg(map + pend_cell[j], (uint16_t)cs_blend(pend_v[j], pend_pv[j], alpha));
   }
-  if (a.diag && tid == 0) a.diag[(size_t)blockIdx.x * 8] = clock64() - t_begin;
+  if (!a.ring_dynamic) break;
+  if (tid == 0) sh_next_unit = (int)(gridDim.x + next_ticket);
+  __syncthreads();
+  unit = sh_next_unit;
+  }
+  if (tl) { tl[0] = clock64() - t_begin; tl[6] = cs_globaltimer(); }
+  cs_pdl_wait();  // the kernel in front has long finished; this only makes "this grid done" imply "that grid done"
 }
 
 // ---------------------------------------------------------------------------------------------------
