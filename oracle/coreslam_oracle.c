@@ -278,7 +278,100 @@ void or_segment_to_cloud(const float* rays, int n, const float segment_pose[3], 
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* CoreSLAM/ObstacleMap.cs:17-22 */
+or_obstaclemap* or_obstaclemap_create(int size_pixels, float size_meters) {
+  or_obstaclemap* m = (or_obstaclemap*)calloc(1, sizeof(*m));
+  m->size = size_pixels;
+  m->scale = (float)size_pixels / size_meters; /* ObstacleMap.cs:20, int -> float, then divide */
+  size_t n = (size_t)size_pixels * (size_t)size_pixels;
+  m->pixels = (int8_t*)calloc(n ? n : 1, 1);
+  m->no_hit = (uint8_t*)calloc(n ? n : 1, 1);
+  return m;
+}
+
+void or_obstaclemap_destroy(or_obstaclemap* m) {
+  if (!m) return;
+  free(m->pixels);
+  free(m->no_hit);
+  free(m);
+}
+
+/* CoreSLAMProcessor.cs:456-490 */
+int64_t or_draw_ray_obstacle(or_obstaclemap* m, int32_t x1, int32_t y1, int32_t x2, int32_t y2, int max_obstacle_hits) {
+  const int size = m->size;
+  int32_t ddx = (int32_t)((uint32_t)x2 - (uint32_t)x1), ddy = (int32_t)((uint32_t)y2 - (uint32_t)y1);
+  if (ddx == INT32_MIN || ddy == INT32_MIN) return -1; /* Math.Abs(int.MinValue) throws */
+  int32_t dx = ddx < 0 ? -ddx : ddx, sx = (ddx > 0) - (ddx < 0); /* :458 */
+  int32_t dy = ddy < 0 ? -ddy : ddy, sy = (ddy > 0) - (ddy < 0); /* :459 */
+  int32_t err = (dx > dy ? dx : -dy) / 2, e2;                    /* :460 */
+  int64_t touched = 0;
+  for (;;) { /* :462 */
+    if (x1 < 0 || x1 >= size || y1 < 0 || y1 >= size) { /* :465-466 */
+      break;
+    } else if (x1 == x2 && y1 == y2) { /* :471 */
+      int8_t* px = &m->pixels[(size_t)y1 * size + x1];
+      if (*px < max_obstacle_hits) (*px)++; /* :474-477 */
+      touched++;
+      break;
+    } else {
+      m->no_hit[(size_t)y1 * size + x1] = 1; /* :483 */
+      touched++;
+    }
+    e2 = err;                                                                   /* :486 */
+    if (e2 > -dx) { err = (int32_t)((uint32_t)err - (uint32_t)dy); x1 += sx; } /* :487 */
+    if (e2 < dy) { err = (int32_t)((uint32_t)err + (uint32_t)dx); y1 += sy; }  /* :488 */
+  }
+  return touched;
+}
+
+/* CoreSLAMProcessor.cs:540-593 */
+int64_t or_update_obstacle_map(or_obstaclemap* m, const float* points, int n, const float pose[3],
+                               int max_obstacle_hits) {
+  const int size = m->size;
+  memset(m->no_hit, 0, (size_t)size * (size_t)size); /* :542 */
+  float px = pose[0] * m->scale + 0.5f; /* :545 */
+  float py = pose[1] * m->scale + 0.5f; /* :546 */
+  float c = cosf(pose[2]) * m->scale;   /* :547 */
+  float s = sinf(pose[2]) * m->scale;   /* :548 */
+  int32_t x1 = or_cvt(px), y1 = or_cvt(py); /* :553-554 */
+  if (x1 < 0 || x1 >= size || y1 < 0 || y1 >= size) return 0; /* :557-560 */
+  int64_t touched = 0;
+  for (int i = 0; i < n; i++) { /* :563 */
+    float X = points[2 * i], Y = points[2 * i + 1];
+    float fx = px + c * X; /* :566, left-associative, one rounding per operation */
+    fx = fx - s * Y;
+    float fy = py + s * X; /* :567 */
+    fy = fy + c * Y;
+    int32_t x2 = or_cvt(fx), y2 = or_cvt(fy);
+    int64_t t = or_draw_ray_obstacle(m, x1, y1, x2, y2, max_obstacle_hits); /* :570 */
+    if (t > 0) touched += t;
+  }
+  for (int y = 0; y < size; y++) { /* :576-592 */
+    for (int x = 0; x < size; x++) {
+      size_t k = (size_t)y * size + x;
+      if (m->no_hit[k]) {
+        if (m->pixels[k] < 0) m->pixels[k]++;
+        else if (m->pixels[k] > 0) m->pixels[k]--;
+      }
+    }
+  }
+  return touched;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* CoreSLAMProcessor.cs:119-175 */
+or_processor* or_processor_create_full(float physical_map_size, int hole_map_size, int obstacle_map_size,
+                                       const float start_pose[3], float sigma_xy, float sigma_theta,
+                                       int iterations_per_thread, int num_search_threads) {
+  or_processor* p = or_processor_create(physical_map_size, hole_map_size, start_pose, sigma_xy, sigma_theta,
+                                        iterations_per_thread, num_search_threads);
+  if (obstacle_map_size > 0) {
+    p->omap = or_obstaclemap_create(obstacle_map_size, physical_map_size); /* :132 */
+    or_processor_reset(p);
+  }
+  return p;
+}
+
 or_processor* or_processor_create(float physical_map_size, int hole_map_size, const float start_pose[3],
                                   float sigma_xy, float sigma_theta, int iterations_per_thread,
                                   int num_search_threads) {
@@ -292,6 +385,8 @@ or_processor* or_processor_create(float physical_map_size, int hole_map_size, co
   p->quality = 50;
   p->hole_width = 0.6f;
   p->position_search_beginning = 5;
+  p->unmapped_obstacle_hits = -5; /* :98 */
+  p->max_obstacle_hits = 10;      /* :103 */
   p->map = or_holemap_create(hole_map_size, physical_map_size); /* :131 */
   or_processor_reset(p);                                        /* :140 */
   return p;
@@ -300,6 +395,7 @@ or_processor* or_processor_create(float physical_map_size, int hole_map_size, co
 void or_processor_destroy(or_processor* p) {
   if (!p) return;
   or_holemap_destroy(p->map);
+  or_obstaclemap_destroy(p->omap);
   free(p);
 }
 
@@ -308,6 +404,9 @@ void or_processor_reset(or_processor* p) {
   size_t n = (size_t)p->map->size * (size_t)p->map->size;
   uint16_t v = (uint16_t)((OR_TS_OBSTACLE + OR_TS_NO_OBSTACLE) / 2); /* :169 -> 32750 */
   for (size_t i = 0; i < n; i++) p->map->pixels[i] = v;
+  if (p->omap) /* :170 ArrayEx.Fill(ObstacleMap.Pixels, UnmappedObstacleHits) */
+    memset(p->omap->pixels, (int8_t)p->unmapped_obstacle_hits, (size_t)p->omap->size * (size_t)p->omap->size);
+  p->obstacle_visits = 0;
   memcpy(p->pose, p->start_pose, sizeof(float) * 3); /* :172 */
   memset(p->last_odometry_pose, 0, sizeof(float) * 3); /* :173 */
   p->scan_count = 0; /* :174 */
@@ -345,6 +444,7 @@ static void update_common(or_processor* p, or_worker* w, const float* points, in
   new_pose[2] = or_normalize_angle(new_pose[2]);         /* :746 */
   memcpy(p->pose, new_pose, sizeof(float) * 3);          /* :747 */
   p->visits = or_update_hole_map(p->map, points, n, p->pose, p->hole_width, p->quality, NULL); /* :750 */
+  if (p->omap) p->obstacle_visits = or_update_obstacle_map(p->omap, points, n, p->pose, p->max_obstacle_hits); /* :751 */
 }
 
 /* CoreSLAMProcessor.cs:717-752 */

@@ -76,6 +76,26 @@ void or_parallel_search(const or_holemap* m, const float* points, int n, const f
 void or_segment_to_cloud(const float* rays, int n, const float segment_pose[3], const float odometry_pose[3],
                          float* points_out);
 
+/* ---- ObstacleMap half of Update ------------------------------------------------- */
+/* CoreSLAM/ObstacleMap.cs:11-44: sbyte[size,size] (first index Y), Scale = sizePixels / sizeMeters.
+ * no_hit is CoreSLAMProcessor's private bool[,] noHitMap (:30, :133). */
+typedef struct {
+  int size;
+  float scale;
+  int8_t* pixels;  /* row-major y*size+x */
+  uint8_t* no_hit; /* row-major y*size+x, 0/1 */
+} or_obstaclemap;
+
+or_obstaclemap* or_obstaclemap_create(int size_pixels, float size_meters);
+void or_obstaclemap_destroy(or_obstaclemap* m);
+/* DrawLaserRayOnObstacleMap, CoreSLAMProcessor.cs:456-490.  Returns the number of loop iterations that
+ * touched the map (no-hit marks + the hit).  A ray whose Math.Abs argument is int.MinValue (the reference
+ * throws OverflowException there) is skipped and returns -1. */
+int64_t or_draw_ray_obstacle(or_obstaclemap* m, int32_t x1, int32_t y1, int32_t x2, int32_t y2, int max_obstacle_hits);
+/* UpdateObstacleMap, CoreSLAMProcessor.cs:540-593.  Returns the cells touched by the rays (sum of the above). */
+int64_t or_update_obstacle_map(or_obstaclemap* m, const float* points, int n, const float pose[3],
+                               int max_obstacle_hits);
+
 /* ---- CoreSLAMProcessor state machine: ctor :119-162, Reset :167-175, Update :717-752 ---- */
 typedef struct {
   or_holemap* map;
@@ -92,16 +112,26 @@ typedef struct {
   int64_t visits;                /* cells written by the last Update (measurement only) */
   int32_t last_distance;         /* winner's distance of the last search, INT32_MAX if none */
   int32_t last_index;
+  or_obstaclemap* omap;          /* :53, NULL when created without an obstacle map */
+  int unmapped_obstacle_hits;    /* :98, default -5 (sbyte) */
+  int max_obstacle_hits;         /* :103, default 10 (sbyte) */
+  int64_t obstacle_visits;       /* map cells touched by the rays of the last UpdateObstacleMap */
 } or_processor;
 
 or_processor* or_processor_create(float physical_map_size, int hole_map_size, const float start_pose[3],
                                   float sigma_xy, float sigma_theta, int iterations_per_thread,
                                   int num_search_threads);
+/* the full constructor (:119-120): obstacle_map_size > 0 also creates the ObstacleMap, and Update then ends
+ * with UpdateObstacleMap (:751) */
+or_processor* or_processor_create_full(float physical_map_size, int hole_map_size, int obstacle_map_size,
+                                       const float start_pose[3], float sigma_xy, float sigma_theta,
+                                       int iterations_per_thread, int num_search_threads);
 void or_processor_destroy(or_processor* p);
 void or_processor_reset(or_processor* p);
 /* Update with an already-built cloud (points in the lidar frame relative to odometry_pose) and the
  * T*I candidate offsets that the reference would have dequeued for this scan (ignored while
- * scan_count < position_search_beginning). The obstacle-map half of Update (:751) is out of scope. */
+ * scan_count < position_search_beginning).  UpdateObstacleMap (:751) runs when the processor has an
+ * obstacle map (or_processor_create_full). */
 void or_processor_update(or_processor* p, const float* points, int n, const float odometry_pose[3],
                          const float* offsets);
 

@@ -30,6 +30,10 @@ class _HoleMap(C.Structure):
     _fields_ = [("size", C.c_int), ("scale", C.c_float), ("pixels", C.POINTER(C.c_uint16))]
 
 
+class _ObstacleMap(C.Structure):
+    _fields_ = [("size", C.c_int), ("scale", C.c_float), ("pixels", C.POINTER(C.c_int8)), ("no_hit", C.POINTER(C.c_uint8))]
+
+
 class _Processor(C.Structure):
     _fields_ = [
         ("map", C.POINTER(_HoleMap)),
@@ -48,6 +52,10 @@ class _Processor(C.Structure):
         ("visits", C.c_int64),
         ("last_distance", C.c_int32),
         ("last_index", C.c_int32),
+        ("omap", C.POINTER(_ObstacleMap)),
+        ("unmapped_obstacle_hits", C.c_int),
+        ("max_obstacle_hits", C.c_int),
+        ("obstacle_visits", C.c_int64),
     ]
 
 
@@ -82,6 +90,15 @@ def lib():
     L.or_segment_to_cloud.argtypes = [fp, C.c_int, fp, fp, fp]
     L.or_processor_create.restype = C.POINTER(_Processor)
     L.or_processor_create.argtypes = [C.c_float, C.c_int, fp, C.c_float, C.c_float, C.c_int, C.c_int]
+    L.or_processor_create_full.restype = C.POINTER(_Processor)
+    L.or_processor_create_full.argtypes = [C.c_float, C.c_int, C.c_int, fp, C.c_float, C.c_float, C.c_int, C.c_int]
+    L.or_obstaclemap_create.restype = C.POINTER(_ObstacleMap)
+    L.or_obstaclemap_create.argtypes = [C.c_int, C.c_float]
+    L.or_obstaclemap_destroy.argtypes = [C.POINTER(_ObstacleMap)]
+    L.or_draw_ray_obstacle.restype = C.c_int64
+    L.or_draw_ray_obstacle.argtypes = [C.POINTER(_ObstacleMap)] + [C.c_int32] * 4 + [C.c_int]
+    L.or_update_obstacle_map.restype = C.c_int64
+    L.or_update_obstacle_map.argtypes = [C.POINTER(_ObstacleMap), fp, C.c_int, fp, C.c_int]
     L.or_processor_destroy.argtypes = [C.POINTER(_Processor)]
     L.or_processor_reset.argtypes = [C.POINTER(_Processor)]
     L.or_processor_update.argtypes = [C.POINTER(_Processor), fp, C.c_int, fp, fp]
@@ -132,6 +149,36 @@ class HoleMap:
         if getattr(self, "_own", False) and self._p:
             lib().or_holemap_destroy(self._p)
             self._p = None
+
+
+class ObstacleMap:
+    """CoreSLAM/ObstacleMap.cs:11-44 — pixels / no_hit are numpy views (size, size), first index Y."""
+
+    def __init__(self, size_pixels: int, size_meters: float, _ptr=None):
+        self._own = _ptr is None
+        self._p = lib().or_obstaclemap_create(size_pixels, float(size_meters)) if _ptr is None else _ptr
+        self.size = self._p.contents.size
+        self.scale = self._p.contents.scale
+        self.pixels = np.ctypeslib.as_array(self._p.contents.pixels, shape=(self.size, self.size))
+        self.no_hit = np.ctypeslib.as_array(self._p.contents.no_hit, shape=(self.size, self.size))
+
+    def fill(self, v: int):
+        self.pixels[:] = v
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self._p:
+            lib().or_obstaclemap_destroy(self._p)
+            self._p = None
+
+
+def draw_ray_obstacle(m: ObstacleMap, x1, y1, x2, y2, max_obstacle_hits=10) -> int:
+    return int(lib().or_draw_ray_obstacle(m._p, x1, y1, x2, y2, int(max_obstacle_hits)))
+
+
+def update_obstacle_map(m: ObstacleMap, points, pose, max_obstacle_hits=10) -> int:
+    pts, pp = _f(points)
+    po, pop = _f(pose)
+    return int(lib().or_update_obstacle_map(m._p, pp, pts.size // 2, pop, int(max_obstacle_hits)))
 
 
 def cvt(f: float) -> int:
@@ -239,11 +286,22 @@ class Processor:
     """CoreSLAMProcessor state machine (ctor :119-162, Reset :167-175, Update :717-752)."""
 
     def __init__(self, physical_map_size, hole_map_size, start_pose, sigma_xy, sigma_theta,
-                 iterations_per_thread, num_search_threads):
+                 iterations_per_thread, num_search_threads, obstacle_map_size=0):
         sp, spp = _f(start_pose)
-        self._p = lib().or_processor_create(float(physical_map_size), int(hole_map_size), spp, float(sigma_xy),
-                                            float(sigma_theta), int(iterations_per_thread), int(num_search_threads))
+        self._p = lib().or_processor_create_full(float(physical_map_size), int(hole_map_size), int(obstacle_map_size), spp,
+                                                 float(sigma_xy), float(sigma_theta), int(iterations_per_thread),
+                                                 int(num_search_threads))
         self.map = HoleMap(0, 0, _ptr=self._p.contents.map)
+        self.obstacle_map = ObstacleMap(0, 0, _ptr=self._p.contents.omap) if obstacle_map_size > 0 else None
+
+    unmapped_obstacle_hits = property(lambda s: s._p.contents.unmapped_obstacle_hits,
+                                      lambda s, v: setattr(s._p.contents, "unmapped_obstacle_hits", int(v)))
+    max_obstacle_hits = property(lambda s: s._p.contents.max_obstacle_hits,
+                                 lambda s, v: setattr(s._p.contents, "max_obstacle_hits", int(v)))
+
+    @property
+    def obstacle_visits(self):
+        return int(self._p.contents.obstacle_visits)
 
     quality = property(lambda s: s._p.contents.quality, lambda s, v: setattr(s._p.contents, "quality", int(v)))
     hole_width = property(lambda s: s._p.contents.hole_width,
@@ -290,5 +348,6 @@ class Processor:
     def __del__(self):
         if getattr(self, "_p", None):
             self.map = None
+            self.obstacle_map = None
             lib().or_processor_destroy(self._p)
             self._p = None

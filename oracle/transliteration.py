@@ -214,6 +214,75 @@ def update_hole_map(hm: HoleMapT, points, pose, hole_width, quality) -> int:
         return visits
 
 
+class ObstacleMapT:
+    """CoreSLAM/ObstacleMap.cs:11-44"""
+
+    def __init__(self, size_pixels: int, size_meters: float):
+        self.Size = size_pixels
+        self.Scale = F(size_pixels) / F(size_meters)  # ObstacleMap.cs:20
+        self.Pixels = np.zeros((size_pixels, size_pixels), dtype=np.int8)  # [y, x]
+
+
+def draw_laser_ray_on_obstacle_map(om: ObstacleMapT, no_hit_map, x1, y1, x2, y2, max_obstacle_hits) -> int:
+    """:456-490.  Returns how many map cells the loop touched; raises OverflowError where Math.Abs would throw."""
+    if i32(x2 - x1) == INT_MIN or i32(y2 - y1) == INT_MIN:
+        raise OverflowError("Math.Abs(int.MinValue)")
+    dx = abs(i32(x2 - x1))
+    sx = sign(i32(x2 - x1))
+    dy = abs(i32(y2 - y1))
+    sy = sign(i32(y2 - y1))
+    err = cdiv(dx if dx > dy else -dy, 2)
+    touched = 0
+    while True:
+        if x1 < 0 or x1 >= om.Size or y1 < 0 or y1 >= om.Size:
+            break
+        elif x1 == x2 and y1 == y2:
+            if om.Pixels[y1, x1] < max_obstacle_hits:
+                om.Pixels[y1, x1] += 1
+            touched += 1
+            break
+        else:
+            no_hit_map[y1, x1] = True
+            touched += 1
+        e2 = err
+        if e2 > -dx:
+            err = i32(err - dy)
+            x1 = i32(x1 + sx)
+        if e2 < dy:
+            err = i32(err + dx)
+            y1 = i32(y1 + sy)
+    return touched
+
+
+def update_obstacle_map(om: ObstacleMapT, points, pose, max_obstacle_hits) -> int:
+    """:540-593"""
+    with np.errstate(all="ignore"):
+        no_hit_map = np.zeros((om.Size, om.Size), dtype=bool)
+        px = F(pose[0]) * om.Scale + F(0.5)
+        py = F(pose[1]) * om.Scale + F(0.5)
+        c = cosf(F(pose[2])) * om.Scale
+        s = sinf(F(pose[2])) * om.Scale
+        x1 = to_int(px)
+        y1 = to_int(py)
+        if x1 < 0 or x1 >= om.Size or y1 < 0 or y1 >= om.Size:
+            return 0
+        touched = 0
+        for X, Y in points:
+            X = F(X)
+            Y = F(Y)
+            x2 = to_int(px + c * X - s * Y)
+            y2 = to_int(py + s * X + c * Y)
+            touched += draw_laser_ray_on_obstacle_map(om, no_hit_map, x1, y1, x2, y2, max_obstacle_hits)
+        for y in range(om.Size):
+            for x in range(om.Size):
+                if no_hit_map[y, x]:
+                    if om.Pixels[y, x] < 0:
+                        om.Pixels[y, x] += 1
+                    elif om.Pixels[y, x] > 0:
+                        om.Pixels[y, x] -= 1
+        return touched
+
+
 def monte_carlo_search(hm, points, search_pose, offsets):
     """:624-653 — offsets: iterable of (dx, dy, dtheta) in dequeue order"""
     best_pose = tuple(F(v) for v in search_pose)
@@ -246,10 +315,14 @@ def parallel_monte_carlo_search(hm, points, search_pose, offsets, iterations, th
 
 
 class ProcessorT:
-    """ctor :119-162, Reset :167-175, Update :717-752 (HoleMap half)"""
+    """ctor :119-162, Reset :167-175, Update :717-752"""
 
-    def __init__(self, physical_map_size, hole_map_size, start_pose, sigma_xy, sigma_theta, iterations, threads):
+    def __init__(self, physical_map_size, hole_map_size, start_pose, sigma_xy, sigma_theta, iterations, threads,
+                 obstacle_map_size=0):
         self.HoleMap = HoleMapT(hole_map_size, physical_map_size)
+        self.ObstacleMap = ObstacleMapT(obstacle_map_size, physical_map_size) if obstacle_map_size > 0 else None
+        self.UnmappedObstacleHits = -5  # :98
+        self.MaxObstacleHits = 10  # :103
         self.start_pose = tuple(F(v) for v in start_pose)
         self.iterations = iterations
         self.threads = threads
@@ -260,6 +333,8 @@ class ProcessorT:
 
     def Reset(self):
         self.HoleMap.Pixels[:] = (TS_OBSTACLE + TS_NO_OBSTACLE) // 2
+        if self.ObstacleMap is not None:
+            self.ObstacleMap.Pixels[:] = self.UnmappedObstacleHits  # :170
         self.Pose = self.start_pose
         self.lastOdometryPose = (F(0), F(0), F(0))
         self.scanCount = 0
@@ -280,3 +355,5 @@ class ProcessorT:
         new_pose = (new_pose[0], new_pose[1], normalize_angle(new_pose[2]))
         self.Pose = new_pose
         update_hole_map(self.HoleMap, points, self.Pose, self.HoleWidth, self.Quality)
+        if self.ObstacleMap is not None:
+            update_obstacle_map(self.ObstacleMap, points, self.Pose, self.MaxObstacleHits)  # :751
