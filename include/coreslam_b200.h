@@ -49,7 +49,8 @@ typedef struct cs_batch cs_batch;         /* opaque; N independent sessions on o
 
 /* Mirrors the constructor CoreSLAMProcessor(physicalMapSize, holeMapSize, obstacleMapSize, startPose,
  * sigmaXY, sigmaTheta, iterationsPerThread, numSearchThreads), CoreSLAMProcessor.cs:119-120.
- * obstacleMapSize is not taken: the ObstacleMap half of Update stays in C# (out of scope). */
+ * obstacle_map_size = 0 leaves the ObstacleMap half of Update (:751) out (the scan-to-pose benchmarks do);
+ * > 0 keeps a device-resident ObstacleMap and every Update / cs_integrate also runs UpdateObstacleMap. */
 typedef struct cs_config {
   float physical_map_size;   /* metres, edge of the square map */
   int32_t hole_map_size;     /* pixels per edge (HoleMap.Size, HoleMap.cs:17-22) */
@@ -63,7 +64,7 @@ typedef struct cs_config {
   uint64_t seed;             /* Philox seed for production-mode candidates */
   void* stream;              /* optional cudaStream_t to run on; NULL -> the handle creates its own */
   uint32_t flags;            /* CS_FLAG_* */
-  uint32_t reserved;
+  int32_t obstacle_map_size; /* pixels per edge of the ObstacleMap (ObstacleMap.cs:17-22), 0 = none */
 } cs_config;
 
 /* Result of one search / update.  distance = INT32_MAX and index = 0 when nothing was in bounds or
@@ -82,6 +83,8 @@ typedef struct cs_timing {
   float h2d_ms;
   float total_device_ms;
   double host_wait_ms;                        /* host wall time of the last cs_update until the pose was available */
+  float obstacle_ms;                          /* UpdateObstacleMap kernels of the last call (0 without an ObstacleMap) */
+  float reserved;
 } cs_timing;
 
 int32_t cs_abi_version(void);
@@ -100,6 +103,17 @@ cs_status cs_set_position_search_beginning(cs_processor* h, int32_t scans);  /* 
 cs_status cs_get_pose(cs_processor* h, float pose[3]);                       /* Pose */
 cs_status cs_set_pose(cs_processor* h, const float pose[3], const float last_odometry[3], int32_t scan_count);
 cs_status cs_get_map_info(const cs_processor* h, int32_t* size, float* scale); /* HoleMap.Size / HoleMap.Scale */
+
+/* ---- ObstacleMap: CoreSLAM/ObstacleMap.cs:11-44, CoreSLAMProcessor.cs:53 (needs cs_config.obstacle_map_size > 0) ----
+ * UpdateObstacleMap (:540-593) and DrawLaserRayOnObstacleMap (:456-490) run on the device at the end of every
+ * cs_update / cs_integrate / cs_replay step, after the HoleMap integration, from the same pose and cloud.   */
+cs_status cs_set_unmapped_obstacle_hits(cs_processor* h, int32_t hits); /* UnmappedObstacleHits (:98), sbyte, default -5; used by the next cs_reset */
+cs_status cs_set_max_obstacle_hits(cs_processor* h, int32_t hits);      /* MaxObstacleHits (:103), sbyte, default 10 */
+cs_status cs_get_obstacle_map_info(const cs_processor* h, int32_t* size, float* scale); /* ObstacleMap.Size / .Scale (0 when absent) */
+cs_status cs_obstacle_map_download(cs_processor* h, int8_t* pixels);      /* ObstacleMap.Pixels, Size*Size sbyte, [y, x] row-major */
+cs_status cs_obstacle_map_upload(cs_processor* h, const int8_t* pixels);
+cs_status cs_obstacle_map_fill(cs_processor* h, int32_t value);
+cs_status cs_get_obstacle_visits(cs_processor* h, int64_t* touched);      /* map cells the rays touched since the last reset/fill (measurement) */
 
 /* ---- the hot path ---------------------------------------------------------------------------------- */
 

@@ -69,7 +69,7 @@ class Config(C.Structure):
         ("seed", C.c_uint64),
         ("stream", C.c_void_p),
         ("flags", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("obstacle_map_size", C.c_int32),
     ]
 
 
@@ -91,6 +91,8 @@ class Timing(C.Structure):
         ("h2d_ms", C.c_float),
         ("total_device_ms", C.c_float),
         ("host_wait_ms", C.c_double),
+        ("obstacle_ms", C.c_float),
+        ("reserved", C.c_float),
     ]
 
 
@@ -120,6 +122,13 @@ SIGNATURES = {
     "cs_get_pose": (C.c_int, [_vp, _fp]),
     "cs_set_pose": (C.c_int, [_vp, _fp, _fp, C.c_int32]),
     "cs_get_map_info": (C.c_int, [_vp, _ip, _fp]),
+    "cs_set_unmapped_obstacle_hits": (C.c_int, [_vp, C.c_int32]),
+    "cs_set_max_obstacle_hits": (C.c_int, [_vp, C.c_int32]),
+    "cs_get_obstacle_map_info": (C.c_int, [_vp, _ip, _fp]),
+    "cs_obstacle_map_download": (C.c_int, [_vp, _vp]),
+    "cs_obstacle_map_upload": (C.c_int, [_vp, _vp]),
+    "cs_obstacle_map_fill": (C.c_int, [_vp, C.c_int32]),
+    "cs_get_obstacle_visits": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cs_search": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_uint32, C.POINTER(Result), _ip]),
     "cs_integrate": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(C.c_int64)]),
     "cs_update": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(Result)]),

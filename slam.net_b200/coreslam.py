@@ -5,6 +5,7 @@ Same names, argument meaning and call order as the C# classes they stand in for
 
   Ray, ScanSegment, ScanCloud   BaseSLAM/Ray.cs:10-32, ScanSegment.cs:13-29, ScanCloud.cs:10-21
   HoleMap                       CoreSLAM/HoleMap.cs:17-55
+  ObstacleMap                   CoreSLAM/ObstacleMap.cs:11-44
   CoreSLAMProcessor             CoreSLAM/CoreSLAMProcessor.cs:18-775 (ctor :119, Reset :167, Update :717,
                                 Dispose :757; properties :40-106)
 
@@ -140,10 +141,11 @@ class Processor:
 
     def __init__(self, physical_map_size: float, hole_map_size: int, start_pose, sigma_xy: float, sigma_theta: float,
                  iterations_per_thread: int, num_search_threads: int, *, device: int = 0, max_points: int = 0,
-                 seed: int = 0, stream: int = 0, flags: int = 0):
+                 seed: int = 0, stream: int = 0, flags: int = 0, obstacle_map_size: int = 0):
         cfg = N.Config()
         cfg.physical_map_size = physical_map_size
         cfg.hole_map_size = hole_map_size
+        cfg.obstacle_map_size = obstacle_map_size
         cfg.start_pose = (C.c_float * 3)(*[float(v) for v in start_pose])
         cfg.sigma_xy = sigma_xy
         cfg.sigma_theta = sigma_theta
@@ -164,6 +166,9 @@ class Processor:
         self.scale = float(scale.value)
         self.seed = seed
         self.sigma_xy, self.sigma_theta = sigma_xy, sigma_theta
+        self.obstacle_size = obstacle_map_size
+        N.lib().cs_get_obstacle_map_info(self._h, C.byref(size), C.byref(scale))
+        self.obstacle_scale = float(scale.value)
 
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
@@ -284,6 +289,32 @@ class Processor:
     def map_checksum(self) -> int:
         v = C.c_uint64()
         self._ck(N.lib().cs_map_checksum(self._h, C.byref(v)))
+        return int(v.value)
+
+    # -- ObstacleMap (needs obstacle_map_size > 0) -------------------------------------------------
+    def set_unmapped_obstacle_hits(self, v: int):
+        self._ck(N.lib().cs_set_unmapped_obstacle_hits(self._h, int(v)))
+
+    def set_max_obstacle_hits(self, v: int):
+        self._ck(N.lib().cs_set_max_obstacle_hits(self._h, int(v)))
+
+    def obstacle_map_download(self) -> np.ndarray:
+        px = np.empty((self.obstacle_size, self.obstacle_size), dtype=np.int8)
+        self._ck(N.lib().cs_obstacle_map_download(self._h, px.ctypes.data))
+        return px
+
+    def obstacle_map_upload(self, pixels):
+        px = np.ascontiguousarray(pixels, dtype=np.int8).reshape(-1)
+        if px.size != self.obstacle_size * self.obstacle_size:
+            raise ValueError("pixels must have Size*Size entries")
+        self._ck(N.lib().cs_obstacle_map_upload(self._h, px.ctypes.data))
+
+    def obstacle_map_fill(self, value: int):
+        self._ck(N.lib().cs_obstacle_map_fill(self._h, int(value)))
+
+    def obstacle_visits(self) -> int:
+        v = C.c_int64()
+        self._ck(N.lib().cs_get_obstacle_visits(self._h, C.byref(v)))
         return int(v.value)
 
     # -- diagnostics ------------------------------------------------------------------------------
@@ -460,9 +491,23 @@ class HoleMap:
         return self._proc.map_packed()
 
 
+class ObstacleMap:
+    """CoreSLAM/ObstacleMap.cs:11-44.  Pixels is a public readonly sbyte[,] (first index Y); reading it pulls the
+    device-resident map."""
+
+    def __init__(self, proc: Processor, size_pixels: int, size_meters: float):
+        self._proc = proc
+        self.Size = size_pixels
+        self.Scale = proc.obstacle_scale
+
+    @property
+    def Pixels(self) -> np.ndarray:
+        return self._proc.obstacle_map_download()
+
+
 class CoreSLAMProcessor:
-    """Drop-in for CoreSLAM.CoreSLAMProcessor (CoreSLAM/CoreSLAMProcessor.cs).  The ObstacleMap half of
-    Update (:540-593) is outside the accelerated path and not provided."""
+    """Drop-in for CoreSLAM.CoreSLAMProcessor (CoreSLAM/CoreSLAMProcessor.cs): both halves of Update run on the
+    device (HoleMap :496-534, ObstacleMap :540-593)."""
 
     def __init__(self, physicalMapSize: float, holeMapSize: int, obstacleMapSize: int, startPose, sigmaXY: float,
                  sigmaTheta: float, iterationsPerThread: int, numSearchThreads: int, *, device: int = 0,
@@ -473,10 +518,12 @@ class CoreSLAMProcessor:
         self.SearchIterationsPerThread = int(iterationsPerThread)
         self.NumSearchThreads = int(numSearchThreads)
         self._proc = Processor(physicalMapSize, holeMapSize, startPose, sigmaXY, sigmaTheta, iterationsPerThread,
-                               numSearchThreads, device=device, seed=seed, max_points=max_points, flags=flags)
+                               numSearchThreads, device=device, seed=seed, max_points=max_points, flags=flags,
+                               obstacle_map_size=obstacleMapSize)
         self.HoleMap = HoleMap(self._proc, holeMapSize, physicalMapSize)
-        self.ObstacleMap = None  # out of scope (stays in C# on the host)
+        self.ObstacleMap = ObstacleMap(self._proc, obstacleMapSize, physicalMapSize) if obstacleMapSize > 0 else None
         self._quality, self._hole_width, self._psb = 50, 0.6, 5
+        self._unmapped, self._max_hits = -5, 10
         self._pose = _f32(startPose)
         self.LastResult: Optional[SearchResult] = None
 
@@ -485,6 +532,19 @@ class CoreSLAMProcessor:
     Quality = property(lambda s: s._quality)
     HoleWidth = property(lambda s: s._hole_width)
     PositionSearchBeginning = property(lambda s: s._psb)
+    UnmappedObstacleHits = property(lambda s: s._unmapped)
+    MaxObstacleHits = property(lambda s: s._max_hits)
+
+    @UnmappedObstacleHits.setter
+    def UnmappedObstacleHits(self, v):
+        """:98 — 'After changing this, Reset function has to be called!' """
+        self._proc.set_unmapped_obstacle_hits(v)
+        self._unmapped = int(v)
+
+    @MaxObstacleHits.setter
+    def MaxObstacleHits(self, v):
+        self._proc.set_max_obstacle_hits(v)
+        self._max_hits = int(v)
 
     @Quality.setter
     def Quality(self, v):

@@ -19,6 +19,7 @@
 
 #include "../../include/coreslam_b200.h"
 #include "cs_kernels.cuh"
+#include "cs_obstacle.cuh"
 
 static_assert(sizeof(CsDevResult) == sizeof(cs_result), "cs_result layout");
 static_assert(sizeof(cs_config) == 72, "cs_config layout (ctypes / P/Invoke mirror it)");
@@ -63,6 +64,11 @@ struct cs_processor {
   int* d_distances = nullptr;
   long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
+
+  // ObstacleMap (cfg.obstacle_map_size > 0): CoreSLAM/ObstacleMap.cs, CoreSLAMProcessor.cs:53, :132-133
+  CsObstacle ho{};               // host mirror of the descriptor
+  CsObstacle* d_obst = nullptr;
+  int unmapped_obstacle_hits = -5;  // :98
 
   // staging: [hdr 64][points][cand][cand_cs]
   size_t stage_bytes = 0;
@@ -352,6 +358,24 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   return cudaGetLastError();
 }
 
+// UpdateObstacleMap (CoreSLAMProcessor.cs:540-593) for n_sessions sessions: the ray kernel (hits + no-hit marks), then the
+// sweep over the marked tiles.  Plain stream order: both follow the rings kernel of the same step.
+cudaError_t launch_obstacle_update(cudaStream_t stream, const CsSession* d_sess, const CsObstacle* d_obst, const CsObstacle& ho,
+                                   const CsStepArgs& a, int n_points, int n_sessions, int num_sms, uint64_t* launches) {
+  const int warps = CS_OBST_RAY_THREADS / 32;
+  int blocks = (n_points + warps - 1) / warps;
+  if (blocks > num_sms * 8) blocks = num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  cs_obstacle_rays_kernel<<<dim3((unsigned)blocks, (unsigned)n_sessions), CS_OBST_RAY_THREADS, 0, stream>>>(d_sess, d_obst, a);
+  (*launches)++;
+  const int n_words = ho.words_per_row * (ho.rows / 4);
+  int sblocks = (n_words + 255) / 256;
+  if (sblocks > num_sms * 8) sblocks = num_sms * 8;
+  cs_obstacle_sweep_kernel<<<dim3((unsigned)sblocks, (unsigned)n_sessions), 256, 0, stream>>>(d_obst);
+  (*launches)++;
+  return cudaGetLastError();
+}
+
 cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base, int phases = CS_PHASE_ALL) {
   LaunchCtx c{};
   c.num_sms = device_sm_count(h->device);
@@ -368,6 +392,10 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.ev_pose = (want_pose_event && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 0] : nullptr;
   c.ev_done = (timing && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 1] : nullptr;
   CS_CUDA(h, launch_step_ctx(c, a, n_points, rings, phases));
+  if (h->d_obst && (phases & CS_PHASE_FINISH) && a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0) {
+    // UpdateObstacleMap (:751) follows UpdateHoleMap (:750): same pose (CsSession::cur_pose), same cloud
+    CS_CUDA(h, launch_obstacle_update(c.stream, h->d_sess, h->d_obst, h->ho, a, n_points, 1, c.num_sms, &h->launches));
+  }
   if (c.ev_done) cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
   return CS_OK;
 }
@@ -415,6 +443,8 @@ cs_status collect_timing(cs_processor* h, bool had_h2d) {
   cudaEventElapsedTime(&ms, h->tm.ev[2], h->tm.ev[3]); t.integrate_ms = ms;  // rings kernel (+ set-up kernels of big scans)
   t.finalize_ms = 0.f;
   cudaEventElapsedTime(&ms, h->tm.ev[0], h->tm.ev[4]); t.total_device_ms = ms;
+  t.obstacle_ms = 0.f;
+  if (h->d_obst) { cudaEventElapsedTime(&ms, h->tm.ev[3], h->tm.ev[4]); t.obstacle_ms = ms; }
   return CS_OK;
 }
 
@@ -452,6 +482,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   if (n_cand > (1ll << 26)) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "too many candidates per scan");
   const int max_points = cfg->max_points > 0 ? cfg->max_points : 16384;
   if (max_points > 65536) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "max_points must be <= 65536");
+  if (cfg->obstacle_map_size < 0 || cfg->obstacle_map_size > 16384)
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "obstacle_map_size must be 0 (no ObstacleMap) or in [1, 16384], got %d",
+                cfg->obstacle_map_size);
 
   int ndev = cs_device_count();
   if (ndev <= 0)
@@ -514,6 +547,20 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_slot, h->h_slot, 0));
   memset(h->h_slot, 0, 128);
   for (auto& e : h->tm.ev) CS_CREATE_CUDA(cudaEventCreate(&e));
+  if (cfg->obstacle_map_size > 0) {  // :132-133
+    CsObstacle& o = h->ho;
+    o.size = cfg->obstacle_map_size;
+    o.pitch = (o.size + 7) / 8 * 8;
+    o.rows = (o.size + 3) / 4 * 4;
+    o.words_per_row = o.pitch / 8;
+    o.scale = (float)cfg->obstacle_map_size / cfg->physical_map_size;  // ObstacleMap.cs:20
+    o.max_hits = 10;                                                   // :103
+    CS_CREATE_CUDA(cudaMalloc(&o.pixels, (size_t)o.pitch * o.rows));
+    CS_CREATE_CUDA(cudaMalloc(&o.no_hit, (size_t)o.words_per_row * (o.rows / 4) * sizeof(uint32_t)));
+    CS_CREATE_CUDA(cudaMalloc(&o.touched, sizeof(long long)));
+    CS_CREATE_CUDA(cudaMalloc(&h->d_obst, sizeof(CsObstacle)));
+    CS_CREATE_CUDA(cudaMemcpy(h->d_obst, &o, sizeof(CsObstacle), cudaMemcpyHostToDevice));
+  }
 
   // Optional L2 persistence window over the map (the gathers are served from L2 either way when the
   // map fits the 126 MB L2; the window only matters next to other L2-hungry work).
@@ -585,6 +632,10 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
   cudaFree(h->d_stage);
+  cudaFree(h->ho.pixels);
+  cudaFree(h->ho.no_hit);
+  cudaFree(h->ho.touched);
+  cudaFree(h->d_obst);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   if (h->h_slot) cudaFreeHost(h->h_slot);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -612,7 +663,86 @@ cs_status cs_reset(cs_processor* h) {  // CoreSLAMProcessor.cs:167-175
   if (st != CS_OK) return st;
   st = launch_fill(h, (uint16_t)((CS_TS_OBSTACLE + CS_TS_NO_OBSTACLE) / 2));  // :169
   if (st != CS_OK) return st;
+  if (h->d_obst) {  // :170 ArrayEx.Fill(ObstacleMap.Pixels, UnmappedObstacleHits)
+    cs_obstacle_fill_kernel<<<148 * 2, 256, 0, h->stream>>>(h->ho, h->unmapped_obstacle_hits);
+    h->launches++;
+    CS_CUDA(h, cudaGetLastError());
+  }
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+// ---- ObstacleMap (CoreSLAM/ObstacleMap.cs; CoreSLAMProcessor.cs:53, :98, :103) --------------------------
+#define CS_NEED_OBSTACLE(h)                                                                                  \
+  do {                                                                                                       \
+    if (!(h)->d_obst) return fail((h), CS_ERR_STATE, "the handle was created without an ObstacleMap (obstacle_map_size = 0)"); \
+  } while (0)
+
+cs_status cs_set_unmapped_obstacle_hits(cs_processor* h, int32_t hits) {
+  CS_CHECK_HANDLE(h);
+  if (hits < -128 || hits > 127) return fail(h, CS_ERR_INVALID_ARGUMENT, "UnmappedObstacleHits is an sbyte");
+  h->unmapped_obstacle_hits = hits;  // takes effect at the next Reset, as in the reference (:96)
+  return CS_OK;
+}
+
+cs_status cs_set_max_obstacle_hits(cs_processor* h, int32_t hits) {
+  CS_CHECK_HANDLE(h);
+  if (hits < -128 || hits > 127) return fail(h, CS_ERR_INVALID_ARGUMENT, "MaxObstacleHits is an sbyte");
+  h->ho.max_hits = hits;
+  if (!h->d_obst) return CS_OK;
+  CS_CUDA(h, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(h->d_obst) + offsetof(CsObstacle, max_hits), &h->ho.max_hits, sizeof(int),
+                             cudaMemcpyHostToDevice, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_get_obstacle_map_info(const cs_processor* h, int32_t* size, float* scale) {
+  if (!h) return CS_ERR_INVALID_ARGUMENT;
+  if (size) *size = h->ho.size;
+  if (scale) *scale = h->ho.scale;
+  return CS_OK;
+}
+
+cs_status cs_obstacle_map_download(cs_processor* h, int8_t* pixels) {
+  CS_CHECK_HANDLE(h);
+  CS_NEED_OBSTACLE(h);
+  if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
+  const CsObstacle& o = h->ho;
+  CS_CUDA(h, cudaMemcpy2DAsync(pixels, (size_t)o.size, o.pixels, (size_t)o.pitch, (size_t)o.size, (size_t)o.size,
+                               cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_obstacle_map_upload(cs_processor* h, const int8_t* pixels) {
+  CS_CHECK_HANDLE(h);
+  CS_NEED_OBSTACLE(h);
+  if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
+  const CsObstacle& o = h->ho;
+  CS_CUDA(h, cudaMemcpy2DAsync(o.pixels, (size_t)o.pitch, pixels, (size_t)o.size, (size_t)o.size, (size_t)o.size,
+                               cudaMemcpyHostToDevice, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
+}
+
+cs_status cs_obstacle_map_fill(cs_processor* h, int32_t value) {
+  CS_CHECK_HANDLE(h);
+  CS_NEED_OBSTACLE(h);
+  if (value < -128 || value > 127) return fail(h, CS_ERR_INVALID_ARGUMENT, "ObstacleMap pixels are sbyte");
+  cs_obstacle_fill_kernel<<<148 * 2, 256, 0, h->stream>>>(h->ho, value);
+  h->launches++;
+  CS_CUDA(h, cudaGetLastError());
+  return CS_OK;
+}
+
+cs_status cs_get_obstacle_visits(cs_processor* h, int64_t* touched) {
+  CS_CHECK_HANDLE(h);
+  CS_NEED_OBSTACLE(h);
+  if (!touched) return fail(h, CS_ERR_INVALID_ARGUMENT, "null out");
+  long long v = 0;
+  CS_CUDA(h, cudaMemcpyAsync(&v, h->ho.touched, sizeof(v), cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  *touched = v;
   return CS_OK;
 }
 
@@ -1265,6 +1395,9 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   const cs_config& c0 = cfgs[0];
   if (c0.hole_map_size < 8 || c0.hole_map_size > 16384 || !(c0.physical_map_size > 0.f) || c0.iterations_per_thread < 0)
     return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_batch_create: bad map size / iterations");
+  for (int j = 0; j < n_sessions; j++)
+    if (cfgs[j].obstacle_map_size != 0)
+      return bfail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_batch_create: session batches carry no ObstacleMap (obstacle_map_size must be 0)");
   for (int j = 1; j < n_sessions; j++) {
     const cs_config& c = cfgs[j];
     if (c.hole_map_size != c0.hole_map_size || c.physical_map_size != c0.physical_map_size ||
