@@ -42,6 +42,8 @@ typedef enum cs_status {
 #define CS_FLAG_NO_HOST_SPIN 0x8u  /* wait for the pose with cudaEventSynchronize instead of polling mapped memory */
 #define CS_FLAG_L2_PERSIST 0x10u   /* put a persisting L2 access-policy window over the map */
 #define CS_FLAG_DEBUG_RAYS 0x20u   /* keep x1,y1,x2,y2,xp,yp of every ray of the last integration (cs_get_rays) */
+#define CS_FLAG_SEARCH_WARP 0x40u  /* always search with the warp-per-candidate kernel (default: by candidate count) */
+#define CS_FLAG_SEARCH_SLAB 0x80u  /* always search with the heading-sorted slab kernels, whatever the candidate count */
 
 typedef struct cs_processor cs_processor; /* opaque; replaces a CoreSLAMProcessor instance */
 typedef struct cs_scanlog cs_scanlog;     /* opaque; device-resident scan log for replays */

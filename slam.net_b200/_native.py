@@ -102,6 +102,8 @@ FLAG_KEEP_DISTANCES = 0x4
 FLAG_NO_HOST_SPIN = 0x8
 FLAG_L2_PERSIST = 0x10
 FLAG_DEBUG_RAYS = 0x20
+FLAG_SEARCH_WARP = 0x40
+FLAG_SEARCH_SLAB = 0x80
 
 STATUS_NAMES = {0: "CS_OK", 1: "CS_ERR_INVALID_ARGUMENT", 2: "CS_ERR_NO_DEVICE", 3: "CS_ERR_CUDA",
                 4: "CS_ERR_OUT_OF_MEMORY", 5: "CS_ERR_CAPACITY", 6: "CS_ERR_STATE", 7: "CS_ERR_NCCL"}

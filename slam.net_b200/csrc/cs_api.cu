@@ -65,6 +65,14 @@ struct cs_processor {
   long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
 
+  // slab search scratch (CsSession::s2_*), allocated when the handle has enough candidates for it to pay
+  float4* d_s2_sorted = nullptr;
+  float4* d_s2_tmp = nullptr;
+  unsigned long long* d_s2_meta = nullptr;
+  unsigned long long* d_s2_acc = nullptr;
+  unsigned* d_s2_ghist = nullptr;
+  int s2_cap = 0, s2_toggle = 0;
+
   // ObstacleMap (cfg.obstacle_map_size > 0): CoreSLAM/ObstacleMap.cs, CoreSLAMProcessor.cs:53, :132-133
   CsObstacle ho{};               // host mirror of the descriptor
   CsObstacle* d_obst = nullptr;
@@ -208,9 +216,14 @@ double max_range_of(const float* points, int n) {
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0;
+  int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
+    search2 = geti("CS_TUNE_SEARCH2");          // -1: never use the slab search, 0: built-in rule
+    s2_points = geti("CS_TUNE_S2_POINTS");      // points per cluster
+    s2_threads = geti("CS_TUNE_S2_THREADS");    // candidates per slab
+    s2_min_cand = geti("CS_TUNE_S2_MIN_CAND");  // fewest candidates the slab search is used for
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
   }
@@ -249,7 +262,74 @@ int cs_search_warps(long long cand_count, int n_sessions, int num_sms) {
   return best;
 }
 
+// Slab search (cs_sort_kernel + cs_search2_kernel) instead of the warp-per-candidate kernel: one session alone whose
+// candidate count fills the machine with slabs.  Block (c, s) = points [c*points, ...) x sorted candidates [s*threads, ...).
+constexpr int kS2MinCand = 1024;
+struct S2Plan {
+  int points = 0, threads = 0, clusters = 0, slabs = 0;
+};
+int cs_s2_min_cand(uint32_t flags) {  // fewest candidates (searchPose included) the slab search is used for; 0 = never
+  if ((flags & CS_FLAG_SEARCH_WARP) || tune().search2 < 0) return 0;
+  if (flags & CS_FLAG_SEARCH_SLAB) return 1;
+  return tune().s2_min_cand > 0 ? tune().s2_min_cand : kS2MinCand;
+}
+bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_count, int n_points, int num_sms, S2Plan* p) {
+  if (min_cand <= 0 || n_sessions != 1 || s2_cap <= 0 || cand_count > s2_cap || n_points < 1) return false;
+  if (cand_count < min_cand) return false;
+  // the plan depends on (candidates, points, SMs) only: remember the last one (a replay asks for the same every scan)
+  struct Memo { long long cand = -1; int points = -1, sms = -1; bool ok = false; S2Plan plan; };
+  static thread_local Memo memo;
+  if (memo.cand == cand_count && memo.points == n_points && memo.sms == num_sms) {
+    *p = memo.plan;
+    return memo.ok;
+  }
+  memo.cand = cand_count; memo.points = n_points; memo.sms = num_sms; memo.ok = false;
+  // Launch shape: the kernel is one resident wave of blocks (clusters x slabs) and ends when the busiest SM ends.  A lane
+  // pays a fixed set-up (candidate pose, cos/sin: ~kSetup instruction slots) plus ~kLookup per point of its cluster, in
+  // whole batches of CS_S2_BATCH; a block's cost is that times its warps, and an SM issues about kIpcPerWarp
+  // instructions per clock and resident warp, up to kIpcMax.  Pick the (points, threads) pair with the shortest busiest SM.
+  constexpr double kSetup = 450.0, kLookup = 26.0, kIpcPerWarp = 0.12, kIpcMax = 3.0;
+  int best_points = 0, best_threads = 0;
+  double best_cost = 0.0;
+  const int p_lo = tune().s2_points > 0 ? tune().s2_points : CS_S2_BATCH;
+  const int p_hi = tune().s2_points > 0 ? tune().s2_points : CS_S2_MAX_POINTS;
+  const int t_lo = tune().s2_threads > 0 ? (tune().s2_threads + 31) / 32 * 32 : 64;
+  const int t_hi = tune().s2_threads > 0 ? (t_lo < CS_S2_MAX_THREADS ? t_lo : CS_S2_MAX_THREADS) : CS_S2_MAX_THREADS;
+  for (int points = p_lo; points <= p_hi && points <= CS_S2_MAX_POINTS; points += 4) {
+    const long long clusters = (n_points + points - 1) / points;
+    if (clusters > CS_S2_MAX_CLUSTERS) continue;
+    const int batches = ((int)((n_points + clusters - 1) / clusters) + CS_S2_BATCH - 1) / CS_S2_BATCH;  // of the fullest cluster
+    for (int threads = t_hi; threads >= t_lo; threads -= 32) {  // bigger blocks win ties: one cluster's lines shared by more warps
+      const long long slabs = (cand_count + threads - 1) / threads;
+      if (slabs > 65535) continue;
+      const long long blocks = clusters * slabs;
+      const long long per_sm = (blocks + num_sms - 1) / num_sms;
+      const double warps = (double)per_sm * (threads / 32);
+      const double resident = warps < 48.0 ? warps : 48.0;
+      const double ipc = resident * kIpcPerWarp < kIpcMax ? resident * kIpcPerWarp : kIpcMax;
+      const double cost = warps * (kSetup + kLookup * CS_S2_BATCH * batches) / ipc;
+      if (best_points == 0 || cost < best_cost * 0.999) { best_cost = cost; best_points = points; best_threads = threads; }
+    }
+  }
+  if (best_points == 0) return false;
+  const long long clusters = (n_points + best_points - 1) / best_points;
+  const long long slabs = (cand_count + best_threads - 1) / best_threads;
+  if (slabs > 65535 || clusters > CS_S2_MAX_CLUSTERS) return false;
+  // even out: the same number of blocks with the smallest equal shares
+  p->clusters = (int)clusters;
+  p->points = (int)((n_points + clusters - 1) / clusters);
+  p->slabs = (int)slabs;
+  p->threads = (int)(((cand_count + slabs - 1) / slabs + 31) / 32 * 32);
+  memo.plan = *p;
+  memo.ok = true;
+  return true;
+}
+
 struct LaunchCtx {
+  int s2_cap = 0;            // capacity of the slab-search scratch (0: none)
+  int s2_min_cand = 0;       // cs_s2_min_cand of the handle
+  int* s2_toggle = nullptr;  // which half of CsSession::s2_sorted the next sort writes
+  const CsSession* hs = nullptr;  // host mirror of the session (host-owned constants for the slab kernels)
   int num_sms;
   cudaStream_t stream;
   CsSession* d_sess;
@@ -301,7 +381,45 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.step_id = *c.step_counter;
   }
   cudaError_t e = cudaSuccess;
-  if ((phases & CS_PHASE_SEARCH) && searching) {
+  S2Plan s2;
+  if ((phases & CS_PHASE_SEARCH) && searching &&
+      cs_plan_search2(c.n_sessions, c.s2_cap, c.s2_min_cand, a.cand_count, a.s2_host_points, c.num_sms, &s2)) {
+    a.s2_points = s2.points;
+    a.s2_slab = s2.threads;
+    a.s2_slot = (*c.s2_toggle ^= 1);
+    a.s2_map = c.hs->map;
+    a.s2_sorted = c.hs->s2_sorted + (size_t)a.s2_slot * c.hs->s2_cap;
+    a.s2_tmp = c.hs->s2_tmp;
+    a.s2_meta = c.hs->s2_meta;
+    a.s2_acc = c.hs->s2_acc;
+    a.s2_ghist = c.hs->s2_ghist;
+    a.s2_seed = c.hs->seed;
+    a.s2_size = c.hs->size;
+    a.s2_pitch_tiles = c.hs->pitch_tiles;
+    a.s2_scale = c.hs->scale;
+    a.s2_sigma_xy = c.hs->sigma_xy;
+    a.s2_sigma_theta = c.hs->sigma_theta;
+    if (a.cand_count <= CS_SORT_THREADS * CS_SORT_REG) {
+      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>, dim3(1), dim3(CS_SORT_THREADS), 0,
+                     c.stream, c.d_sess, a);
+      if (e != cudaSuccess) return e;
+      (*c.launches)++;
+    } else {
+      const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_THREADS * CS_SORT_REG - 1) / (CS_SORT_THREADS * CS_SORT_REG));
+      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_hist_kernel<true> : cs_sort_hist_kernel<false>, dim3(sort_blocks),
+                     dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+      if (e != cudaSuccess) return e;
+      e = launch_pdl(cs_sort_scatter_kernel, dim3(sort_blocks), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+      if (e != cudaSuccess) return e;
+      (*c.launches) += 2;
+    }
+    dispatch_layout(c.tiled, [&](auto T) {
+      e = launch_pdl(cs_search2_kernel<decltype(T)::value>, dim3((unsigned)s2.clusters, (unsigned)s2.slabs), dim3(s2.threads), 0,
+                     c.stream, c.d_sess, a);
+    });
+    if (e != cudaSuccess) return e;
+    (*c.launches)++;
+  } else if ((phases & CS_PHASE_SEARCH) && searching) {
     const int warps = cs_search_warps(a.cand_count, c.n_sessions, c.num_sms);
     dim3 grid((unsigned)((a.cand_count + warps - 1) / warps), (unsigned)c.n_sessions);
     int chunk = (n_points + 1) & ~1;  // even: the staging loop moves two points per 16-byte load
@@ -387,6 +505,10 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.step_counter = &h->step_counter;
   c.diag = h->d_ring_cycles;
   c.diag_rings = h->size;
+  c.s2_cap = h->s2_cap;
+  c.s2_min_cand = cs_s2_min_cand(h->cfg.flags);
+  c.s2_toggle = &h->s2_toggle;
+  c.hs = &h->hs;
   a.hdr_stride = 1;
   const bool want_pose_event = timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN));
   c.ev_pose = (want_pose_event && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 0] : nullptr;
@@ -540,6 +662,16 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
                                       (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
+  if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
+    h->s2_cap = (int)n_cand + 1;
+    CS_CREATE_CUDA(cudaMalloc(&h->d_s2_sorted, (size_t)2 * h->s2_cap * sizeof(float4)));
+    CS_CREATE_CUDA(cudaMalloc(&h->d_s2_tmp, (size_t)h->s2_cap * sizeof(float4)));
+    CS_CREATE_CUDA(cudaMalloc(&h->d_s2_meta, (size_t)h->s2_cap * sizeof(unsigned long long)));
+    CS_CREATE_CUDA(cudaMalloc(&h->d_s2_acc, (size_t)h->s2_cap * sizeof(unsigned long long)));
+    CS_CREATE_CUDA(cudaMemsetAsync(h->d_s2_acc, 0, (size_t)h->s2_cap * sizeof(unsigned long long), h->stream));
+    CS_CREATE_CUDA(cudaMalloc(&h->d_s2_ghist, (size_t)(CS_SORT_BINS + 1) * sizeof(unsigned)));
+    CS_CREATE_CUDA(cudaMemsetAsync(h->d_s2_ghist, 0, (size_t)(CS_SORT_BINS + 1) * sizeof(unsigned), h->stream));
+  }
   h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total;
   CS_CREATE_CUDA(cudaHostAlloc(&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
   CS_CREATE_CUDA(cudaMalloc(&h->d_stage, h->stage_bytes));
@@ -605,6 +737,12 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   s.ray_stride = h->ray_stride;
   s.batch_stride = h->batch_stride;
   s.prep_words = h->d_prep_words;
+  s.s2_sorted = h->d_s2_sorted;
+  s.s2_tmp = h->d_s2_tmp;
+  s.s2_meta = h->d_s2_meta;
+  s.s2_acc = h->d_s2_acc;
+  s.s2_ghist = h->d_s2_ghist;
+  s.s2_cap = h->s2_cap;
   s.ray_dbg = h->d_ray_dbg;
   s.distances = (cfg->flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
   cs_status st = cs_reset(h);
@@ -631,6 +769,11 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
+  cudaFree(h->d_s2_sorted);
+  cudaFree(h->d_s2_tmp);
+  cudaFree(h->d_s2_meta);
+  cudaFree(h->d_s2_acc);
+  cudaFree(h->d_s2_ghist);
   cudaFree(h->d_stage);
   cudaFree(h->ho.pixels);
   cudaFree(h->ho.no_hit);
@@ -839,6 +982,7 @@ cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, cons
   a.n_cand = n_cand;
   a.cand_first = 0;
   a.cand_count = n_cand + 1;
+  a.s2_host_points = n_points;
   cs_status st = launch_step(h, a, 0, 0, false, 0);
   if (st != CS_OK) return st;
   if (distances) {
@@ -927,6 +1071,7 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   a.n_cand = h->n_cand;
   a.cand_first = 0;
   a.cand_count = h->n_cand + 1;
+  a.s2_host_points = n_points;
   *out_args = a;
   return CS_OK;
 }
@@ -1266,6 +1411,7 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     a.n_cand = h->n_cand;
     a.cand_first = 0;
     a.cand_count = h->n_cand + 1;
+    a.s2_host_points = log->h_hdr[sidx].n_points;
     cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, rings_hint(h, log->h_max_range[sidx]), per_kernel, 2);
     if (st != CS_OK) return st;
     h->parity ^= 1;
@@ -1707,8 +1853,9 @@ cs_status cs_batch_get_launch_count(cs_batch* b, uint64_t* launches) {
 
 cs_status cs_set_flags(cs_processor* h, uint32_t flags) {
   CS_CHECK_HANDLE(h);
-  const uint32_t fixed = CS_FLAG_ROW_MAJOR_MAP | CS_FLAG_L2_PERSIST | CS_FLAG_DEBUG_RAYS;
-  if ((flags & fixed) != (h->cfg.flags & fixed)) return fail(h, CS_ERR_INVALID_ARGUMENT, "map layout / L2 window are fixed at creation");
+  const uint32_t fixed = CS_FLAG_ROW_MAJOR_MAP | CS_FLAG_L2_PERSIST | CS_FLAG_DEBUG_RAYS | CS_FLAG_SEARCH_WARP | CS_FLAG_SEARCH_SLAB;
+  if ((flags & fixed) != (h->cfg.flags & fixed))
+    return fail(h, CS_ERR_INVALID_ARGUMENT, "map layout / L2 window / debug rays / search kernel choice are fixed at creation");
   h->cfg.flags = flags;
   int* dist = (flags & CS_FLAG_KEEP_DISTANCES) ? h->d_distances : nullptr;
   h->hs.distances = dist;

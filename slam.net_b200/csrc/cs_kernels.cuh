@@ -76,7 +76,7 @@ struct CsDevResult {  // device twin of cs_result (include/coreslam_b200.h)
 };
 
 struct CsSession {  // one CoreSLAMProcessor, device resident
-  uint16_t* map;    // HoleMap.Pixels; tiled: 8x8-cell tiles of 128 B, 4x4-cell quadrants of 32 B
+  uint16_t* map;    // HoleMap.Pixels; tiled: 8x8-cell tiles of 128 B (one line), rows of 8 cells inside, 8x2 cells per 32 B sector
   int size;         // HoleMap.Size
   int pitch_tiles;  // tiles per tile-row (tiled layout)
   float scale;      // HoleMap.Scale
@@ -111,6 +111,14 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   long long visits_slot[2];    // cells written by the integration of step id & 1 = sum over valid rays of dxc+1
   unsigned ring_ticket[2];     // work-unit tickets of the rings kernel; slot = step id & 1, re-armed for the next step by
                                // the publishing thread of this step
+  // ---- scratch of the slab search (cs_sort_kernel + cs_search2_kernel; one session alone, many candidates)
+  float4* s2_sorted;            // [2][s2_cap]: this step's candidates in ascending order of heading offset, as
+                                // (x, y, theta [offsets or absolute pose], flat index bits); slot = CsStepArgs::s2_slot
+  float4* s2_tmp;               // [s2_cap] the same entries in flat order (scratch of the running sort)
+  unsigned long long* s2_meta;  // [s2_cap] heading bin << 32 | rank inside the bin (scratch of the running sort)
+  unsigned long long* s2_acc;   // [s2_cap] per sorted position: cell sum | in-bounds count << 32 | clusters arrived << 49; zero between steps
+  int s2_cap, pad3;
+  unsigned* s2_ghist;           // [CS_SORT_BINS + 1] histogram of the multi-block sort + its arrival counter; zero between steps
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
@@ -140,6 +148,23 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   long long* diag;        // optional diagnostics buffer (8 values per block of the rings kernel, then 8 per block of
                           // the search kernel), see cs_get_ring_cycles
   int diag_rings;         // records reserved for the rings kernel in diag
+  // slab search (cs_search2_kernel): block (c, s) evaluates points [c*s2_points, ...) for sorted candidates [s*s2_slab, ...)
+  int s2_points;          // points per cluster (<= CS_S2_MAX_POINTS)
+  int s2_slab;            // candidates per slab (multiple of 32, = threads per block)
+  int s2_slot;            // which half of CsSession::s2_sorted this step uses
+  int s2_host_points;     // the host's copy of hdr.n_points (0: unknown, the slab search is not used)
+  // host-owned session constants by value, so that the slab kernels' first instructions do not wait for a (cold)
+  // read of the session descriptor: CsSession::map, size, pitch_tiles, scale, sigmas, seed, and the scratch pointers
+  const uint16_t* s2_map;
+  float4* s2_sorted;             // this step's half of CsSession::s2_sorted
+  float4* s2_tmp;
+  unsigned long long* s2_meta;
+  unsigned long long* s2_acc;
+  unsigned* s2_ghist;            // CS_SORT_BINS + 1 words, zero between steps (multi-block sort)
+  unsigned long long s2_seed;
+  int s2_size, s2_pitch_tiles;
+  float s2_scale, s2_sigma_xy, s2_sigma_theta;
+  int s2_pad;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -148,9 +173,11 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
 template <bool TILED>
 __device__ __forceinline__ uint32_t cs_cell_offset(int x, int y, int size, int pitch_tiles) {
   if (TILED) {
-    uint32_t tile = (uint32_t)(y >> 3) * (uint32_t)pitch_tiles + (uint32_t)(x >> 3);
-    uint32_t in = (uint32_t)(x & 3) | ((uint32_t)(y & 3) << 2) | ((uint32_t)(x & 4) << 2) | ((uint32_t)(y & 4) << 3);
-    return tile * 64u + in;
+    // tile (y>>3, x>>3) * 64 + (y&7)*8 + (x&7), written so that it costs two AND, one shift-add and two multiply-adds:
+    // x + 7*(x & ~7) = (x&7) + 64*(x>>3);  8*y + (y & ~7)*(8*pitch - 8) = 64*pitch*(y>>3) + 8*(y&7)
+    const uint32_t ux = (uint32_t)x, uy = (uint32_t)y;
+    const uint32_t xx = (ux & ~7u) * 7u + ux;
+    return (uy & ~7u) * ((uint32_t)pitch_tiles * 8u - 8u) + (uy << 3) + xx;
   } else {
     return (uint32_t)y * (uint32_t)size + (uint32_t)x;
   }
@@ -630,6 +657,340 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   CsDevResult* result = a.result ? a.result + (size_t)sj * a.result_stride : nullptr;
   cs_publish(S, hdr, a, cand, result, guess != ~0ull, guess);
   if (tl) { tl[6] = cs_globaltimer(); tl[7] = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// slab search: the same arithmetic as cs_search_kernel, laid out for cache locality instead of one warp per
+// candidate.  Used for one session alone with many candidates (the host decides, see cs_use_search2).
+//
+// A candidate's lookups land where the search pose's would, displaced by its offsets: (dx, dy) moves a point by a
+// few cells, dtheta by range x dtheta — tens to hundreds of cells.  So candidates with nearly the same heading
+// offset read nearly the same cells for the same point.  cs_sort_kernel orders the step's candidates by heading
+// offset (a counting sort over fixed bins of width sigma_theta / 256: only locality depends on it, the arg-min is
+// decided by (distance, flat index) whatever the evaluation order).  cs_search2_kernel then gives every LANE one
+// candidate of the sorted order and walks a cluster of consecutive scan points (broadcast from shared memory):
+//   * the 32 lanes of a warp look the same point up under 32 neighbouring headings: a handful of 128-byte tiles
+//     per request instead of one per lane (the L1 tag stage handles one line per clock);
+//   * a block = one slab of consecutive sorted candidates x one cluster of consecutive points sweeps a compact
+//     piece of the map, which its SM's L1 keeps: L2 sees each tile about once per block instead of once per lookup;
+//   * no warp reduction: a lane owns its candidate's partial sum and adds it (cells << 0 | in-bounds count << 40)
+//     to the candidate's 64-bit accumulator with one RED per cluster.
+// The cluster that arrives last at a slab turns the slab's sums into distances (:251-258) and arg-mins them; the slab
+// that finishes last runs the Update glue exactly like the last block of cs_search_kernel.
+// ---------------------------------------------------------------------------------------------------
+#define CS_S2_MAX_POINTS 128   // most points per cluster (1 KB of shared memory)
+#define CS_S2_BATCH 16         // lookups a lane has in flight: the cluster is walked in batches of this many points
+#define CS_S2_MAX_THREADS 512  // most candidates per slab
+#define CS_S2_ARRIVAL_SHIFT 49 // accumulator word: cells (bits 0-31) | in-bounds count (32-48) | clusters arrived (49-63)
+#define CS_S2_MAX_CLUSTERS 16384
+#define CS_SORT_BINS 2048      // heading bins: [-4 sigma, 4 sigma) in steps of sigma / 256, clamped
+#define CS_SORT_THREADS 1024
+#define CS_SORT_REG 8          // candidates a thread keeps in registers between the two passes (more: global scratch)
+
+// heading bin of a candidate whose heading differs from the search pose's by `rel`
+__device__ __forceinline__ unsigned cs_sort_bin(float rel, float inv) {
+  return (unsigned)(int)fminf(fmaxf(rel * inv + (float)(CS_SORT_BINS / 2), 0.f), (float)(CS_SORT_BINS - 1));  // NaN -> 0
+}
+
+// Block-wide exclusive scan of s_hist[CS_SORT_BINS] in place (CS_SORT_THREADS threads, two bins each); `c0`, `c1` are
+// this thread's two counts.
+__device__ __forceinline__ void cs_sort_scan(unsigned* s_hist, unsigned* s_warp, unsigned c0, unsigned c1) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned v = c0 + c1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  if (lane == 31) s_warp[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned w0 = s_warp[lane];
+    unsigned w = w0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    s_warp[lane] = w - w0;  // exclusive over warps
+  }
+  __syncthreads();
+  const unsigned excl = v - (c0 + c1) + s_warp[warp];
+  s_hist[2 * tid] = excl;
+  s_hist[2 * tid + 1] = excl + c0;
+  __syncthreads();
+}
+
+// One block sorts up to CS_SORT_THREADS * CS_SORT_REG candidates.  PHILOX = false: the candidates come from a table
+// (offsets or absolute poses); every load of the pass is in flight at once, everything stays in registers.  PHILOX =
+// true: the deviates are generated here, one candidate at a time (the generator is long; unrolling it eight times
+// would cost more in instruction fetch than it saves), parked in global scratch between the two passes.
+template <bool PHILOX>
+__global__ void __launch_bounds__(CS_SORT_THREADS)
+cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  __shared__ unsigned s_hist[CS_SORT_BINS];
+  __shared__ unsigned s_warp[CS_SORT_THREADS / 32];
+  // Nothing here depends on the previous step (inputs of this step and host-owned constants only), so no wait in
+  // front; the wait at the end keeps completion transitive: "this grid done" must imply "the grid in front done" for
+  // the search kernel behind.
+  cs_pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int n = a.cand_count;
+  float4* __restrict__ out = a.s2_sorted;
+  for (int i = tid; i < CS_SORT_BINS; i += CS_SORT_THREADS) s_hist[i] = 0u;
+  __syncthreads();
+  const float inv = a.s2_sigma_theta > 0.f ? 256.0f / a.s2_sigma_theta : 0.f;
+  if (PHILOX) {
+#pragma unroll 1
+    for (int i = tid; i < n; i += CS_SORT_THREADS) {
+      const int idx = a.cand_first + i;
+      float off[3] = {0.f, 0.f, 0.f};
+      if (idx > 0) cs_gauss3(a.s2_seed, a.scan_index, (uint32_t)(idx - 1), a.s2_sigma_xy, a.s2_sigma_theta, off);
+      const unsigned bin = cs_sort_bin(off[2], inv);
+      const unsigned rank = atomicAdd(&s_hist[bin], 1u);
+      a.s2_tmp[i] = make_float4(off[0], off[1], off[2], __int_as_float(idx));
+      a.s2_meta[i] = ((unsigned long long)bin << 32) | rank;
+    }
+    __syncthreads();
+    cs_sort_scan(s_hist, s_warp, s_hist[2 * tid], s_hist[2 * tid + 1]);
+#pragma unroll 1
+    for (int i = tid; i < n; i += CS_SORT_THREADS) {
+      const unsigned long long m = a.s2_meta[i];
+      out[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = a.s2_tmp[i];
+    }
+  } else {
+    const float ref = a.cand_mode == CS_CAND_ABSOLUTE ? a.hdr[0].odo[2] : 0.f;  // headings are binned relative to the search pose
+    float ex[CS_SORT_REG], ey[CS_SORT_REG], ez[CS_SORT_REG];
+    unsigned met[CS_SORT_REG];  // bin << 16 | rank inside the bin (< 8192)
+#pragma unroll
+    for (int k = 0; k < CS_SORT_REG; k++) {
+      const int i = tid + k * CS_SORT_THREADS;
+      const int idx = a.cand_first + i;
+      ex[k] = 0.f; ey[k] = 0.f; ez[k] = 0.f;
+      if (i < n && idx > 0) {
+        const float* p = a.cand + 3 * (size_t)(idx - 1);
+        ex[k] = __ldg(p); ey[k] = __ldg(p + 1); ez[k] = __ldg(p + 2);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CS_SORT_REG; k++) {
+      const int i = tid + k * CS_SORT_THREADS;
+      const unsigned bin = cs_sort_bin((a.cand_first + i) > 0 ? ez[k] - ref : 0.f, inv);
+      met[k] = bin << 16;
+      if (i < n) met[k] |= atomicAdd(&s_hist[bin], 1u);
+    }
+    __syncthreads();
+    cs_sort_scan(s_hist, s_warp, s_hist[2 * tid], s_hist[2 * tid + 1]);
+#pragma unroll
+    for (int k = 0; k < CS_SORT_REG; k++) {
+      const int i = tid + k * CS_SORT_THREADS;
+      if (i < n) out[s_hist[met[k] >> 16] + (met[k] & 0xffffu)] = make_float4(ex[k], ey[k], ez[k], __int_as_float(a.cand_first + i));
+    }
+  }
+  cs_pdl_wait();
+}
+
+// Candidate sets too big for one block: the same counting sort over several blocks and two kernels.
+// cs_sort_hist_kernel: every block bins its CS_SORT_THREADS * CS_SORT_REG candidates, reserves a run inside each bin of the
+// global histogram (one atomicAdd per non-empty bin and block, the returned value is the block's base rank in that bin)
+// and parks entry and (bin, rank) in global scratch.  cs_sort_scatter_kernel: every block scans the complete histogram
+// and moves its candidates to their final positions; the last block re-arms the histogram.
+template <bool PHILOX>
+__global__ void __launch_bounds__(CS_SORT_THREADS)
+cs_sort_hist_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  __shared__ unsigned s_hist[CS_SORT_BINS];
+  cs_pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int n = a.cand_count;
+  const int base_i = blockIdx.x * (CS_SORT_THREADS * CS_SORT_REG);
+  const int end_i = min(n, base_i + CS_SORT_THREADS * CS_SORT_REG);
+  for (int i = tid; i < CS_SORT_BINS; i += CS_SORT_THREADS) s_hist[i] = 0u;
+  __syncthreads();
+  const float inv = a.s2_sigma_theta > 0.f ? 256.0f / a.s2_sigma_theta : 0.f;
+  const float ref = (!PHILOX && a.cand_mode == CS_CAND_ABSOLUTE) ? a.hdr[0].odo[2] : 0.f;
+#pragma unroll 1
+  for (int i = base_i + tid; i < end_i; i += CS_SORT_THREADS) {
+    const int idx = a.cand_first + i;
+    float off[3] = {0.f, 0.f, 0.f};
+    float rel = 0.f;
+    if (idx > 0) {
+      if (PHILOX) {
+        cs_gauss3(a.s2_seed, a.scan_index, (uint32_t)(idx - 1), a.s2_sigma_xy, a.s2_sigma_theta, off);
+        rel = off[2];
+      } else {
+        const float* p = a.cand + 3 * (size_t)(idx - 1);
+        off[0] = __ldg(p); off[1] = __ldg(p + 1); off[2] = __ldg(p + 2);
+        rel = off[2] - ref;
+      }
+    }
+    const unsigned bin = cs_sort_bin(rel, inv);
+    const unsigned rank = atomicAdd(&s_hist[bin], 1u);
+    a.s2_tmp[i] = make_float4(off[0], off[1], off[2], __int_as_float(idx));
+    a.s2_meta[i] = ((unsigned long long)bin << 32) | rank;
+  }
+  __syncthreads();
+  for (int b = tid; b < CS_SORT_BINS; b += CS_SORT_THREADS) {
+    const unsigned cnt = s_hist[b];
+    s_hist[b] = cnt ? atomicAdd(&a.s2_ghist[b], cnt) : 0u;  // this block's base rank inside bin b
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int i = base_i + tid; i < end_i; i += CS_SORT_THREADS) {
+    const unsigned long long m = a.s2_meta[i];  // this thread's own store
+    a.s2_meta[i] = m + s_hist[(unsigned)(m >> 32)];
+  }
+  cs_pdl_wait();  // completion stays transitive (see cs_sort_kernel)
+}
+
+__global__ void __launch_bounds__(CS_SORT_THREADS)
+cs_sort_scatter_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  __shared__ unsigned s_hist[CS_SORT_BINS];
+  __shared__ unsigned s_warp[CS_SORT_THREADS / 32];
+  __shared__ int s_last;
+  cs_pdl_wait();  // the histogram is complete
+  cs_pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const int n = a.cand_count;
+  const int base_i = blockIdx.x * (CS_SORT_THREADS * CS_SORT_REG);
+  cs_sort_scan(s_hist, s_warp, __ldcg(&a.s2_ghist[2 * tid]), __ldcg(&a.s2_ghist[2 * tid + 1]));
+#pragma unroll
+  for (int k = 0; k < CS_SORT_REG; k++) {
+    const int i = base_i + tid + k * CS_SORT_THREADS;
+    if (i < n) {
+      const unsigned long long m = __ldcg(&a.s2_meta[i]);
+      a.s2_sorted[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = __ldcg(&a.s2_tmp[i]);
+    }
+  }
+  // the last block to get here re-arms the histogram for the next step (every block has read it by then)
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(&a.s2_ghist[CS_SORT_BINS], 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last)
+    for (int b = tid; b <= CS_SORT_BINS; b += CS_SORT_THREADS) a.s2_ghist[b] = 0u;
+}
+
+template <bool TILED>
+__global__ void __launch_bounds__(CS_S2_MAX_THREADS)
+cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
+  __shared__ float2 s_pts[CS_S2_MAX_POINTS];
+  CsSession& S = sessions[0];
+  const CsStepHeader& hdr = a.hdr[0];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int cluster = blockIdx.x, slab = blockIdx.y;
+  const unsigned n_clusters = gridDim.x;
+
+  // ---- before the dependency wait: this step's inputs and host-owned constants only
+  const int P = a.s2_host_points;  // = hdr.n_points
+  const int p0 = cluster * a.s2_points;
+  const int np = max(0, min(a.s2_points, P - p0));
+  const int np_pad = (np + CS_S2_BATCH - 1) / CS_S2_BATCH * CS_S2_BATCH;
+  // the last batch is padded with NaN points: they fail the bounds test like any NaN point does (:244)
+  if (tid < np_pad) s_pts[tid] = tid < np ? __ldg(a.points + p0 + tid) : make_float2(__int_as_float(0x7fc00000), 0.f);
+  const int size = a.s2_size, pitch_tiles = a.s2_pitch_tiles;
+  const uint16_t* __restrict__ map = a.s2_map;
+  const float scale = a.s2_scale;
+  int* const distances = S.distances;
+  const int pos = slab * a.s2_slab + tid;  // position in the sorted order
+  const bool valid = pos < a.cand_count;
+
+  cs_pdl_wait();  // the sort of this step — and through it the previous step — is complete
+  cs_pdl_launch_dependents();
+
+  float px = 0.f, py = 0.f, c = 0.f, s = 0.f;
+  int idx = 0;
+  if (valid) {
+    const float4 e = __ldcg(a.s2_sorted + pos);
+    idx = __float_as_int(e.w);
+    float sp[3], pose[3];
+    cs_search_pose(S, hdr, a, sp);
+    if (idx == 0) {
+      pose[0] = sp[0]; pose[1] = sp[1]; pose[2] = sp[2];
+    } else if (a.cand_mode == CS_CAND_ABSOLUTE) {
+      pose[0] = e.x; pose[1] = e.y; pose[2] = e.z;
+    } else {
+      pose[0] = __fadd_rn(sp[0], e.x);  // :635-637
+      pose[1] = __fadd_rn(sp[1], e.y);
+      pose[2] = __fadd_rn(sp[2], e.z);
+    }
+    float ct, st;
+    if (a.cand_cs) {
+      ct = a.cand_cs[2 * (size_t)idx];
+      st = a.cand_cs[2 * (size_t)idx + 1];
+    } else {
+      ct = cs_cosf(pose[2]);
+      st = cs_sinf(pose[2]);
+    }
+    px = __fadd_rn(__fmul_rn(pose[0], scale), 0.5f);  // :232
+    py = __fadd_rn(__fmul_rn(pose[1], scale), 0.5f);  // :233
+    c = __fmul_rn(ct, scale);                         // :234
+    s = __fmul_rn(st, scale);                         // :235
+  }
+  __syncthreads();  // s_pts
+  const unsigned act = __ballot_sync(0xffffffffu, valid);  // lanes of this warp that own a candidate
+  if (!valid) return;
+
+  unsigned sum = 0, nb = 0;  // sum <= 65535 * 128
+#pragma unroll 1
+  for (int i0 = 0; i0 < np_pad; i0 += CS_S2_BATCH) {
+    unsigned cell[CS_S2_BATCH];
+    unsigned v[CS_S2_BATCH];
+#pragma unroll
+    for (int j = 0; j < CS_S2_BATCH; j++) {
+      const float2 p = s_pts[i0 + j];  // broadcast
+      float fx = __fsub_rn(__fadd_rn(px, __fmul_rn(c, p.x)), __fmul_rn(s, p.y));  // :240
+      float fy = __fadd_rn(__fadd_rn(py, __fmul_rn(s, p.x)), __fmul_rn(c, p.y));  // :241
+      int x = __float2int_rz(fmaxf(fx, -2.0f));  // see cs_search_kernel
+      int y = __float2int_rz(fmaxf(fy, -2.0f));
+      const bool in = ((unsigned)x < (unsigned)size) && ((unsigned)y < (unsigned)size);  // :244
+      cell[j] = in ? cs_cell_offset<TILED>(x, y, size, pitch_tiles) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int j = 0; j < CS_S2_BATCH; j++) {
+      v[j] = 0u;
+      if (cell[j] != 0xffffffffu) v[j] = (unsigned)__ldg(map + cell[j]);  // :246
+    }
+#pragma unroll
+    for (int j = 0; j < CS_S2_BATCH; j++) {
+      sum += v[j];
+      nb += cell[j] != 0xffffffffu;
+    }
+  }
+
+  // ---- one atomic per (candidate, cluster): adds the partial sums and counts the arrival.  The cluster that arrives
+  // last at a candidate sees every other cluster's contribution in the returned word (single-address atomics are
+  // totally ordered), so it owns the candidate's complete sum: distance (:251-258), arg-min, and the word goes back to
+  // zero for the next step.  No fence, no block-wide wait.
+  const unsigned long long mine = (1ull << CS_S2_ARRIVAL_SHIFT) | ((unsigned long long)nb << 32) | (unsigned long long)sum;
+  const unsigned long long old = atomicAdd(&a.s2_acc[pos], mine);
+  const bool fin = (unsigned)(old >> CS_S2_ARRIVAL_SHIFT) == n_clusters - 1u;
+  unsigned long long key = ~0ull;
+  if (fin) {
+    const unsigned long long tot = old + mine;
+    const unsigned long long cells = tot & 0xffffffffull, cnt = (tot >> 32) & 0x1ffffull;
+    const int d = cnt > 0 ? (int)((cells * 1024ull) / (unsigned long long)P) : 2147483647;  // :251-258
+    key = ((unsigned long long)(unsigned)d << 32) | (unsigned)idx;
+    if (distances) distances[idx] = d;
+    a.s2_acc[pos] = 0ull;
+  }
+  const unsigned fin_mask = __ballot_sync(act, fin);
+  if (fin_mask == 0u) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(act, key, o);
+    if (act >> (lane ^ o) & 1u) key = min(key, other);
+  }
+  if (lane != (int)(__ffs(act) - 1)) return;
+  const unsigned long long seen = atomicMin(&S.key[a.parity], key);
+  if (!a.fuse_publish) return;
+  // ---- the warp that completes the last candidates owns the complete arg-min: Update glue, pose out (as the last block
+  // of cs_search_kernel does).  Its own atomicMin has returned, so it is performed; the fence orders it before the count.
+  const unsigned long long guess = min(seen, key);
+  __threadfence();
+  const unsigned nfin = (unsigned)__popc(fin_mask);
+  const bool last = atomicAdd(&S.search_done, nfin) + nfin == (unsigned)a.cand_count;
+  if (!last) return;
+  S.search_done = 0;
+  cs_publish(S, hdr, a, a.cand, a.result, true, guess);
 }
 
 // ---------------------------------------------------------------------------------------------------

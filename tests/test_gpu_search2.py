@@ -1,0 +1,221 @@
+"""The heading-sorted slab search (cs_sort_kernel + cs_search2_kernel) vs the CPU oracle and vs the warp-per-candidate
+kernel, through the C ABI.  CS_FLAG_SEARCH_SLAB forces the slab kernels for any candidate count, CS_FLAG_SEARCH_WARP
+forces the other one; without either flag the library picks by candidate count (>= 1024 candidates: slabs).
+
+Bit-exact: per-candidate distances, arg-min under the reference's tie-break order, poses, maps.
+"""
+import numpy as np
+import pytest
+
+import slam.net_b200 as sn
+from slam.net_b200 import _native as N
+from slam.net_b200 import parallel as par
+from slam.net_b200 import synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SLAB, WARP = N.FLAG_SEARCH_SLAB, N.FLAG_SEARCH_WARP
+
+
+def _oracle_map(size, phys, pixels):
+    m = orc.HoleMap(size, phys)
+    m.pixels[:] = pixels
+    return m
+
+
+@pytest.mark.parametrize("layout", [0, N.FLAG_ROW_MAJOR_MAP])
+@pytest.mark.parametrize("size,n_points,iters,threads", [(64, 1, 1, 1), (100, 37, 7, 3), (256, 360, 250, 4), (333, 2049, 33, 2),
+                                                         (512, 5000, 16, 4), (300, 129, 1500, 3), (300, 70, 3011, 3)])
+def test_slab_search_distances_bit_exact(layout, size, n_points, iters, threads):
+    rng = np.random.default_rng(size * 7 + n_points)
+    phys = 10.0
+    px = synth.random_map(size, seed=size)
+    p = sn.Processor(phys, size, (0, 0, 0), 0.1, 0.17, iters, threads, flags=layout | SLAB, max_points=max(n_points, 64), seed=1)
+    p.map_upload(px)
+    m = _oracle_map(size, phys, px)
+    pts = rng.normal(0, 3.0, (n_points, 2)).astype(np.float32)
+    for trial in range(3):
+        sp = np.array([rng.uniform(0, phys), rng.uniform(0, phys), rng.uniform(-7, 7)], dtype=np.float32)
+        if trial == 2:
+            sp[:2] = [-3.0, phys + 2.0]  # mostly out of bounds
+        off = rng.normal(0, [0.3, 0.3, 0.4], (iters * threads, 3)).astype(np.float32)
+        cand = (sp[None, :] + off).astype(np.float32)
+        best, bd, d, bi = orc.parallel_search(m, pts, sp, off, iters, threads)
+        res, dist = p.search(pts, sp, cand)
+        assert np.array_equal(dist, d)
+        assert (res.distance, res.index) == (bd, bi)
+        assert np.array_equal(res.pose, best)
+    # fewer candidates than the handle's T*I in one call (the scratch is reused, sums must be back at zero)
+    n_few = max(1, (iters * threads) // 3)
+    best, bd, d, bi = orc.parallel_search(m, pts, sp, off[:n_few], n_few, 1)
+    res, dist = p.search(pts, sp, cand[:n_few])
+    assert np.array_equal(dist, d) and (res.distance, res.index) == (bd, bi)
+    p.close()
+
+
+def test_slab_search_edge_cases():
+    size, phys = 128, 8.0
+    p = sn.Processor(phys, size, (0, 0, 0), 0.1, 0.17, 8, 2, flags=SLAB, seed=1)
+    px = synth.random_map(size, 3)
+    p.map_upload(px)
+    m = _oracle_map(size, phys, px)
+    sp = np.array([4.0, 4.0, 0.5], dtype=np.float32)
+    off = np.random.default_rng(0).normal(0, 0.2, (16, 3)).astype(np.float32)
+    off[3, 2] = np.nan   # a NaN heading sorts into bin 0 and evaluates to int.MaxValue like in the reference
+    off[5, 2] = 1e9      # far outside the binned range
+    off[6, 2] = -1e9
+    pts = np.array([[np.nan, 0.0], [np.inf, 1.0], [-np.inf, -1.0], [1e30, 1e30], [-1e30, 2.0], [0.3, -0.2],
+                    [-4.0 - 0.5 / 16, -4.0 - 0.5 / 16], [3.99, 3.99], [1e-40, -1e-40]], dtype=np.float32)
+    best, bd, d, bi = orc.parallel_search(m, pts, sp, off, 8, 2)
+    res, dist = p.search(pts, sp, sp[None, :] + off)
+    assert np.array_equal(dist, d) and (res.distance, res.index) == (bd, bi)
+    far = np.array([1e6, -1e6, 0.0], dtype=np.float32)
+    off[3, 2] = 0.1
+    res, dist = p.search(pts[5:8], far, far[None, :] + off)
+    assert (dist == 2147483647).all() and res.index == 0 and res.distance == 2147483647
+    assert np.array_equal(res.pose, far)
+    p.map_fill(1234)  # ties: every candidate in bounds -> flat index 0 wins
+    small = np.array([[0.1, 0.1], [-0.1, 0.2]], dtype=np.float32)
+    res, dist = p.search(small, sp, sp[None, :] + off * 0.01)
+    assert res.index == 0 and (dist == 1234 * 1024).all()
+    cand = (sp[None, :] + off).astype(np.float32)  # host-supplied cos/sin table is honoured
+    ang = np.concatenate([[sp[2]], cand[:, 2]]).astype(np.float32)
+    c, s = orc.libm_sincos(ang)
+    p.map_upload(px)
+    r1, d1 = p.search(pts, sp, cand)
+    r2, d2 = p.search(pts, sp, cand, cand_cs=np.stack([c, s], axis=1))
+    assert np.array_equal(d1, d2) and r1.index == r2.index
+    p.close()
+
+
+@pytest.mark.parametrize("iters", [300, 2500])  # 2500 x 4 + 1 candidates: the two-kernel sort
+def test_slab_search_philox_mode_matches_host_twin(iters):
+    size, phys, threads = 256, 10.0, 4
+    p = sn.Processor(phys, size, (0, 0, 0), 0.1, 0.17, iters, threads, flags=SLAB, seed=0xC0FFEE)
+    px = synth.random_map(size, 9)
+    p.map_upload(px)
+    m = _oracle_map(size, phys, px)
+    pts = np.random.default_rng(4).normal(0, 2.0, (200, 2)).astype(np.float32)
+    sp = np.array([5.0, 5.0, -1.0], dtype=np.float32)
+    for scan in (0, 1, 77):
+        off = sn.philox_offsets(0xC0FFEE, scan, iters * threads, 0.1, 0.17)
+        best, bd, d, bi = orc.parallel_search(m, pts, sp, off, iters, threads)
+        res, dist = p.search(pts, sp, None, scan_index=scan)
+        assert np.array_equal(dist, d)
+        assert (res.distance, res.index) == (bd, bi) and np.array_equal(res.pose, best)
+    p.close()
+
+
+@pytest.mark.parametrize("philox", [False, True])
+@pytest.mark.parametrize("layout", [0, N.FLAG_ROW_MAJOR_MAP])
+def test_slab_update_replay_bit_exact(philox, layout):
+    n_scans, n_points, size, phys, iters, threads = 40, 360, 400, 40.0, 100, 4
+    rp = synth.make_replay(n_scans, n_points, phys, seed=0x5EED0000)
+    p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, flags=layout | SLAB, max_points=n_points, seed=0x5EED0000)
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    for k in range(n_scans):
+        if philox:
+            off = sn.philox_offsets(0x5EED0000, k, iters * threads, 0.1, 0.17)
+            res = p.update(rp.points[k], rp.odometry[k], None)
+        else:
+            off = synth.candidate_offsets(0x5EED0000, k, iters * threads, 0.1, 0.17)
+            res = p.update(rp.points[k], rp.odometry[k], off)
+        o.update(rp.points[k], rp.odometry[k], off)
+        assert np.array_equal(res.pose, o.pose), "scan %d" % k
+        if res.searched:
+            assert res.distance == o.last_distance and res.index == o.last_index
+    assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+    p.close()
+
+
+@pytest.mark.parametrize("philox", [False, True])
+def test_slab_scanlog_replay_back_to_back(philox):
+    """cs_replay queues every scan's sort / search / rings kernels back to back (programmatic dependent launches, no host
+    round trip): the chain must give the oracle's poses and map, and the same as the warp-per-candidate kernel."""
+    n_scans, n_points, size, phys, iters, threads = 60, 512, 640, 40.0, 320, 4
+    rp = synth.make_replay(n_scans, n_points, phys, seed=77)
+    log = sn.ScanLog(n_scans, n_points, n_offsets=0 if philox else iters * threads)
+    offs = []
+    for k in range(n_scans):
+        off = (sn.philox_offsets(99, k, iters * threads, 0.1, 0.17) if philox else synth.candidate_offsets(5, k, iters * threads, 0.1, 0.17))
+        offs.append(off)
+        log.set(k, rp.points[k], rp.odometry[k], None if philox else off)
+    log.upload()
+    out = {}
+    for name, flag in (("slab", SLAB), ("warp", WARP), ("auto", 0)):
+        q = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, flags=flag, max_points=n_points, seed=99)
+        res = q.replay(log, 0, 25)
+        res += q.replay(log, 25, n_scans - 25)
+        out[name] = (res, q.map_download(), q.get_pose())
+        q.close()
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    for k in range(n_scans):
+        o.update(rp.points[k], rp.odometry[k], offs[k])
+        for name in out:
+            r = out[name][0][k]
+            assert np.array_equal(r.pose, o.pose), (name, k)
+            if k >= 5:
+                assert (r.distance, r.index) == (o.last_distance, o.last_index), (name, k)
+    for name in out:
+        assert np.array_equal(out[name][1], np.array(o.map.pixels)), name
+        assert np.array_equal(out[name][2], o.pose)
+    log.close()
+
+
+def test_slab_cfg2_slice_distances_equal_warp_kernel_and_oracle():
+    """configs[1] at full size: 4096 candidates x 1024 points, 2048x2048 — the default choice here is the slab search."""
+    n = 10
+    rp = synth.make_replay(n, 1024, 40.0)
+    ps = [sn.Processor(40.0, 2048, rp.odometry[0], 0.1, 0.17, 1024, 4, max_points=1024, flags=N.FLAG_KEEP_DISTANCES | f)
+          for f in (0, WARP)]
+    o = orc.Processor(40.0, 2048, rp.odometry[0], 0.1, 0.17, 1024, 4)
+    for k in range(n):
+        off = synth.candidate_offsets(12, k, 4096, 0.1, 0.17)
+        rs = [p.update(rp.points[k], rp.odometry[k], off) for p in ps]
+        sp = o.pose + (rp.odometry[k] - np.array(list(o._p.contents.last_odometry_pose), dtype=np.float32))
+        if k >= 5:
+            _, _, d, _ = orc.parallel_search(o.map, rp.points[k], sp.astype(np.float32), off, 1024, 4)
+            for p in ps:
+                assert np.array_equal(p.distances(), d)
+        o.update(rp.points[k], rp.odometry[k], off)
+        for r in rs:
+            assert np.array_equal(r.pose, o.pose)
+    launches = [p.launch_count() for p in ps]
+    assert launches[0] > launches[1]  # the slab path really ran: one more kernel (the sort) per searched scan
+    for p in ps:
+        assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+        p.close()
+
+
+def test_slab_candidate_split_two_handles_one_device():
+    """The multi-GPU candidate split with the slab kernels: each 'rank' sorts and evaluates its own slice of the flat indices."""
+    import torch
+    n_scans, P, size, phys, iters, threads = 14, 300, 320, 40.0, 61, 4
+    rp = synth.make_replay(n_scans, P, phys, seed=21)
+    ranks = [sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=3, flags=SLAB) for _ in range(2)]
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    n_flat = iters * threads + 1
+    for k in range(n_scans):
+        off = synth.candidate_offsets(4, k, iters * threads, 0.1, 0.17)
+        ptrs = []
+        for g, p in enumerate(ranks):
+            lo, cnt = par.candidate_slice(n_flat, 2, g)
+            ptrs.append(p.update_begin(rp.points[k], rp.odometry[k], off, lo, cnt))
+        if k >= 5:
+            for p in ranks:
+                p.sync()
+            keys = [par.device_key_tensor(x, 0) for x in ptrs]
+            m = torch.minimum(keys[0], keys[1])
+            keys[0].copy_(m)
+            keys[1].copy_(m)
+            torch.cuda.synchronize()
+        res = [p.update_finish() for p in ranks]
+        o.update(rp.points[k], rp.odometry[k], off)
+        for r in res:
+            assert np.array_equal(r.pose, o.pose), k
+            if k >= 5:
+                assert (r.distance, r.index) == (o.last_distance, o.last_index)
+    for p in ranks:
+        assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+        p.close()
