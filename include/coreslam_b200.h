@@ -148,6 +148,19 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
 cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
                     const float* cand_offsets, cs_result* out);
 
+/* CoreSLAMProcessor.Update(List<ScanSegment>) exactly as the reference declares it (:717-752), ScanSegmentsToCloud
+ * (:187-207) included: the host uploads the raw rays and segment poses, the cloud is computed on the device (same f32
+ * operations in the same order, libm-identical cosf/sinf) and feeds the search and both map integrations directly.
+ *   rays        n_rays * (angle [rad], radius [m]) of all segments back to back (BaseSLAM/Ray.cs, ScanSegment.Rays)
+ *   seg_first   n_segments + 1 indices: segment s owns rays [seg_first[s], seg_first[s+1]); seg_first[n_segments] = n_rays
+ *   seg_poses   n_segments * (x, y, theta): ScanSegment.Pose; the odometry pose of the Update is the LAST segment's (:719)
+ * n_segments = 0 fails like segments.Last() on an empty list does (InvalidOperationException -> CS_ERR_INVALID_ARGUMENT). */
+cs_status cs_update_segments(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
+                             int32_t n_segments, const float* cand_offsets, cs_result* out);
+/* ScanSegmentsToCloud alone (:187-207) for an explicit odometry pose: points_out receives n_rays * (x, y). */
+cs_status cs_segments_to_cloud(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
+                               int32_t n_segments, const float odometry_pose[3], float* points_out);
+
 /* Multi-GPU candidate split (very large candidate sets, BASELINE cfg4): the map is replicated, GPU g
  * evaluates the flat candidate indices [cand_first, cand_first + cand_count) of the same scan, and ONE
  * 8-byte exchange picks the winner: the packed key (uint32 distance << 32 | uint32 flat index) is

@@ -134,6 +134,8 @@ SIGNATURES = {
     "cs_search": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, _fp, C.c_int32, C.c_uint32, C.POINTER(Result), _ip]),
     "cs_integrate": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(C.c_int64)]),
     "cs_update": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(Result)]),
+    "cs_update_segments": (C.c_int, [_vp, _fp, _ip, _fp, C.c_int32, C.c_int32, _fp, C.POINTER(Result)]),
+    "cs_segments_to_cloud": (C.c_int, [_vp, _fp, _ip, _fp, C.c_int32, C.c_int32, _fp, _fp]),
     "cs_update_begin": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "cs_update_finish": (C.c_int, [_vp, C.POINTER(Result)]),
     "cs_sync": (C.c_int, [_vp]),

@@ -65,8 +65,21 @@ class ScanCloud:
     Points: np.ndarray = field(default_factory=lambda: np.zeros((0, 2), dtype=np.float32))
 
 
+def pack_segments(segments: Sequence[ScanSegment]):
+    """List<ScanSegment> -> the flat arrays cs_update_segments takes: rays (n,2) = (angle, radius) of all segments back
+    to back, seg_first (n_segments+1) int32, seg_poses (n_segments,3)."""
+    arrays = [seg.rays_array() for seg in segments]
+    rays = np.concatenate(arrays, axis=0) if arrays else np.zeros((0, 2), dtype=np.float32)
+    first = np.zeros(len(arrays) + 1, dtype=np.int32)
+    if arrays:
+        first[1:] = np.cumsum([a.shape[0] for a in arrays])
+    poses = _f32([tuple(seg.Pose) for seg in segments]).reshape(-1, 3)
+    return _f32(rays), first, poses
+
+
 def scan_segments_to_cloud(segments: Sequence[ScanSegment], odometry_pose) -> ScanCloud:
-    """ScanSegmentsToCloud, CoreSLAM/CoreSLAMProcessor.cs:187-207 (stays on the host, O(P)).
+    """ScanSegmentsToCloud, CoreSLAM/CoreSLAMProcessor.cs:187-207, on the host (the product path runs it on the
+    device: Processor.update_segments / Processor.segments_to_cloud; this twin exists for comparisons).
     cosf/sinf come from the library's host build of its glibc-identical routine."""
     odo = _f32(odometry_pose)
     out = []
@@ -240,6 +253,25 @@ class Processor:
         r = N.Result()
         self._ck(N.lib().cs_update(self._h, _ptr(pts), pts.shape[0], _ptr(_f32(odometry_pose)), _ptr(off), C.byref(r)))
         return _result(r)
+
+    def update_segments(self, segments: Sequence[ScanSegment], cand_offsets=None) -> SearchResult:
+        """CoreSLAMProcessor.Update(List<ScanSegment>) whole, ScanSegmentsToCloud on the device (cs_update_segments)."""
+        rays, first, poses = pack_segments(segments)
+        off = None if cand_offsets is None else _f32(cand_offsets).reshape(-1, 3)
+        if off is not None and off.shape[0] != self.n_cand:
+            raise ValueError("cand_offsets needs T*I = %d rows" % self.n_cand)
+        r = N.Result()
+        self._ck(N.lib().cs_update_segments(self._h, _ptr(rays), first.ctypes.data_as(N._ip), _ptr(poses), rays.shape[0],
+                                            poses.shape[0], _ptr(off), C.byref(r)))
+        return _result(r)
+
+    def segments_to_cloud(self, segments: Sequence[ScanSegment], odometry_pose) -> np.ndarray:
+        """ScanSegmentsToCloud (:187-207) on the device for an explicit odometry pose; returns the (n,2) points."""
+        rays, first, poses = pack_segments(segments)
+        out = np.empty((rays.shape[0], 2), dtype=np.float32)
+        self._ck(N.lib().cs_segments_to_cloud(self._h, _ptr(rays), first.ctypes.data_as(N._ip), _ptr(poses), rays.shape[0],
+                                              poses.shape[0], _ptr(_f32(odometry_pose)), _ptr(out)))
+        return out
 
     # -- multi-GPU candidate split (cs_update_begin / cs_update_finish) -----------------------------
     def update_begin(self, points, odometry_pose, cand_offsets, cand_first: int, cand_count: int) -> int:
@@ -570,9 +602,7 @@ class CoreSLAMProcessor:
         """:717-752.  candidateOffsets (T*I x 3) switches on verification mode for this scan."""
         if not segments:
             raise ValueError("Sequence contains no elements")  # segments.Last() on an empty list (:719)
-        odo = _f32(segments[-1].Pose)
-        cloud = scan_segments_to_cloud(segments, odo)  # :723
-        self.LastResult = self._proc.update(cloud.Points, odo, candidateOffsets)
+        self.LastResult = self._proc.update_segments(segments, candidateOffsets)  # :719-752, cloud (:723) included
         self._pose = self.LastResult.pose
 
     def Dispose(self):

@@ -78,7 +78,9 @@ struct cs_processor {
   CsObstacle* d_obst = nullptr;
   int unmapped_obstacle_hits = -5;  // :98
 
-  // staging: [hdr 64][points][cand][cand_cs]
+  float2* d_cloud = nullptr;  // scan points computed on the device from raw segments (cs_update_segments)
+
+  // staging: [hdr 64][points][cand][cand_cs]; segments path: [hdr 64][rays][seg_first][seg_poses][cand]
   size_t stage_bytes = 0;
   uint8_t* h_stage = nullptr;  // pinned
   uint8_t* d_stage = nullptr;
@@ -353,8 +355,18 @@ enum { CS_PHASE_SEARCH = 1, CS_PHASE_FINISH = 2, CS_PHASE_ALL = 3 };
 // Launch with the programmatic-stream-serialization attribute: the kernel may become resident while its
 // predecessor in the stream drains; every kernel here calls cs_pdl_wait() before it reads anything the
 // predecessor wrote.
+// One-shot: the next launch_pdl on this thread is a plain (fully serialised) launch.  Set after a kernel that PRODUCES
+// inputs of the step (cs_cloud_kernel writes the scan points): the step's first kernel reads its inputs before its
+// dependency wait, which is only sound when they were complete before it could start.
+thread_local bool g_next_launch_plain = false;
+
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  if (g_next_launch_plain) {
+    g_next_launch_plain = false;
+    kernel<<<grid, block, smem, stream>>>(args...);
+    return cudaGetLastError();
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -672,7 +684,8 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
     CS_CREATE_CUDA(cudaMalloc(&h->d_s2_ghist, (size_t)(CS_SORT_BINS + 1) * sizeof(unsigned)));
     CS_CREATE_CUDA(cudaMemsetAsync(h->d_s2_ghist, 0, (size_t)(CS_SORT_BINS + 1) * sizeof(unsigned), h->stream));
   }
-  h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total;
+  h->stage_bytes = plan_stage(max_points, (int)n_cand, true).total + 16 * ((size_t)max_points + 1) + 64;  // + segment tables
+  CS_CREATE_CUDA(cudaMalloc(&h->d_cloud, (size_t)max_points * sizeof(float2)));
   CS_CREATE_CUDA(cudaHostAlloc(&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
   CS_CREATE_CUDA(cudaMalloc(&h->d_stage, h->stage_bytes));
   CS_CREATE_CUDA(cudaHostAlloc(&h->h_slot, 128, cudaHostAllocMapped));
@@ -769,6 +782,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
+  cudaFree(h->d_cloud);
   cudaFree(h->d_s2_sorted);
   cudaFree(h->d_s2_tmp);
   cudaFree(h->d_s2_meta);
@@ -1033,9 +1047,53 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
 }
 
 // Stages one scan and fills the step arguments of an Update; shared by cs_update and cs_update_begin.
+// Raw scan segments of one Update (cs_update_segments): the cloud is computed on the device.
+struct SegInput {
+  const float* rays;        // n_points * (angle, radius)
+  const int32_t* seg_first; // n_segments + 1
+  const float* seg_poses;   // n_segments * 3
+  int n_segments;
+};
+
+static cs_status launch_cloud(cs_processor* h, const uint8_t* d_rays, const uint8_t* d_first, const uint8_t* d_poses, int n_rays,
+                              int n_segments, const float odo[3]) {
+  cs_cloud_kernel<<<(n_rays + CS_CLOUD_THREADS - 1) / CS_CLOUD_THREADS, CS_CLOUD_THREADS, 0, h->stream>>>(
+      reinterpret_cast<const float2*>(d_rays), reinterpret_cast<const int*>(d_first), reinterpret_cast<const float*>(d_poses),
+      n_segments, n_rays, odo[0], odo[1], odo[2], h->d_cloud);
+  h->launches++;
+  CS_CUDA(h, cudaGetLastError());
+  return CS_OK;
+}
+
+static cs_status check_segments(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
+                                int32_t n_segments) {
+  if (!rays || !seg_first || !seg_poses || n_rays <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "segments: bad argument");
+  if (n_segments <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "Sequence contains no elements (segments.Last(), CoreSLAMProcessor.cs:719)");
+  if (n_rays > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_rays %d > max_points %d", n_rays, h->max_points);
+  if (n_segments > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_segments %d > max_points %d", n_segments, h->max_points);
+  if (seg_first[0] != 0 || seg_first[n_segments] != n_rays) return fail(h, CS_ERR_INVALID_ARGUMENT, "seg_first must run from 0 to n_rays");
+  for (int s = 0; s < n_segments; s++)
+    if (seg_first[s + 1] < seg_first[s]) return fail(h, CS_ERR_INVALID_ARGUMENT, "seg_first must be non-decreasing");
+  return CS_OK;
+}
+
+// upper bound of |point| over the cloud of the segments: |segment.Pose - odometry| + |radius|
+static double max_range_of_segments(const float* rays, const int32_t* seg_first, const float* seg_poses, int n_segments, const float odo[3]) {
+  double m = 0.0;
+  for (int s = 0; s < n_segments; s++) {
+    const double dx = (double)seg_poses[3 * s] - odo[0], dy = (double)seg_poses[3 * s + 1] - odo[1];
+    const double d0 = std::sqrt(dx * dx + dy * dy);
+    for (int i = seg_first[s]; i < seg_first[s + 1]; i++) {
+      const double r = d0 + std::fabs((double)rays[2 * i + 1]);
+      if (!(r <= m)) m = r;  // NaN sticks
+    }
+  }
+  return m;
+}
+
 static cs_status stage_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
-                              const float* cand_offsets, bool timing, CsStepArgs* out_args) {
-  if (!points || !odometry_pose || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
+                              const float* cand_offsets, bool timing, CsStepArgs* out_args, const SegInput* seg = nullptr) {
+  if ((!points && !seg) || !odometry_pose || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
   if (!finite3(odometry_pose)) return fail(h, CS_ERR_INVALID_ARGUMENT, "odometry pose is NaN");
   if (h->pending) return fail(h, CS_ERR_STATE, "a split-phase update is in flight: call cs_update_finish first");
@@ -1049,16 +1107,32 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   memset(hdr, 0, kHdrBytes);
   hdr->odo[0] = odometry_pose[0]; hdr->odo[1] = odometry_pose[1]; hdr->odo[2] = odometry_pose[2];
   hdr->n_points = n_points;
-  memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
+  size_t off_first = 0, off_poses = 0;
+  if (seg) {  // the points slot carries the raw rays; the segment tables go behind the candidate table
+    memcpy(h->h_stage + sp.off_points, seg->rays, (size_t)n_points * 8);
+    off_first = sp.total;
+    off_poses = align_up(off_first + (size_t)(seg->n_segments + 1) * 4, 16);
+    sp.total = align_up(off_poses + (size_t)seg->n_segments * 12, 16);
+    memcpy(h->h_stage + off_first, seg->seg_first, (size_t)(seg->n_segments + 1) * 4);
+    memcpy(h->h_stage + off_poses, seg->seg_poses, (size_t)seg->n_segments * 12);
+  } else {
+    memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
+  }
   if (with_offsets) memcpy(h->h_stage + sp.off_cand, cand_offsets, (size_t)h->n_cand * 12);
 
   if (timing) cudaEventRecord(h->tm.ev[0], h->stream);
   CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+  if (seg) {  // ScanSegmentsToCloud (:723) on the device; the step's first kernel must not start before it is complete
+    cs_status cst = launch_cloud(h, h->d_stage + sp.off_points, h->d_stage + off_first, h->d_stage + off_poses, n_points,
+                                 seg->n_segments, odometry_pose);
+    if (cst != CS_OK) return cst;
+    g_next_launch_plain = true;
+  }
   if (timing) cudaEventRecord(h->tm.ev[1], h->stream);
 
   CsStepArgs a{};
   a.hdr = reinterpret_cast<const CsStepHeader*>(h->d_stage);
-  a.points = reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
+  a.points = seg ? h->d_cloud : reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
   a.cand = with_offsets ? reinterpret_cast<const float*>(h->d_stage + sp.off_cand) : nullptr;
   a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
   a.seq_flag = reinterpret_cast<volatile unsigned*>(h->d_slot + 64);
@@ -1111,6 +1185,46 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
   st = launch_step(h, a, n_points, rings_hint(h, max_range_of(points, n_points)), timing, 2);
   if (st != CS_OK) return st;
   return complete_update(h, a, timing, out);
+}
+
+// CoreSLAMProcessor.Update(List<ScanSegment>) whole (:717-752): ScanSegmentsToCloud included.
+cs_status cs_update_segments(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
+                             int32_t n_segments, const float* cand_offsets, cs_result* out) {
+  CS_CHECK_HANDLE(h);
+  cs_status st = check_segments(h, rays, seg_first, seg_poses, n_rays, n_segments);
+  if (st != CS_OK) return st;
+  const float* odo = seg_poses + 3 * (size_t)(n_segments - 1);  // :719 odoPose = segments.Last().Pose
+  const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
+  SegInput seg{rays, seg_first, seg_poses, n_segments};
+  CsStepArgs a{};
+  st = stage_update(h, nullptr, n_rays, odo, cand_offsets, timing, &a, &seg);
+  if (st != CS_OK) { g_next_launch_plain = false; return st; }
+  st = launch_step(h, a, n_rays, rings_hint(h, max_range_of_segments(rays, seg_first, seg_poses, n_segments, odo)), timing, 2);
+  g_next_launch_plain = false;
+  if (st != CS_OK) return st;
+  return complete_update(h, a, timing, out);
+}
+
+cs_status cs_segments_to_cloud(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
+                               int32_t n_segments, const float odometry_pose[3], float* points_out) {
+  CS_CHECK_HANDLE(h);
+  cs_status st = check_segments(h, rays, seg_first, seg_poses, n_rays, n_segments);
+  if (st != CS_OK) return st;
+  if (!odometry_pose || !points_out) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_segments_to_cloud: null argument");
+  if (h->pending) return fail(h, CS_ERR_STATE, "a split-phase update is in flight: call cs_update_finish first");
+  const size_t off_rays = kHdrBytes;
+  const size_t off_first = align_up(off_rays + (size_t)n_rays * 8, 16);
+  const size_t off_poses = align_up(off_first + (size_t)(n_segments + 1) * 4, 16);
+  const size_t total = align_up(off_poses + (size_t)n_segments * 12, 16);
+  memcpy(h->h_stage + off_rays, rays, (size_t)n_rays * 8);
+  memcpy(h->h_stage + off_first, seg_first, (size_t)(n_segments + 1) * 4);
+  memcpy(h->h_stage + off_poses, seg_poses, (size_t)n_segments * 12);
+  CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, total, cudaMemcpyHostToDevice, h->stream));
+  st = launch_cloud(h, h->d_stage + off_rays, h->d_stage + off_first, h->d_stage + off_poses, n_rays, n_segments, odometry_pose);
+  if (st != CS_OK) return st;
+  CS_CUDA(h, cudaMemcpyAsync(points_out, h->d_cloud, (size_t)n_rays * 8, cudaMemcpyDeviceToHost, h->stream));
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CS_OK;
 }
 
 // ---- multi-GPU candidate split (BASELINE cfg4) ---------------------------------------------

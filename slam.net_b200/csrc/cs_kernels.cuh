@@ -1443,6 +1443,33 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ScanSegmentsToCloud (CoreSLAMProcessor.cs:187-207) on the device: one thread per ray.  rays = (angle, radius) of all
+// segments back to back; seg_first[s] = index of segment s's first ray (n_seg + 1 entries); seg_poses = (x, y, theta)
+// per segment; (ox, oy, oz) = the odometry pose the cloud is relative to (the last segment's pose, :719).
+// Same operations in the same order as the C#: pose = segment.Pose - odometryPose (:194), then
+// pose.X + r.Radius * MathF.Cos(r.Angle + pose.Z) (:200-201), one rounding each, libm-identical cosf/sinf.
+// ---------------------------------------------------------------------------------------------------
+#define CS_CLOUD_THREADS 128
+__global__ void __launch_bounds__(CS_CLOUD_THREADS)
+cs_cloud_kernel(const float2* __restrict__ rays, const int* __restrict__ seg_first, const float* __restrict__ seg_poses, int n_seg,
+                int n_rays, float ox, float oy, float oz, float2* __restrict__ points) {
+  const int i = blockIdx.x * CS_CLOUD_THREADS + threadIdx.x;
+  if (i >= n_rays) return;
+  int lo = 0, hi = n_seg - 1;  // last segment whose first ray is <= i (empty segments are skipped by the search)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(seg_first + mid) <= i) lo = mid; else hi = mid - 1;
+  }
+  const float px = __fsub_rn(__ldg(seg_poses + 3 * lo), ox);      // :194
+  const float py = __fsub_rn(__ldg(seg_poses + 3 * lo + 1), oy);
+  const float pz = __fsub_rn(__ldg(seg_poses + 3 * lo + 2), oz);
+  const float2 r = __ldg(rays + i);
+  const float ang = __fadd_rn(r.x, pz);
+  points[i] = make_float2(__fadd_rn(px, __fmul_rn(r.y, cs_cosf(ang))),   // :200
+                          __fadd_rn(py, __fmul_rn(r.y, cs_sinf(ang))));  // :201
+}
+
+// ---------------------------------------------------------------------------------------------------
 // map helpers
 // ---------------------------------------------------------------------------------------------------
 __global__ void cs_fill_kernel(uint16_t* __restrict__ map, size_t n_cells, uint16_t value) {
