@@ -1,7 +1,7 @@
-// CoreSLAMProcessor.B200.cs — drop-in for CoreSLAM/CoreSLAMProcessor.cs with the search and the HoleMap
-// integration running on a B200 through libcoreslam_b200.  Public surface identical to the reference
-// (ctor :119-120, Reset :167, Update :717, Dispose :757, properties :40-106); ObstacleMap handling is
-// unchanged C# and omitted here for brevity.  NOT COMPILED IN THIS REPOSITORY (no .NET SDK in the image).
+// CoreSLAMProcessor.B200.cs — drop-in for CoreSLAM/CoreSLAMProcessor.cs with the whole of Update (ScanSegmentsToCloud,
+// search, HoleMap and ObstacleMap integration) running on a B200 through libcoreslam_b200.  Public surface identical
+// to the reference (ctor :119-120, Reset :167, Update :717, Dispose :757, properties :40-106).
+// NOT COMPILED IN THIS REPOSITORY (no .NET SDK in the image).
 using System;
 using System.Collections.Generic;
 using System.Linq;
@@ -38,10 +38,29 @@ namespace CoreSLAM.B200
         }
     }
 
+    public sealed unsafe class ObstacleMap                     // CoreSLAM/ObstacleMap.cs:11-44
+    {
+        private readonly IntPtr handle;
+        internal ObstacleMap(IntPtr handle, int sizePixels, float sizeMeters)
+        {
+            this.handle = handle;
+            Size = sizePixels;
+            Scale = sizePixels / sizeMeters;                  // ObstacleMap.cs:20
+            Pixels = new sbyte[sizePixels, sizePixels];       // [y, x], host copy refreshed by SyncToHost()
+        }
+        public readonly sbyte[,] Pixels;                      // ObstacleMap.cs:27 (public field, kept)
+        public int Size { get; }
+        public float Scale { get; }
+        public void SyncToHost()
+        {
+            fixed (sbyte* p = Pixels) Native.Check(Native.cs_obstacle_map_download(handle, p), handle);
+        }
+    }
+
     public sealed unsafe class CoreSLAMProcessor : IDisposable
     {
         private IntPtr handle;
-        private readonly IntPtr staging;      // pinned float2[maxPoints]: ScanSegmentsToCloud writes here in place
+        private readonly IntPtr staging;      // pinned: raw rays, segment poses and first-ray indices of the current Update
         private readonly int maxPoints;
         private byte quality = 50;
         private float holeWidth = 0.6f;
@@ -49,6 +68,7 @@ namespace CoreSLAM.B200
 
         public float PhysicalMapSize { get; }
         public HoleMap HoleMap { get; }
+        public ObstacleMap ObstacleMap { get; }
         public float SigmaXY { get; }
         public float SigmaTheta { get; }
         public int SearchIterationsPerThread { get; }
@@ -65,6 +85,18 @@ namespace CoreSLAM.B200
             set { Native.Check(Native.cs_set_position_search_beginning(handle, value), handle); positionSearchBeginning = value; }
         }
 
+        private sbyte unmappedObstacleHits = -5, maxObstacleHits = 10;
+        public sbyte UnmappedObstacleHits   // :98 — takes effect at the next Reset(), as in the reference
+        {
+            get => unmappedObstacleHits;
+            set { Native.Check(Native.cs_set_unmapped_obstacle_hits(handle, value), handle); unmappedObstacleHits = value; }
+        }
+        public sbyte MaxObstacleHits        // :103
+        {
+            get => maxObstacleHits;
+            set { Native.Check(Native.cs_set_max_obstacle_hits(handle, value), handle); maxObstacleHits = value; }
+        }
+
         public CoreSLAMProcessor(float physicalMapSize, int holeMapSize, int obstacleMapSize, Vector3 startPose,
             float sigmaXY, float sigmaTheta, int iterationsPerThread, int numSearchThreads,
             int device = 0, ulong seed = 0x5EED, int maxPoints = 16384)
@@ -76,12 +108,13 @@ namespace CoreSLAM.B200
             {
                 PhysicalMapSize = physicalMapSize, HoleMapSize = holeMapSize, SigmaXY = sigmaXY, SigmaTheta = sigmaTheta,
                 IterationsPerThread = iterationsPerThread, NumSearchThreads = numSearchThreads,
-                Device = device, MaxPoints = maxPoints, Seed = seed
+                Device = device, MaxPoints = maxPoints, Seed = seed, ObstacleMapSize = obstacleMapSize
             };
             cfg.StartPose[0] = startPose.X; cfg.StartPose[1] = startPose.Y; cfg.StartPose[2] = startPose.Z;
             Native.Check(Native.cs_create(ref cfg, out handle), IntPtr.Zero);
-            Native.Check(Native.cs_pinned_alloc(out staging, (ulong)maxPoints * 8), handle);
+            Native.Check(Native.cs_pinned_alloc(out staging, (ulong)maxPoints * (8 + 12 + 4) + 4), handle);  // rays, segment poses, first-ray indices
             HoleMap = new HoleMap(handle, holeMapSize, physicalMapSize);
+            ObstacleMap = new ObstacleMap(handle, obstacleMapSize, physicalMapSize);
             Pose = startPose;
         }
 
@@ -93,30 +126,35 @@ namespace CoreSLAM.B200
             Pose = new Vector3(p[0], p[1], p[2]);
         }
 
-        /// CoreSLAMProcessor.Update (:717-752).  ScanSegmentsToCloud (:187-207) stays here on the host and
-        /// writes straight into the pinned staging block; search + NormalizeAngle + HoleMap integration
-        /// run on the device.  Returns when the pose is known; the integration overlaps the caller.
+        /// CoreSLAMProcessor.Update (:717-752), whole: the raw rays and segment poses are written straight into the
+        /// pinned staging block and uploaded; ScanSegmentsToCloud (:187-207), search, NormalizeAngle and both map
+        /// integrations run on the device.  Returns when the pose is known; the integration overlaps the caller.
         public void Update(List<ScanSegment> segments)
         {
-            Vector3 odoPose = segments.Last().Pose;
-            float* pts = (float*)staging;
-            int n = 0;
+            if (segments.Count == 0) throw new InvalidOperationException("Sequence contains no elements");  // segments.Last(), :719
+            float* rays = (float*)staging;                       // maxPoints * (angle, radius)
+            float* poses = rays + 2 * maxPoints;                 // maxPoints * (x, y, theta)   (at most one segment per ray)
+            int* first = (int*)(poses + 3 * maxPoints);          // maxPoints + 1
+            int n = 0, s = 0;
             foreach (ScanSegment segment in segments)
             {
-                Vector3 pose = segment.Pose - odoPose;
+                if (s >= maxPoints) throw new InvalidOperationException("more segments than maxPoints");
+                first[s] = n;
+                poses[3 * s] = segment.Pose.X; poses[3 * s + 1] = segment.Pose.Y; poses[3 * s + 2] = segment.Pose.Z;
+                s++;
                 foreach (Ray r in segment.Rays)
                 {
                     if (n >= maxPoints) throw new InvalidOperationException("scan larger than maxPoints");
-                    pts[2 * n] = pose.X + r.Radius * MathF.Cos(r.Angle + pose.Z);
-                    pts[2 * n + 1] = pose.Y + r.Radius * MathF.Sin(r.Angle + pose.Z);
+                    rays[2 * n] = r.Angle;
+                    rays[2 * n + 1] = r.Radius;
                     n++;
                 }
             }
-            float* odo = stackalloc float[3] { odoPose.X, odoPose.Y, odoPose.Z };
-            Native.Check(Native.cs_update(handle, pts, n, odo, null, out CsResult res), handle);
+            first[s] = n;
+            Native.Check(Native.cs_update_segments(handle, rays, first, poses, n, s, null, out CsResult res), handle);
             Pose = new Vector3(res.Pose[0], res.Pose[1], res.Pose[2]);
             if (SyncMapAfterUpdate) HoleMap.SyncToHost();
-            // UpdateObstacleMap(cloud) continues in C# exactly as in the reference (:751)
+            // UpdateObstacleMap (:751) ran on the device too when the handle was created with obstacle_map_size > 0
         }
 
         public void Dispose()

@@ -14,7 +14,8 @@ namespace CoreSLAM.B200
     [Flags]
     public enum CsFlags : uint
     {
-        None = 0, RowMajorMap = 0x1, Timing = 0x2, KeepDistances = 0x4, NoHostSpin = 0x8, L2Persist = 0x10, DebugRays = 0x20
+        None = 0, RowMajorMap = 0x1, Timing = 0x2, KeepDistances = 0x4, NoHostSpin = 0x8, L2Persist = 0x10, DebugRays = 0x20,
+        SearchWarp = 0x40, SearchSlab = 0x80
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -32,7 +33,7 @@ namespace CoreSLAM.B200
         public ulong Seed;
         public IntPtr Stream;
         public uint Flags;
-        public uint Reserved;
+        public int ObstacleMapSize;        // 0: no ObstacleMap on the device
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -61,6 +62,10 @@ namespace CoreSLAM.B200
         [DllImport(Lib)] public static extern CsStatus cs_get_pose(IntPtr h, float* pose3);
         [DllImport(Lib)] public static extern CsStatus cs_update(IntPtr h, float* pointsXY, int nPoints, float* odometryPose3,
                                                                  float* candOffsets /* T*I*3 or null */, out CsResult result);
+        [DllImport(Lib)] public static extern CsStatus cs_update_segments(IntPtr h, float* raysAngleRadius, int* segFirst, float* segPoses3,
+                                                                          int nRays, int nSegments, float* candOffsets, out CsResult result);
+        [DllImport(Lib)] public static extern CsStatus cs_segments_to_cloud(IntPtr h, float* raysAngleRadius, int* segFirst, float* segPoses3,
+                                                                            int nRays, int nSegments, float* odometryPose3, float* pointsOut);
         [DllImport(Lib)] public static extern CsStatus cs_search(IntPtr h, float* pointsXY, int nPoints, float* searchPose3,
                                                                  float* candPoses, float* candCosSin, int nCand, uint scanIndex,
                                                                  out CsResult best, int* distances);
@@ -70,6 +75,9 @@ namespace CoreSLAM.B200
         [DllImport(Lib)] public static extern CsStatus cs_map_download(IntPtr h, ushort* pixels);
         [DllImport(Lib)] public static extern CsStatus cs_map_upload(IntPtr h, ushort* pixels);
         [DllImport(Lib)] public static extern CsStatus cs_map_packed(IntPtr h, byte* packed);
+        [DllImport(Lib)] public static extern CsStatus cs_set_unmapped_obstacle_hits(IntPtr h, int hits);
+        [DllImport(Lib)] public static extern CsStatus cs_set_max_obstacle_hits(IntPtr h, int hits);
+        [DllImport(Lib)] public static extern CsStatus cs_obstacle_map_download(IntPtr h, sbyte* pixels);
         [DllImport(Lib)] public static extern CsStatus cs_pinned_alloc(out IntPtr ptr, ulong bytes);
         [DllImport(Lib)] public static extern CsStatus cs_pinned_free(IntPtr ptr);
 

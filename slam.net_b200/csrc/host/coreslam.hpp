@@ -109,7 +109,7 @@ class CoreSLAMProcessor {  // CoreSLAM/CoreSLAMProcessor.cs
     pose_ = {p[0], p[1], p[2]};
   }
 
-  // ScanSegmentsToCloud, :187-207 (host side, O(P))
+  // ScanSegmentsToCloud, :187-207, host twin (Update() below runs it on the device through cs_update_segments)
   static void ScanSegmentsToCloud(const std::vector<BaseSLAM::ScanSegment>& segments, Vector3 odometryPose,
                                   BaseSLAM::ScanCloud& cloud) {
     cloud.Points.clear();
@@ -124,10 +124,17 @@ class CoreSLAMProcessor {  // CoreSLAM/CoreSLAMProcessor.cs
   // nullptr uses the on-device Philox stream.
   void Update(const std::vector<BaseSLAM::ScanSegment>& segments, const float* candidateOffsets = nullptr) {
     if (segments.empty()) throw std::invalid_argument("Sequence contains no elements");  // segments.Last(), :719
-    const Vector3 odo = segments.back().Pose;
-    ScanSegmentsToCloud(segments, odo, cloud_);
-    const float odoPose[3] = {odo.X, odo.Y, odo.Z};
-    check(cs_update(h_, &cloud_.Points[0].X, (int32_t)cloud_.Points.size(), odoPose, candidateOffsets, &last_));
+    // flatten List<ScanSegment>: rays (angle, radius) back to back, first-ray index and pose per segment; the cloud
+    // (:723) is computed on the device, the odometry pose is the last segment's (:719)
+    rays_.clear(); segFirst_.clear(); segPoses_.clear();
+    for (const auto& seg : segments) {
+      segFirst_.push_back((int32_t)(rays_.size() / 2));
+      segPoses_.insert(segPoses_.end(), {seg.Pose.X, seg.Pose.Y, seg.Pose.Z});
+      for (const auto& r : seg.Rays) { rays_.push_back(r.Angle); rays_.push_back(r.Radius); }
+    }
+    segFirst_.push_back((int32_t)(rays_.size() / 2));
+    check(cs_update_segments(h_, rays_.data(), segFirst_.data(), segPoses_.data(), (int32_t)(rays_.size() / 2),
+                             (int32_t)segments.size(), candidateOffsets, &last_));
     pose_ = {last_.pose[0], last_.pose[1], last_.pose[2]};
   }
 
@@ -146,7 +153,8 @@ class CoreSLAMProcessor {  // CoreSLAM/CoreSLAMProcessor.cs
   cs_processor* h_ = nullptr;
   HoleMap map_;
   Vector3 pose_;
-  BaseSLAM::ScanCloud cloud_;
+  std::vector<float> rays_, segPoses_;  // flattened List<ScanSegment> of the current Update
+  std::vector<int32_t> segFirst_;
   cs_result last_{};
   int quality_ = 50, psb_ = 5;
   float holeWidth_ = 0.6f;
