@@ -183,6 +183,17 @@ cs_status cs_map_download(cs_processor* h, uint16_t* pixels);      /* Size*Size 
 cs_status cs_map_upload(cs_processor* h, const uint16_t* pixels);
 cs_status cs_map_fill(cs_processor* h, uint16_t value);
 cs_status cs_map_packed(cs_processor* h, uint8_t* packed);          /* HoleMap.GetPackedPixels, HoleMap.cs:44-55 */
+/* Asynchronous export in the reference's viewer formats: a snapshot is taken in stream order (after the last
+ * integration, before the next Update) and copied to `dst` on a side stream while the next Updates run.  `dst` should be
+ * pinned (cs_pinned_alloc) for the copy to overlap; it is valid after cs_map_export_wait.  One export in flight per handle
+ * (a second cs_map_export_begin queues behind the first). */
+typedef enum cs_export_format {
+  CS_EXPORT_GRAY16 = 0,      /* HoleMap.Pixels, Size*Size uint16 row-major: what MainWindow.xaml.cs:227-229 feeds a Gray16 bitmap */
+  CS_EXPORT_PACKED4 = 1,     /* HoleMap.GetPackedPixels (HoleMap.cs:44-55), Size*Size/2 bytes */
+  CS_EXPORT_OBSTACLE_I8 = 2  /* ObstacleMap.Pixels, Size*Size sbyte [y, x] */
+} cs_export_format;
+cs_status cs_map_export_begin(cs_processor* h, int32_t format, void* dst);
+cs_status cs_map_export_wait(cs_processor* h);
 cs_status cs_map_checksum(cs_processor* h, uint64_t* checksum);     /* position-dependent 64-bit hash computed on the device */
 uint64_t cs_host_map_checksum(const uint16_t* pixels, int32_t size); /* same hash of a host row-major map */
 

@@ -104,6 +104,7 @@ FLAG_L2_PERSIST = 0x10
 FLAG_DEBUG_RAYS = 0x20
 FLAG_SEARCH_WARP = 0x40
 FLAG_SEARCH_SLAB = 0x80
+EXPORT_GRAY16, EXPORT_PACKED4, EXPORT_OBSTACLE_I8 = 0, 1, 2
 
 STATUS_NAMES = {0: "CS_OK", 1: "CS_ERR_INVALID_ARGUMENT", 2: "CS_ERR_NO_DEVICE", 3: "CS_ERR_CUDA",
                 4: "CS_ERR_OUT_OF_MEMORY", 5: "CS_ERR_CAPACITY", 6: "CS_ERR_STATE", 7: "CS_ERR_NCCL"}
@@ -143,6 +144,8 @@ SIGNATURES = {
     "cs_map_upload": (C.c_int, [_vp, _vp]),
     "cs_map_fill": (C.c_int, [_vp, C.c_uint16]),
     "cs_map_packed": (C.c_int, [_vp, _vp]),
+    "cs_map_export_begin": (C.c_int, [_vp, C.c_int32, _vp]),
+    "cs_map_export_wait": (C.c_int, [_vp]),
     "cs_map_checksum": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_host_map_checksum": (C.c_uint64, [_vp, C.c_int32]),
     "cs_set_flags": (C.c_int, [_vp, C.c_uint32]),

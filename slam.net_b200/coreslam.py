@@ -313,6 +313,13 @@ class Processor:
     def map_fill(self, value: int):
         self._ck(N.lib().cs_map_fill(self._h, int(value)))
 
+    def map_export_begin(self, fmt: int, out: np.ndarray):
+        """Asynchronous export (cs_map_export_begin): `out` must stay alive and untouched until map_export_wait()."""
+        self._ck(N.lib().cs_map_export_begin(self._h, int(fmt), out.ctypes.data))
+
+    def map_export_wait(self):
+        self._ck(N.lib().cs_map_export_wait(self._h))
+
     def map_packed(self) -> np.ndarray:
         out = np.empty(self.size * self.size // 2, dtype=np.uint8)
         self._ck(N.lib().cs_map_packed(self._h, out.ctypes.data))

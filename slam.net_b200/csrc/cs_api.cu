@@ -78,6 +78,12 @@ struct cs_processor {
   CsObstacle* d_obst = nullptr;
   int unmapped_obstacle_hits = -5;  // :98
 
+  // asynchronous map export (cs_map_export_begin / _wait): snapshot on the main stream, D2H on a side stream
+  cudaStream_t export_stream = nullptr;
+  cudaEvent_t ev_export_snap = nullptr, ev_export_done = nullptr;
+  bool export_busy = false;
+  int8_t* d_obst_snap = nullptr;
+
   float2* d_cloud = nullptr;  // scan points computed on the device from raw segments (cs_update_segments)
 
   // staging: [hdr 64][points][cand][cand_cs]; segments path: [hdr 64][rays][seg_first][seg_poses][cand]
@@ -783,6 +789,11 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
   cudaFree(h->d_cloud);
+  if (h->export_stream) cudaStreamSynchronize(h->export_stream);
+  if (h->ev_export_snap) cudaEventDestroy(h->ev_export_snap);
+  if (h->ev_export_done) cudaEventDestroy(h->ev_export_done);
+  if (h->export_stream) cudaStreamDestroy(h->export_stream);
+  cudaFree(h->d_obst_snap);
   cudaFree(h->d_s2_sorted);
   cudaFree(h->d_s2_tmp);
   cudaFree(h->d_s2_meta);
@@ -1273,7 +1284,17 @@ cs_status cs_sync(cs_processor* h) {
 }
 
 // -----------------------------------------------------------------------------------------------------
+static cs_status export_wait(cs_processor* h) {
+  if (h->export_busy) {
+    CS_CUDA(h, cudaEventSynchronize(h->ev_export_done));
+    h->export_busy = false;
+  }
+  return CS_OK;
+}
+
 static cs_status ensure_linear(cs_processor* h) {
+  cs_status st = export_wait(h);  // the staging buffers below may still be read by an export's D2H copy
+  if (st != CS_OK) return st;
   if (!h->d_linear) CS_CUDA(h, cudaMalloc(&h->d_linear, (size_t)h->size * h->size * sizeof(uint16_t)));
   return CS_OK;
 }
@@ -1317,6 +1338,10 @@ cs_status cs_map_fill(cs_processor* h, uint16_t value) {
 cs_status cs_map_packed(cs_processor* h, uint8_t* packed) {
   CS_CHECK_HANDLE(h);
   if (!packed) return fail(h, CS_ERR_INVALID_ARGUMENT, "null packed");
+  {
+    cs_status wst = export_wait(h);
+    if (wst != CS_OK) return wst;
+  }
   size_t n = ((size_t)h->size * h->size) / 2;
   if (!h->d_packed) CS_CUDA(h, cudaMalloc(&h->d_packed, n));
   dispatch_layout(h->tiled, [&](auto T) {
@@ -1326,6 +1351,62 @@ cs_status cs_map_packed(cs_processor* h, uint8_t* packed) {
   CS_CUDA(h, cudaMemcpyAsync(packed, h->d_packed, n, cudaMemcpyDeviceToHost, h->stream));
   CS_CUDA(h, cudaStreamSynchronize(h->stream));
   return CS_OK;
+}
+
+// Map export without stalling the update stream: the viewer formats of the reference — Gray16
+// (MainWindow.xaml.cs:227-229 writes HoleMap.Pixels into a Gray16 bitmap), 4-bpp packed (HoleMap.GetPackedPixels,
+// HoleMap.cs:44-55) and the ObstacleMap's sbyte grid — are snapshotted by a short kernel in stream order (after the
+// last integration, before the next), and the device-to-host copy of the snapshot runs on a side stream while the next
+// Updates proceed.
+cs_status cs_map_export_begin(cs_processor* h, int32_t format, void* dst) {
+  CS_CHECK_HANDLE(h);
+  if (!dst) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_map_export_begin: null destination");
+  if (format < CS_EXPORT_GRAY16 || format > CS_EXPORT_OBSTACLE_I8) return fail(h, CS_ERR_INVALID_ARGUMENT, "unknown export format %d", format);
+  if (format == CS_EXPORT_OBSTACLE_I8 && !h->d_obst) return fail(h, CS_ERR_STATE, "this processor has no ObstacleMap");
+  if (!h->export_stream) {
+    CS_CUDA(h, cudaStreamCreateWithFlags(&h->export_stream, cudaStreamNonBlocking));
+    CS_CUDA(h, cudaEventCreateWithFlags(&h->ev_export_snap, cudaEventDisableTiming));
+    CS_CUDA(h, cudaEventCreateWithFlags(&h->ev_export_done, cudaEventDisableTiming));
+  }
+  // the previous export's copy must be through with the snapshot buffers before they are overwritten (device-side wait)
+  if (h->export_busy) CS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_export_done, 0));
+  const size_t cells = (size_t)h->size * h->size;
+  const void* src = nullptr;
+  size_t bytes = 0;
+  if (format == CS_EXPORT_GRAY16) {
+    if (!h->d_linear) CS_CUDA(h, cudaMalloc(&h->d_linear, cells * sizeof(uint16_t)));
+    dispatch_layout(h->tiled, [&](auto T) {
+      cs_relayout_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->d_linear, h->size, h->pitch_tiles, 0);
+    });
+    h->launches++;
+    src = h->d_linear; bytes = cells * 2;
+  } else if (format == CS_EXPORT_PACKED4) {
+    if (!h->d_packed) CS_CUDA(h, cudaMalloc(&h->d_packed, cells / 2));
+    dispatch_layout(h->tiled, [&](auto T) {
+      cs_pack_kernel<decltype(T)::value><<<148 * 8, 256, 0, h->stream>>>(h->d_map, h->size, h->pitch_tiles, h->d_packed);
+    });
+    h->launches++;
+    src = h->d_packed; bytes = cells / 2;
+  } else {
+    const CsObstacle& o = h->ho;
+    bytes = (size_t)o.size * o.size;
+    if (!h->d_obst_snap) CS_CUDA(h, cudaMalloc(&h->d_obst_snap, bytes));
+    CS_CUDA(h, cudaMemcpy2DAsync(h->d_obst_snap, (size_t)o.size, o.pixels, (size_t)o.pitch, (size_t)o.size, (size_t)o.size,
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    src = h->d_obst_snap;
+  }
+  CS_CUDA(h, cudaGetLastError());
+  CS_CUDA(h, cudaEventRecord(h->ev_export_snap, h->stream));
+  CS_CUDA(h, cudaStreamWaitEvent(h->export_stream, h->ev_export_snap, 0));
+  CS_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->export_stream));
+  CS_CUDA(h, cudaEventRecord(h->ev_export_done, h->export_stream));
+  h->export_busy = true;
+  return CS_OK;
+}
+
+cs_status cs_map_export_wait(cs_processor* h) {
+  CS_CHECK_HANDLE(h);
+  return export_wait(h);
 }
 
 cs_status cs_map_checksum(cs_processor* h, uint64_t* checksum) {
