@@ -224,6 +224,17 @@ cs_status cs_scanlog_set(cs_scanlog* log, int32_t scan, const float* points, int
                          const float odometry_pose[3], const float* cand_offsets /* n_offsets*3 or NULL */);
 cs_status cs_scanlog_upload(cs_scanlog* log);
 cs_status cs_scanlog_destroy(cs_scanlog* log);
+/* Scan-log files (the reference has no log format — its simulator generates scans live, MainWindow.xaml.cs:380-407 —
+ * so a recorded drive can be replayed through both implementations).  Little-endian:
+ *   header 32 B : "CSLG", u32 version = 1, u32 n_scans, u32 max_points, u32 n_offsets, 12 B reserved (0)
+ *   per scan    : u32 n_points, f32 odometry[3], f32 points[n_points][2] (metres, lidar frame, = ScanCloud.Points),
+ *                 f32 offsets[n_offsets][3] (the candidate deviates the reference would dequeue; absent when n_offsets = 0)
+ * cs_scanlog_file_info / cs_scanlog_file_read are host-only (no CUDA device needed). */
+cs_status cs_scanlog_save(const cs_scanlog* log, const char* path);
+cs_status cs_scanlog_load(int32_t device, const char* path, cs_scanlog** out); /* created, filled and uploaded */
+cs_status cs_scanlog_file_info(const char* path, int32_t* n_scans, int32_t* max_points, int32_t* n_offsets);
+cs_status cs_scanlog_file_read(const char* path, int32_t scan, float* points /* max_points*2 */, int32_t* n_points,
+                               float odometry_pose[3], float* cand_offsets /* n_offsets*3 or NULL */);
 /* Runs Update for scans [first, first+count) back to back on the device; results[count] optional.
  * With results == NULL the call only enqueues the work and returns (cs_sync waits for it). */
 cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);

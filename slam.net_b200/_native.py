@@ -161,6 +161,10 @@ SIGNATURES = {
     "cs_scanlog_set": (C.c_int, [_vp, C.c_int32, _fp, C.c_int32, _fp, _fp]),
     "cs_scanlog_upload": (C.c_int, [_vp]),
     "cs_scanlog_destroy": (C.c_int, [_vp]),
+    "cs_scanlog_save": (C.c_int, [_vp, C.c_char_p]),
+    "cs_scanlog_load": (C.c_int, [C.c_int32, C.c_char_p, C.POINTER(_vp)]),
+    "cs_scanlog_file_info": (C.c_int, [C.c_char_p, _ip, _ip, _ip]),
+    "cs_scanlog_file_read": (C.c_int, [C.c_char_p, C.c_int32, _fp, _ip, _fp, _fp]),
     "cs_replay": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(Result)]),
     "cs_batch_create": (C.c_int, [C.POINTER(Config), C.c_int32, C.POINTER(_vp)]),
     "cs_batch_destroy": (C.c_int, [_vp]),

@@ -137,6 +137,21 @@ class ScanLog:
     def upload(self):
         N.check(N.lib().cs_scanlog_upload(self._h))
 
+    def save(self, path: str):
+        """Write the log as a CSLG file (cs_scanlog_save; format in include/coreslam_b200.h)."""
+        N.check(N.lib().cs_scanlog_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "ScanLog":
+        """A device-resident log from a CSLG file (cs_scanlog_load): created, filled and uploaded."""
+        n, mp, no = C.c_int32(), C.c_int32(), C.c_int32()
+        N.check(N.lib().cs_scanlog_file_info(str(path).encode(), C.byref(n), C.byref(mp), C.byref(no)))
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self.n_scans, self.max_points, self.n_offsets = n.value, mp.value, no.value
+        N.check(N.lib().cs_scanlog_load(device, str(path).encode(), C.byref(self._h)))
+        return self
+
     def close(self):
         if self._h:
             N.lib().cs_scanlog_destroy(self._h)

@@ -1563,6 +1563,128 @@ cs_status cs_scanlog_upload(cs_scanlog* log) {
   return CS_OK;
 }
 
+// ---- scan-log files ---------------------------------------------------------------
+// The reference has no log format (the simulator generates scans live, MainWindow.xaml.cs:380-407); this one lets a
+// recorded drive be replayed through both implementations.  Little-endian, see include/coreslam_b200.h.
+namespace {
+struct CslgHeader {
+  char magic[4];
+  uint32_t version, n_scans, max_points, n_offsets, reserved[3];
+};
+static_assert(sizeof(CslgHeader) == 32, "CSLG header");
+
+struct FileCloser {
+  FILE* f;
+  ~FileCloser() { if (f) fclose(f); }
+};
+
+cs_status cslg_open(const char* path, FILE** f, CslgHeader* hd) {
+  if (!path) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "scan log: null path");
+  *f = fopen(path, "rb");
+  if (!*f) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "scan log: cannot open %s", path);
+  if (fread(hd, sizeof(*hd), 1, *f) != 1 || memcmp(hd->magic, "CSLG", 4) != 0 || hd->version != 1 || hd->n_scans == 0 ||
+      hd->max_points == 0 || hd->max_points > 65536 || hd->n_offsets > (1u << 26)) {
+    fclose(*f);
+    *f = nullptr;
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "scan log: %s is not a CSLG version 1 file", path);
+  }
+  return CS_OK;
+}
+
+// reads the next record; points/offsets may be NULL to skip their payload
+cs_status cslg_read_record(FILE* f, const CslgHeader& hd, int32_t* n_points, float odo[3], float* points, float* offsets) {
+  uint32_t n = 0;
+  if (fread(&n, 4, 1, f) != 1 || n == 0 || n > hd.max_points || fread(odo, 4, 3, f) != 3)
+    return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "scan log: truncated or corrupt record");
+  *n_points = (int32_t)n;
+  const long pts_bytes = (long)n * 8, off_bytes = (long)hd.n_offsets * 12;
+  bool ok = points ? fread(points, 8, n, f) == n : fseek(f, pts_bytes, SEEK_CUR) == 0;
+  if (ok && hd.n_offsets) ok = offsets ? fread(offsets, 12, hd.n_offsets, f) == hd.n_offsets : fseek(f, off_bytes, SEEK_CUR) == 0;
+  return ok ? CS_OK : fail(nullptr, CS_ERR_INVALID_ARGUMENT, "scan log: truncated record");
+}
+}  // namespace
+
+cs_status cs_scanlog_save(const cs_scanlog* log, const char* path) {
+  if (!log || !path) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_save: null argument");
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_save: cannot create %s", path);
+  FileCloser closer{f};
+  CslgHeader hd{};
+  memcpy(hd.magic, "CSLG", 4);
+  hd.version = 1; hd.n_scans = (uint32_t)log->n_scans; hd.max_points = (uint32_t)log->max_points; hd.n_offsets = (uint32_t)log->n_offsets;
+  bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+  for (int k = 0; ok && k < log->n_scans; k++) {
+    const CsStepHeader& sh = log->h_hdr[k];
+    if (sh.n_points <= 0) return fail(nullptr, CS_ERR_STATE, "cs_scanlog_save: scan %d was never set", k);
+    const uint32_t n = (uint32_t)sh.n_points;
+    ok = fwrite(&n, 4, 1, f) == 1 && fwrite(sh.odo, 4, 3, f) == 3 &&
+         fwrite(&log->h_points[(size_t)k * log->max_points * 2], 8, n, f) == n;
+    if (ok && log->n_offsets > 0)
+      ok = fwrite(&log->h_offsets[(size_t)k * log->n_offsets * 3], 12, (size_t)log->n_offsets, f) == (size_t)log->n_offsets;
+  }
+  return ok ? CS_OK : fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_save: write to %s failed", path);
+}
+
+cs_status cs_scanlog_file_info(const char* path, int32_t* n_scans, int32_t* max_points, int32_t* n_offsets) {
+  FILE* f = nullptr;
+  CslgHeader hd;
+  cs_status st = cslg_open(path, &f, &hd);
+  if (st != CS_OK) return st;
+  fclose(f);
+  if (n_scans) *n_scans = (int32_t)hd.n_scans;
+  if (max_points) *max_points = (int32_t)hd.max_points;
+  if (n_offsets) *n_offsets = (int32_t)hd.n_offsets;
+  return CS_OK;
+}
+
+cs_status cs_scanlog_file_read(const char* path, int32_t scan, float* points, int32_t* n_points, float odometry_pose[3],
+                               float* cand_offsets) {
+  if (!n_points || !odometry_pose || scan < 0) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_file_read: bad argument");
+  FILE* f = nullptr;
+  CslgHeader hd;
+  cs_status st = cslg_open(path, &f, &hd);
+  if (st != CS_OK) return st;
+  FileCloser closer{f};
+  if ((uint32_t)scan >= hd.n_scans) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_file_read: scan %d of %u", scan, hd.n_scans);
+  for (int k = 0; k <= scan; k++) {
+    const bool want = k == scan;
+    st = cslg_read_record(f, hd, n_points, odometry_pose, want ? points : nullptr, want ? cand_offsets : nullptr);
+    if (st != CS_OK) return st;
+  }
+  return CS_OK;
+}
+
+cs_status cs_scanlog_load(int32_t device, const char* path, cs_scanlog** out) {
+  if (!out) return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_load: null out");
+  *out = nullptr;
+  FILE* f = nullptr;
+  CslgHeader hd;
+  cs_status st = cslg_open(path, &f, &hd);
+  if (st != CS_OK) return st;
+  FileCloser closer{f};
+  cs_scanlog* log = nullptr;
+  st = cs_scanlog_create(device, (int32_t)hd.n_scans, (int32_t)hd.max_points, (int32_t)hd.n_offsets, &log);
+  if (st != CS_OK) return st;
+  std::vector<float> pts((size_t)hd.max_points * 2), off((size_t)hd.n_offsets * 3);
+  for (uint32_t k = 0; k < hd.n_scans; k++) {
+    int32_t n = 0;
+    float odo[3];
+    st = cslg_read_record(f, hd, &n, odo, pts.data(), hd.n_offsets ? off.data() : nullptr);
+    if (st == CS_OK) st = cs_scanlog_set(log, (int32_t)k, pts.data(), n, odo, hd.n_offsets ? off.data() : nullptr);
+    if (st != CS_OK) {
+      cs_scanlog_destroy(log);
+      return st;
+    }
+  }
+  st = cs_scanlog_upload(log);
+  if (st != CS_OK) {
+    cs_scanlog_destroy(log);
+    return st;
+  }
+  *out = log;
+  return CS_OK;
+}
+
 cs_status cs_scanlog_destroy(cs_scanlog* log) {
   if (!log) return CS_OK;
   cudaSetDevice(log->device);
