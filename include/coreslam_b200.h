@@ -212,6 +212,10 @@ cs_status cs_get_visits(cs_processor* h, int64_t* visits);   /* cells written by
  *                               wait over, [3] scan staged, [4] warp 0 done, [5] block done, [6] pose published
  *                               (last block only), [7] 1 for the block that published */
 cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count);
+/* Which search kernel and launch shape a scan of n_points points and n_cand random candidates gets on this handle:
+ * plan[0] = 1 heading-sorted slab search (cs_sort_kernel + cs_search2_kernel), 0 warp-per-candidate (cs_search_kernel);
+ * plan[1..2] = grid (x, y); plan[3] = threads per block; plan[4] = points per block. */
+cs_status cs_get_search_plan(cs_processor* h, int32_t n_points, int32_t n_cand, int32_t plan[5]);
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches);              /* kernels launched so far by this handle */
 
 /* ---- pinned staging so the C# side can fill ScanCloud points in place ------------------------------- */

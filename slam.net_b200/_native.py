@@ -154,6 +154,7 @@ SIGNATURES = {
     "cs_get_rays": (C.c_int, [_vp, _ip, C.c_int32]),
     "cs_get_visits": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "cs_get_ring_cycles": (C.c_int, [_vp, C.POINTER(C.c_int64), C.c_int32]),
+    "cs_get_search_plan": (C.c_int, [_vp, C.c_int32, C.c_int32, _ip]),
     "cs_get_launch_count": (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     "cs_pinned_alloc": (C.c_int, [C.POINTER(_vp), C.c_uint64]),
     "cs_pinned_free": (C.c_int, [_vp]),

@@ -403,6 +403,13 @@ class Processor:
         self._ck(N.lib().cs_get_ring_cycles(self._h, out.ctypes.data_as(C.POINTER(C.c_int64)), count * 8))
         return out.reshape(count, 8)
 
+    def search_plan(self, n_points: int, n_cand: Optional[int] = None) -> dict:
+        """Which search kernel / launch shape a scan gets (cs_get_search_plan)."""
+        plan = (C.c_int32 * 5)()
+        self._ck(N.lib().cs_get_search_plan(self._h, int(n_points), int(self.n_cand if n_cand is None else n_cand), plan))
+        return {"kernel": "cs_sort_kernel + cs_search2_kernel (heading-sorted slabs)" if plan[0] else "cs_search_kernel (warp per candidate)",
+                "slab": bool(plan[0]), "grid": [int(plan[1]), int(plan[2])], "threads": int(plan[3]), "points_per_block": int(plan[4])}
+
     def launch_count(self) -> int:
         v = C.c_uint64()
         self._ck(N.lib().cs_get_launch_count(self._h, C.byref(v)))

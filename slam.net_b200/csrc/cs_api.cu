@@ -1484,6 +1484,20 @@ cs_status cs_get_ring_cycles(cs_processor* h, int64_t* cycles, int32_t count) {
   return CS_OK;
 }
 
+cs_status cs_get_search_plan(cs_processor* h, int32_t n_points, int32_t n_cand, int32_t plan[5]) {
+  CS_CHECK_HANDLE(h);
+  if (!plan || n_points < 1 || n_cand < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_get_search_plan: bad argument");
+  const int sms = device_sm_count(h->device);
+  S2Plan s2;
+  if (cs_plan_search2(1, h->s2_cap, cs_s2_min_cand(h->cfg.flags), (long long)n_cand + 1, n_points, sms, &s2)) {
+    plan[0] = 1; plan[1] = s2.clusters; plan[2] = s2.slabs; plan[3] = s2.threads; plan[4] = s2.points;
+  } else {
+    const int warps = cs_search_warps((long long)n_cand + 1, 1, sms);
+    plan[0] = 0; plan[1] = (int)(((long long)n_cand + 1 + warps - 1) / warps); plan[2] = 1; plan[3] = warps * 32; plan[4] = n_points;
+  }
+  return CS_OK;
+}
+
 cs_status cs_get_launch_count(cs_processor* h, uint64_t* launches) {
   if (!h || !launches) return CS_ERR_INVALID_ARGUMENT;
   *launches = h->launches;
