@@ -181,8 +181,7 @@ def test_slab_cfg2_slice_distances_equal_warp_kernel_and_oracle():
         o.update(rp.points[k], rp.odometry[k], off)
         for r in rs:
             assert np.array_equal(r.pose, o.pose)
-    launches = [p.launch_count() for p in ps]
-    assert launches[0] > launches[1]  # the slab path really ran: one more kernel (the sort) per searched scan
+    assert ps[0].search_plan(1024)["slab"] and not ps[1].search_plan(1024)["slab"]  # the default really is the slab search
     for p in ps:
         assert np.array_equal(p.map_download(), np.array(o.map.pixels))
         p.close()
