@@ -423,7 +423,7 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
       if (e != cudaSuccess) return e;
       (*c.launches)++;
     } else {
-      const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_THREADS * CS_SORT_REG - 1) / (CS_SORT_THREADS * CS_SORT_REG));
+      const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_MB_CHUNK - 1) / CS_SORT_MB_CHUNK);
       e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_hist_kernel<true> : cs_sort_hist_kernel<false>, dim3(sort_blocks),
                      dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
       if (e != cudaSuccess) return e;

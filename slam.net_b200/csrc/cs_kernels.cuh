@@ -685,7 +685,8 @@ cs_search_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 #define CS_S2_MAX_CLUSTERS 16384
 #define CS_SORT_BINS 2048      // heading bins: [-4 sigma, 4 sigma) in steps of sigma / 256, clamped
 #define CS_SORT_THREADS 1024
-#define CS_SORT_REG 8          // candidates a thread keeps in registers between the two passes (more: global scratch)
+#define CS_SORT_REG 8          // candidates a thread of the one-block sort keeps in registers between its two passes
+#define CS_SORT_MB_CHUNK 1024  // candidates per block of the two-kernel sort
 
 // heading bin of a candidate whose heading differs from the search pose's by `rel`
 __device__ __forceinline__ unsigned cs_sort_bin(float rel, float inv) {
@@ -791,7 +792,7 @@ cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 }
 
 // Candidate sets too big for one block: the same counting sort over several blocks and two kernels.
-// cs_sort_hist_kernel: every block bins its CS_SORT_THREADS * CS_SORT_REG candidates, reserves a run inside each bin of the
+// cs_sort_hist_kernel: every block bins its CS_SORT_MB_CHUNK candidates (one per thread: the blocks spread over the SMs), reserves a run inside each bin of the
 // global histogram (one atomicAdd per non-empty bin and block, the returned value is the block's base rank in that bin)
 // and parks entry and (bin, rank) in global scratch.  cs_sort_scatter_kernel: every block scans the complete histogram
 // and moves its candidates to their final positions; the last block re-arms the histogram.
@@ -802,8 +803,8 @@ cs_sort_hist_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   cs_pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int n = a.cand_count;
-  const int base_i = blockIdx.x * (CS_SORT_THREADS * CS_SORT_REG);
-  const int end_i = min(n, base_i + CS_SORT_THREADS * CS_SORT_REG);
+  const int base_i = blockIdx.x * (CS_SORT_MB_CHUNK);
+  const int end_i = min(n, base_i + CS_SORT_MB_CHUNK);
   for (int i = tid; i < CS_SORT_BINS; i += CS_SORT_THREADS) s_hist[i] = 0u;
   __syncthreads();
   const float inv = a.s2_sigma_theta > 0.f ? 256.0f / a.s2_sigma_theta : 0.f;
@@ -851,15 +852,11 @@ cs_sort_scatter_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   cs_pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int n = a.cand_count;
-  const int base_i = blockIdx.x * (CS_SORT_THREADS * CS_SORT_REG);
+  const int base_i = blockIdx.x * (CS_SORT_MB_CHUNK);
   cs_sort_scan(s_hist, s_warp, __ldcg(&a.s2_ghist[2 * tid]), __ldcg(&a.s2_ghist[2 * tid + 1]));
-#pragma unroll
-  for (int k = 0; k < CS_SORT_REG; k++) {
-    const int i = base_i + tid + k * CS_SORT_THREADS;
-    if (i < n) {
-      const unsigned long long m = __ldcg(&a.s2_meta[i]);
-      a.s2_sorted[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = __ldcg(&a.s2_tmp[i]);
-    }
+  for (int i = base_i + tid; i < min(n, base_i + CS_SORT_MB_CHUNK); i += CS_SORT_THREADS) {
+    const unsigned long long m = __ldcg(&a.s2_meta[i]);
+    a.s2_sorted[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = __ldcg(&a.s2_tmp[i]);
   }
   // the last block to get here re-arms the histogram for the next step (every block has read it by then)
   __syncthreads();
