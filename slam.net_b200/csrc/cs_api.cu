@@ -223,7 +223,7 @@ double max_range_of(const float* points, int n) {
 // Experiment knobs (environment, read once): CS_TUNE_SEARCH_WARPS (2/4/8), CS_TUNE_RING_SPAN, CS_TUNE_RING_THREADS.
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
-  int search_warps = 0, ring_span = 0, ring_threads = 0;
+  int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -234,6 +234,7 @@ struct Tune {
     s2_min_cand = geti("CS_TUNE_S2_MIN_CAND");  // fewest candidates the slab search is used for
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
+    ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
   }
 };
 const Tune& tune() { static Tune t; return t; }
@@ -273,25 +274,29 @@ int cs_search_warps(long long cand_count, int n_sessions, int num_sms) {
 // Slab search (cs_sort_kernel + cs_search2_kernel) instead of the warp-per-candidate kernel: one session alone whose
 // candidate count fills the machine with slabs.  Block (c, s) = points [c*points, ...) x sorted candidates [s*threads, ...).
 constexpr int kS2MinCand = 1024;
+constexpr int kS2MinCandBatch = 256;
 struct S2Plan {
   int points = 0, threads = 0, clusters = 0, slabs = 0;
 };
-int cs_s2_min_cand(uint32_t flags) {  // fewest candidates (searchPose included) the slab search is used for; 0 = never
+int cs_s2_min_cand(uint32_t flags, int n_sessions = 1) {  // fewest candidates (searchPose included) the slab search is used for; 0 = never
   if ((flags & CS_FLAG_SEARCH_WARP) || tune().search2 < 0) return 0;
   if (flags & CS_FLAG_SEARCH_SLAB) return 1;
-  return tune().s2_min_cand > 0 ? tune().s2_min_cand : kS2MinCand;
+  if (tune().s2_min_cand > 0) return tune().s2_min_cand;
+  // a batch fills the machine with its sessions; what the slabs need is enough candidates to amortise a block's set-up
+  return n_sessions > 1 ? kS2MinCandBatch : kS2MinCand;
 }
 bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_count, int n_points, int num_sms, S2Plan* p) {
-  if (min_cand <= 0 || n_sessions != 1 || s2_cap <= 0 || cand_count > s2_cap || n_points < 1) return false;
+  if (min_cand <= 0 || n_sessions < 1 || s2_cap <= 0 || cand_count > s2_cap || n_points < 1) return false;
   if (cand_count < min_cand) return false;
+  if (n_sessions > 1 && (cand_count > CS_SORT_THREADS * CS_SORT_REG || n_sessions > 65535)) return false;  // batches: one sort block per session
   // the plan depends on (candidates, points, SMs) only: remember the last one (a replay asks for the same every scan)
-  struct Memo { long long cand = -1; int points = -1, sms = -1; bool ok = false; S2Plan plan; };
+  struct Memo { long long cand = -1; int points = -1, sms = -1, sessions = -1; bool ok = false; S2Plan plan; };
   static thread_local Memo memo;
-  if (memo.cand == cand_count && memo.points == n_points && memo.sms == num_sms) {
+  if (memo.cand == cand_count && memo.points == n_points && memo.sms == num_sms && memo.sessions == n_sessions) {
     *p = memo.plan;
     return memo.ok;
   }
-  memo.cand = cand_count; memo.points = n_points; memo.sms = num_sms; memo.ok = false;
+  memo.cand = cand_count; memo.points = n_points; memo.sms = num_sms; memo.sessions = n_sessions; memo.ok = false;
   // Launch shape: the kernel is one resident wave of blocks (clusters x slabs) and ends when the busiest SM ends.  A lane
   // pays a fixed set-up (candidate pose, cos/sin: ~kSetup instruction slots) plus ~kLookup per point of its cluster, in
   // whole batches of CS_S2_BATCH; a block's cost is that times its warps, and an SM issues about kIpcPerWarp
@@ -310,7 +315,7 @@ bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_co
     for (int threads = t_hi; threads >= t_lo; threads -= 32) {  // bigger blocks win ties: one cluster's lines shared by more warps
       const long long slabs = (cand_count + threads - 1) / threads;
       if (slabs > 65535) continue;
-      const long long blocks = clusters * slabs;
+      const long long blocks = clusters * slabs * n_sessions;
       const long long per_sm = (blocks + num_sms - 1) / num_sms;
       const double warps = (double)per_sm * (threads / 32);
       const double resident = warps < 48.0 ? warps : 48.0;
@@ -405,6 +410,7 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_points = s2.points;
     a.s2_slab = s2.threads;
     a.s2_slot = (*c.s2_toggle ^= 1);
+    a.s2_batch = c.n_sessions > 1 ? 1 : 0;
     a.s2_map = c.hs->map;
     a.s2_sorted = c.hs->s2_sorted + (size_t)a.s2_slot * c.hs->s2_cap;
     a.s2_tmp = c.hs->s2_tmp;
@@ -418,8 +424,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_sigma_xy = c.hs->sigma_xy;
     a.s2_sigma_theta = c.hs->sigma_theta;
     if (a.cand_count <= CS_SORT_THREADS * CS_SORT_REG) {
-      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>, dim3(1), dim3(CS_SORT_THREADS), 0,
-                     c.stream, c.d_sess, a);
+      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>, dim3(1, (unsigned)c.n_sessions),
+                     dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
       if (e != cudaSuccess) return e;
       (*c.launches)++;
     } else {
@@ -432,8 +438,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
       (*c.launches) += 2;
     }
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(cs_search2_kernel<decltype(T)::value>, dim3((unsigned)s2.clusters, (unsigned)s2.slabs), dim3(s2.threads), 0,
-                     c.stream, c.d_sess, a);
+      e = launch_pdl(cs_search2_kernel<decltype(T)::value>, dim3((unsigned)s2.clusters, (unsigned)s2.slabs, (unsigned)c.n_sessions),
+                     dim3(s2.threads), 0, c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -466,14 +472,18 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (threads > CS_RING_MAX_THREADS) threads = CS_RING_MAX_THREADS;
     if (rings < 1) rings = 1;
     // One session alone: a grid of at most one resident wave (2 blocks per SM) whose blocks draw work units of
-    // `span` rings from a ticket counter.  A batch of sessions: one unit of 8 rings per block, grid.y = sessions.
+    // `span` rings from a ticket counter.  A batch of sessions: one unit of 32 rings per block, grid.y = sessions (measured on cfg5: 8 -> 32 rings per unit and a 2048-entry slot table take a step from 8.6 to 5.1 ms).
     const bool dynamic = c.n_sessions == 1;
-    int span = dynamic ? 1 : 8;
+    int span = dynamic ? 1 : 32;
     if (tune().ring_span > 0) span = tune().ring_span;
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
     a.ring_span = span;
     a.ring_dynamic = dynamic ? 1 : 0;
+    // slot table: a session alone keeps every ring up to k = 1024 in one window; a batch trades windows on its outer
+    // rings for resident blocks (shared memory per block is what limits them)
+    a.ring_slot_bits = dynamic ? CS_RING_MAX_SLOT_BITS : 11;
+    if (tune().ring_slot_bits >= 8 && tune().ring_slot_bits <= CS_RING_MAX_SLOT_BITS) a.ring_slot_bits = tune().ring_slot_bits;
     int blocks = (rings + span - 1) / span;
     if (dynamic && blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
     // the first blocks also prepare the rays, 128 each (one warp per SM sub-partition: the preparation is a
@@ -485,7 +495,7 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (blocks < nprep) blocks = nprep;
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_rings_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
-                     CS_RING_SMEM(threads), c.stream, c.d_sess, a);
+                     CS_RING_SMEM(threads, a.ring_slot_bits), c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -675,9 +685,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_prep_words, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaMemset(h->d_prep_words, 0, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
+                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
   CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS)));
+                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
@@ -1790,6 +1800,11 @@ struct cs_batch {
   int* d_batch_max = nullptr;
   unsigned long long* d_prep_words = nullptr;
   unsigned long long* d_checksum = nullptr;
+  // slab-search scratch of all sessions (CsSession::s2_*): per session 2*cap sorted + cap tmp entries, cap meta + cap acc words
+  float4* d_s2_entries = nullptr;
+  unsigned long long* d_s2_words = nullptr;
+  int s2_cap = 0, s2_toggle = 0;
+  uint32_t flags = 0;
   // staging: [n headers][n * max_points points][n * n_cand offsets]
   size_t off_points = 0, off_cand = 0, stage_bytes = 0;
   uint8_t* h_stage = nullptr;
@@ -1840,6 +1855,10 @@ LaunchCtx batch_ctx(cs_batch* b) {
   c.n_sessions = b->n;
   c.launches = &b->launches;
   c.step_counter = &b->step_counter;
+  c.s2_cap = b->s2_cap;
+  c.s2_min_cand = cs_s2_min_cand(b->flags, b->n);
+  c.s2_toggle = &b->s2_toggle;
+  c.hs = &b->hs[0];
   return c;
 }
 
@@ -1918,14 +1937,25 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_prep_words, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMemset(b->d_prep_words, 0, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
+  b->flags = c0.flags;
+  {
+    const int min_cand = cs_s2_min_cand(c0.flags, n_sessions);
+    if (n_sessions > 1 && min_cand > 0 && n_cand + 1 >= min_cand && n_cand + 1 <= CS_SORT_THREADS * CS_SORT_REG) {
+      b->s2_cap = n_cand + 1;
+      const size_t cap = (size_t)b->s2_cap;
+      ok = ok && cudaMalloc(&b->d_s2_entries, (size_t)n_sessions * 3 * cap * sizeof(float4)) == cudaSuccess;
+      ok = ok && cudaMalloc(&b->d_s2_words, (size_t)n_sessions * 2 * cap * sizeof(unsigned long long)) == cudaSuccess;
+      ok = ok && cudaMemsetAsync(b->d_s2_words, 0, (size_t)n_sessions * 2 * cap * sizeof(unsigned long long), b->stream) == cudaSuccess;
+    }
+  }
   ok = ok && cudaHostAlloc(&b->h_stage, b->stage_bytes, cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS)) == cudaSuccess;
+                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
   ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS)) == cudaSuccess;
+                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
   if (!ok) {
     cudaError_t e = cudaGetLastError();
     bfail(nullptr, e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "cs_batch_create: %s", cudaGetErrorString(e));
@@ -1954,6 +1984,14 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
     s.ray_stride = b->max_points;
     s.batch_stride = b->max_points / 32 + 1;
     s.prep_words = b->d_prep_words + (size_t)j * 2 * 16;
+    if (b->s2_cap > 0) {
+      const size_t cap = (size_t)b->s2_cap;
+      s.s2_sorted = b->d_s2_entries + (size_t)j * 3 * cap;
+      s.s2_tmp = s.s2_sorted + 2 * cap;
+      s.s2_meta = b->d_s2_words + (size_t)j * 2 * cap;
+      s.s2_acc = s.s2_meta + cap;
+      s.s2_cap = b->s2_cap;
+    }
   }
   batch_reset_host(b, cfgs);
   cs_fill_kernel<<<148 * 8, 256, 0, b->stream>>>(b->d_maps, b->map_cells * (size_t)n_sessions,
@@ -1980,6 +2018,8 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_batch_max);
   cudaFree(b->d_prep_words);
   cudaFree(b->d_checksum);
+  cudaFree(b->d_s2_entries);
+  cudaFree(b->d_s2_words);
   cudaFree(b->d_stage);
   cudaFree(b->d_results);
   if (b->h_stage) cudaFreeHost(b->h_stage);
@@ -2068,6 +2108,7 @@ cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_poi
   a.n_cand = b->n_cand;
   a.cand_first = 0;
   a.cand_count = b->n_cand + 1;
+  a.s2_host_points = max_n;
   CS_BCUDA(b, launch_step_ctx(batch_ctx(b), a, max_n, rings_hint_of(b->size, b->scale, batch_max_hole_width(b), max_range), CS_PHASE_ALL));
   b->parity ^= 1;
   b->update_count++;
@@ -2114,6 +2155,7 @@ cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int
     a.n_cand = b->n_cand;
     a.cand_first = 0;
     a.cand_count = b->n_cand + 1;
+    a.s2_host_points = log->h_hdr[sidx].n_points;
     CS_BCUDA(b, launch_step_ctx(batch_ctx(b), a, log->h_hdr[sidx].n_points,
                                 rings_hint_of(b->size, b->scale, hw, log->h_max_range[sidx]), CS_PHASE_ALL));
     b->parity ^= 1;

@@ -142,6 +142,7 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int ring_span;     // rings per work unit of the rings kernel
   int prep_group;    // rays prepared by each of the first blocks of the rings kernel (multiple of 32)
   int ring_dynamic;  // 1: blocks draw further units from CsSession::ring_ticket (one session, grid <= one wave)
+  int ring_slot_bits; // log2 of the rings kernel's slot table (<= CS_RING_MAX_SLOT_BITS)
   int search_chunk;  // points staged in shared memory per pass of the search kernel (<= CS_SEARCH_CHUNK)
   unsigned step_id;  // nonzero, different for consecutive steps on the same session(s): tags ll_pose, selects the counter slots
   long long* visits_out;  // optional device slot that receives the visit count
@@ -164,7 +165,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned long long s2_seed;
   int s2_size, s2_pitch_tiles;
   float s2_scale, s2_sigma_xy, s2_sigma_theta;
-  int s2_pad;
+  int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values
+                                 // above come from CsSession instead, hdr / points / cand / result are strided per session
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -737,30 +739,39 @@ cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   cs_pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int n = a.cand_count;
-  float4* __restrict__ out = a.s2_sorted;
+  // a batch of sessions: one block per session, everything per session comes from its descriptor
+  const int sj = blockIdx.y;
+  const CsSession& S = sessions[sj];
+  const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
+  float4* __restrict__ out = a.s2_batch ? S.s2_sorted + (size_t)a.s2_slot * S.s2_cap : a.s2_sorted;
+  float4* __restrict__ tmp = a.s2_batch ? S.s2_tmp : a.s2_tmp;
+  unsigned long long* __restrict__ meta = a.s2_batch ? S.s2_meta : a.s2_meta;
+  const float sigma_theta = a.s2_batch ? S.sigma_theta : a.s2_sigma_theta;
+  const float sigma_xy = a.s2_batch ? S.sigma_xy : a.s2_sigma_xy;
+  const unsigned long long seed = a.s2_batch ? S.seed : a.s2_seed;
   for (int i = tid; i < CS_SORT_BINS; i += CS_SORT_THREADS) s_hist[i] = 0u;
   __syncthreads();
-  const float inv = a.s2_sigma_theta > 0.f ? 256.0f / a.s2_sigma_theta : 0.f;
+  const float inv = sigma_theta > 0.f ? 256.0f / sigma_theta : 0.f;
   if (PHILOX) {
 #pragma unroll 1
     for (int i = tid; i < n; i += CS_SORT_THREADS) {
       const int idx = a.cand_first + i;
       float off[3] = {0.f, 0.f, 0.f};
-      if (idx > 0) cs_gauss3(a.s2_seed, a.scan_index, (uint32_t)(idx - 1), a.s2_sigma_xy, a.s2_sigma_theta, off);
+      if (idx > 0) cs_gauss3(seed, a.scan_index, (uint32_t)(idx - 1), sigma_xy, sigma_theta, off);
       const unsigned bin = cs_sort_bin(off[2], inv);
       const unsigned rank = atomicAdd(&s_hist[bin], 1u);
-      a.s2_tmp[i] = make_float4(off[0], off[1], off[2], __int_as_float(idx));
-      a.s2_meta[i] = ((unsigned long long)bin << 32) | rank;
+      tmp[i] = make_float4(off[0], off[1], off[2], __int_as_float(idx));
+      meta[i] = ((unsigned long long)bin << 32) | rank;
     }
     __syncthreads();
     cs_sort_scan(s_hist, s_warp, s_hist[2 * tid], s_hist[2 * tid + 1]);
 #pragma unroll 1
     for (int i = tid; i < n; i += CS_SORT_THREADS) {
-      const unsigned long long m = a.s2_meta[i];
-      out[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = a.s2_tmp[i];
+      const unsigned long long m = meta[i];
+      out[s_hist[(unsigned)(m >> 32)] + (unsigned)m] = tmp[i];
     }
   } else {
-    const float ref = a.cand_mode == CS_CAND_ABSOLUTE ? a.hdr[0].odo[2] : 0.f;  // headings are binned relative to the search pose
+    const float ref = a.cand_mode == CS_CAND_ABSOLUTE ? a.hdr[(size_t)sj * a.hdr_stride].odo[2] : 0.f;  // headings are binned relative to the search pose
     float ex[CS_SORT_REG], ey[CS_SORT_REG], ez[CS_SORT_REG];
     unsigned met[CS_SORT_REG];  // bin << 16 | rank inside the bin (< 8192)
 #pragma unroll
@@ -769,7 +780,7 @@ cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       const int idx = a.cand_first + i;
       ex[k] = 0.f; ey[k] = 0.f; ez[k] = 0.f;
       if (i < n && idx > 0) {
-        const float* p = a.cand + 3 * (size_t)(idx - 1);
+        const float* p = cand + 3 * (size_t)(idx - 1);
         ex[k] = __ldg(p); ey[k] = __ldg(p + 1); ez[k] = __ldg(p + 2);
       }
     }
@@ -870,22 +881,27 @@ template <bool TILED>
 __global__ void __launch_bounds__(CS_S2_MAX_THREADS)
 cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ float2 s_pts[CS_S2_MAX_POINTS];
-  CsSession& S = sessions[0];
-  const CsStepHeader& hdr = a.hdr[0];
+  const int sj = blockIdx.z;  // session of a batch (0 for a session alone)
+  CsSession& S = sessions[sj];
+  const CsStepHeader& hdr = a.hdr[(size_t)sj * a.hdr_stride];
+  const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
+  const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   const int tid = threadIdx.x, lane = tid & 31;
   const int cluster = blockIdx.x, slab = blockIdx.y;
   const unsigned n_clusters = gridDim.x;
 
   // ---- before the dependency wait: this step's inputs and host-owned constants only
-  const int P = a.s2_host_points;  // = hdr.n_points
+  const int P = a.s2_batch ? hdr.n_points : a.s2_host_points;  // = hdr.n_points (the sessions of a batch may differ)
   const int p0 = cluster * a.s2_points;
   const int np = max(0, min(a.s2_points, P - p0));
   const int np_pad = (np + CS_S2_BATCH - 1) / CS_S2_BATCH * CS_S2_BATCH;
   // the last batch is padded with NaN points: they fail the bounds test like any NaN point does (:244)
-  if (tid < np_pad) s_pts[tid] = tid < np ? __ldg(a.points + p0 + tid) : make_float2(__int_as_float(0x7fc00000), 0.f);
-  const int size = a.s2_size, pitch_tiles = a.s2_pitch_tiles;
-  const uint16_t* __restrict__ map = a.s2_map;
-  const float scale = a.s2_scale;
+  for (int i = tid; i < np_pad; i += blockDim.x) s_pts[i] = i < np ? __ldg(points + p0 + i) : make_float2(__int_as_float(0x7fc00000), 0.f);
+  const int size = a.s2_batch ? S.size : a.s2_size, pitch_tiles = a.s2_batch ? S.pitch_tiles : a.s2_pitch_tiles;
+  const uint16_t* __restrict__ map = a.s2_batch ? S.map : a.s2_map;
+  const float scale = a.s2_batch ? S.scale : a.s2_scale;
+  const float4* __restrict__ sorted = a.s2_batch ? S.s2_sorted + (size_t)a.s2_slot * S.s2_cap : a.s2_sorted;
+  unsigned long long* __restrict__ acc = a.s2_batch ? S.s2_acc : a.s2_acc;
   int* const distances = S.distances;
   const int pos = slab * a.s2_slab + tid;  // position in the sorted order
   const bool valid = pos < a.cand_count;
@@ -896,7 +912,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   float px = 0.f, py = 0.f, c = 0.f, s = 0.f;
   int idx = 0;
   if (valid) {
-    const float4 e = __ldcg(a.s2_sorted + pos);
+    const float4 e = __ldcg(sorted + pos);
     idx = __float_as_int(e.w);
     float sp[3], pose[3];
     cs_search_pose(S, hdr, a, sp);
@@ -958,7 +974,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // totally ordered), so it owns the candidate's complete sum: distance (:251-258), arg-min, and the word goes back to
   // zero for the next step.  No fence, no block-wide wait.
   const unsigned long long mine = (1ull << CS_S2_ARRIVAL_SHIFT) | ((unsigned long long)nb << 32) | (unsigned long long)sum;
-  const unsigned long long old = atomicAdd(&a.s2_acc[pos], mine);
+  const unsigned long long old = atomicAdd(&acc[pos], mine);
   const bool fin = (unsigned)(old >> CS_S2_ARRIVAL_SHIFT) == n_clusters - 1u;
   unsigned long long key = ~0ull;
   if (fin) {
@@ -967,7 +983,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const int d = cnt > 0 ? (int)((cells * 1024ull) / (unsigned long long)P) : 2147483647;  // :251-258
     key = ((unsigned long long)(unsigned)d << 32) | (unsigned)idx;
     if (distances) distances[idx] = d;
-    a.s2_acc[pos] = 0ull;
+    acc[pos] = 0ull;
   }
   const unsigned fin_mask = __ballot_sync(act, fin);
   if (fin_mask == 0u) return;
@@ -987,7 +1003,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const bool last = atomicAdd(&S.search_done, nfin) + nfin == (unsigned)a.cand_count;
   if (!last) return;
   S.search_done = 0;
-  cs_publish(S, hdr, a, a.cand, a.result, true, guess);
+  cs_publish(S, hdr, a, cand, a.result ? a.result + (size_t)sj * a.result_stride : nullptr, true, guess);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1028,17 +1044,19 @@ cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 //      count+1 times (with the exact fixed-point early-out); for mixed cells the 32-ray batches that visit
 //      the cell are chained in ascending order through the slot (mask of batches + a hand-off word), each
 //      batch applying its lanes in lane order.
-// Rings with more than CS_RING_SLOTS positions (k > 1024) go through the table in windows of positions.
+// Rings with more positions (8k) than the slot table has entries go through the table in windows of positions; the
+// table size is chosen per launch (CsStepArgs::ring_slot_bits): 8192 entries for a session alone, fewer for batches of
+// sessions, where more resident blocks are worth more than single-pass outer rings.
 // No global atomics, no sort, bit-exact for any ray order; shared-memory atomics only on contested visits.
 // Scans with more rays than one round (threads x CS_RING_RPT) are processed in consecutive rounds; a
 // round starts after the previous round's stores, which keeps the ray order across rounds.
 // ---------------------------------------------------------------------------------------------------
 #define CS_RING_MAX_THREADS 512
 #define CS_RING_RPT 2                  // rays per lane and round
-#define CS_RING_SLOTS 8192             // slot table entries: rings up to k = 1024 are indexed directly, longer ones hashed
-#define CS_RING_MAX_SPAN 16
+#define CS_RING_MAX_SLOT_BITS 13        // largest slot table: 8192 entries, rings up to k = 1024 in one window
+#define CS_RING_MAX_SPAN 256
 // dynamic shared memory for a block of `threads` threads
-#define CS_RING_SMEM(threads) ((size_t)CS_RING_SLOTS * 8 + (size_t)(threads) * CS_RING_RPT * (16 + 4))
+#define CS_RING_SMEM(threads, slot_bits) (((size_t)8 << (slot_bits)) + (size_t)(threads) * CS_RING_RPT * (16 + 4))
 
 __device__ __forceinline__ int cs_blend(int old, int pixval, int alpha) {
   return (int)(uint16_t)(((256 - alpha) * old + alpha * pixval) >> 8);  // :431
@@ -1099,12 +1117,13 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const int round_cap = nthreads * CS_RING_RPT;
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned* s_w = reinterpret_cast<unsigned*>(cs_ring_smem);            // slot -> local ray << 18 | pixval (0 .. 2*65500 + carries: 18 bits); later: batch mask
-  unsigned* s_c = s_w + CS_RING_SLOTS;                                   // slot -> contested visits | mixed marks << 16; later: hand-off word
-  int4* s_rays = reinterpret_cast<int4*>(s_c + CS_RING_SLOTS);           // this round's packed rays
+  const int slot_bits = a.ring_slot_bits, n_slots = 1 << slot_bits;
+  unsigned* s_c = s_w + n_slots;                                         // slot -> contested visits | mixed marks << 16; later: hand-off word
+  int4* s_rays = reinterpret_cast<int4*>(s_c + n_slots);                 // this round's packed rays
   int* s_lpv = reinterpret_cast<int*>(s_rays + round_cap);               // pixvals of the visits of mixed cells
   {  // the counters start at zero; done before the dependency wait, so it overlaps the previous kernel's tail
     uint4* c4 = reinterpret_cast<uint4*>(s_c);
-    for (int i = tid; i < CS_RING_SLOTS / 4; i += nthreads) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < n_slots / 4; i += nthreads) c4[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   cs_pdl_launch_dependents();  // the next step's search may become resident once every block here has started
   // No griddepcontrol.wait here: the kernel in front (search / set-up) is not awaited as a whole.  Its publishing
@@ -1252,8 +1271,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
           live[j] = cs_ring_visit<TILED>(r, k, x1, y1, size, pitch_tiles, pos[j], cell[j], pv[j]);
         }
       }
-      // rings longer than the slot table (k > 1024) are handled in windows of CS_RING_SLOTS positions
-      const int nwin = max((8 * k + CS_RING_SLOTS - 1) / CS_RING_SLOTS, 1);
+      // rings longer than the slot table are handled in windows of n_slots positions
+      const int nwin = max((8 * k + n_slots - 1) >> slot_bits, 1);
       bool warp_dead = true;
 #pragma unroll
       for (int j = 0; j < CS_RING_RPT; j++) warp_dead = warp_dead && (bmax[j] < k);
@@ -1282,8 +1301,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         // ---- 1. claim the slots ------------------------------------------------------------------------------
 #pragma unroll
         for (int j = 0; j < CS_RING_RPT; j++) {
-          act[j] = live[j] && (pos[j] >> 13) == win;
-          h[j] = pos[j] & (CS_RING_SLOTS - 1);
+          act[j] = live[j] && (pos[j] >> slot_bits) == win;
+          h[j] = pos[j] & (n_slots - 1);
           if (act[j]) {
             const int li = (warp * CS_RING_RPT + j) * 32 + lane;
             word[j] = ((unsigned)li << 18) | ((unsigned)pv[j] & 0x3ffffu);

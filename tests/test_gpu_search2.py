@@ -218,3 +218,53 @@ def test_slab_candidate_split_two_handles_one_device():
     for p in ranks:
         assert np.array_equal(p.map_download(), np.array(o.map.pixels))
         p.close()
+
+
+@pytest.mark.parametrize("flags", [SLAB, 0])
+def test_slab_batch_update_matches_oracle_per_session(flags):
+    """Session batches (grid.z = session): per-session sort + slab search, ragged point counts, verification tables.
+    flags = 0: 300 candidates per session is above the batch threshold (256), so the default is the slab search too."""
+    n_sess, n_scans, P, size, phys, iters, threads = 5, 12, 200, 256, 40.0, 150, 2
+    rps = [synth.make_replay(n_scans, P, phys, seed=50 + j) for j in range(n_sess)]
+    sxy = [0.05 + 0.02 * j for j in range(n_sess)]
+    sth = [0.10 + 0.01 * j for j in range(n_sess)]
+    b = sn.Batch(n_sess, phys, size, [rp.odometry[0] for rp in rps], sxy, sth, iters, threads, max_points=P, flags=flags)
+    os_ = [orc.Processor(phys, size, rps[j].odometry[0], sxy[j], sth[j], iters, threads) for j in range(n_sess)]
+    for k in range(n_scans):
+        offs = np.stack([synth.candidate_offsets(70 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        pts = [rps[j].points[k][: P - 7 * j] for j in range(n_sess)]  # every session its own point count
+        res = b.update(pts, np.stack([rps[j].odometry[k] for j in range(n_sess)]), offs)
+        for j in range(n_sess):
+            os_[j].update(pts[j], rps[j].odometry[k], offs[j])
+            assert np.array_equal(res[j].pose, os_[j].pose), (k, j)
+            if k >= 5:
+                assert (res[j].distance, res[j].index) == (os_[j].last_distance, os_[j].last_index), (k, j)
+    sums = b.map_checksums()
+    for j in range(n_sess):
+        assert int(sums[j]) == sn.host_map_checksum(np.array(os_[j].map.pixels), size)
+    b.close()
+
+
+def test_slab_batch_replay_shared_log_philox():
+    """Parameter sweep in production mode: one shared device-resident log, per-session seeds and sigmas, on-device Philox
+    candidates sorted per session; equal to the oracle fed the host twin's deviates."""
+    n_sess, n_scans, P, size, phys, iters, threads = 4, 14, 180, 200, 40.0, 80, 4
+    rp = synth.make_replay(n_scans, P, phys, seed=9)
+    seeds = [11, 22, 33, 44]
+    sxy = [0.05, 0.1, 0.15, 0.2]
+    sth = [0.05, 0.1, 0.17, 0.25]
+    b = sn.Batch(n_sess, phys, size, rp.odometry[0], sxy, sth, iters, threads, max_points=P, seeds=seeds, flags=SLAB)
+    log = sn.ScanLog(n_scans, P, n_offsets=0)
+    for k in range(n_scans):
+        log.set(k, rp.points[k], rp.odometry[k])
+    log.upload()
+    b.replay(log, 0, 6)
+    res = b.replay(log, 6, n_scans - 6)
+    for j in range(n_sess):
+        o = orc.Processor(phys, size, rp.odometry[0], sxy[j], sth[j], iters, threads)
+        for k in range(n_scans):
+            o.update(rp.points[k], rp.odometry[k], sn.philox_offsets(seeds[j], k, iters * threads, sxy[j], sth[j]))
+        assert np.array_equal(res[j].pose, o.pose) and (res[j].distance, res[j].index) == (o.last_distance, o.last_index)
+        assert np.array_equal(b.map_download(j), np.array(o.map.pixels))
+    log.close()
+    b.close()
