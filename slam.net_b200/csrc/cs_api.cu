@@ -223,7 +223,7 @@ double max_range_of(const float* points, int n) {
 // Experiment knobs (environment, read once): CS_TUNE_SEARCH_WARPS (2/4/8), CS_TUNE_RING_SPAN, CS_TUNE_RING_THREADS.
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
-  int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0;
+  int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -235,6 +235,7 @@ struct Tune {
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
     ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
+    ring_blocks_per_sm = geti("CS_TUNE_RING_BLOCKS_PER_SM");  // resident blocks per SM the one-session rings grid is capped at
   }
 };
 const Tune& tune() { static Tune t; return t; }
@@ -485,7 +486,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.ring_slot_bits = dynamic ? CS_RING_MAX_SLOT_BITS : 11;
     if (tune().ring_slot_bits >= 8 && tune().ring_slot_bits <= CS_RING_MAX_SLOT_BITS) a.ring_slot_bits = tune().ring_slot_bits;
     int blocks = (rings + span - 1) / span;
-    if (dynamic && blocks > 2 * c.num_sms) blocks = 2 * c.num_sms;
+    const int per_sm = tune().ring_blocks_per_sm > 0 ? tune().ring_blocks_per_sm : 2;
+    if (dynamic && blocks > per_sm * c.num_sms) blocks = per_sm * c.num_sms;
     // the first blocks also prepare the rays, 128 each (one warp per SM sub-partition: the preparation is a
     // latency chain, not throughput); big scans use bigger groups so that at most 64 blocks prepare
     int group = (((n_points + 63) / 64) + 31) / 32 * 32;
