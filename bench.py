@@ -497,6 +497,22 @@ def main():
         e2e_s = time.perf_counter() - t0
         final_pose = proc.get_pose()
 
+        # ---- the same call in production mode: no candidate table, the deviates are generated on the device (Philox);
+        # only the scan is uploaded.  Reported next to e2e (which is the verification mode the parity claim is made in).
+        Kp = min(Ke, 200)
+        latp = np.zeros(Kp)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Kp):
+            ta = time.perf_counter()
+            st = L.cs_update(proc._h, pts_p[i], P, odo_p[i], None, C.byref(res))
+            latp[i] = time.perf_counter() - ta
+            if st != 0:
+                N.check(st, proc._h)
+        proc.sync()
+        barrier()
+        prod_s = time.perf_counter() - t0
+
     # ---- reduce over ranks: max time, summed work
     t_all = torch.tensor([total_ms, e2e_s * 1e3, warm_ms_per_step], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -561,6 +577,11 @@ def main():
                         "scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3),
                                                     "p99": float(np.percentile(lat, 99) * 1e3)}},
                 "gpu_launches": int(launches),
+                "e2e_production_mode": {"value": lookups_per_step * Kp / prod_s, "unit": "lookups/s", "ms_per_step": prod_s / Kp * 1e3,
+                                        "h2d_bytes_per_step": 64 + 8 * P, "d2h_bytes_per_step": 32, "steps": Kp,
+                                        "api": "cs_update(cand_offsets = NULL): on-device Philox candidates, rank 0",
+                                        "scan_to_pose_latency_ms": {"p50": float(np.percentile(latp, 50) * 1e3),
+                                                                    "p99": float(np.percentile(latp, 99) * 1e3)}},
                 "replay_l2_warm": {"ms_per_step": warm_ms_max, "value": world * lookups_per_step / (warm_ms_max * 1e-3),
                                    "note": "same replay without L2 flushes, %d scans back to back" % W},
                 "roofline": roofline,

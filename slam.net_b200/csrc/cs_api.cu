@@ -224,13 +224,14 @@ double max_range_of(const float* points, int n) {
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0;
-  int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0;
+  int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
     search2 = geti("CS_TUNE_SEARCH2");          // -1: never use the slab search, 0: built-in rule
     s2_points = geti("CS_TUNE_S2_POINTS");      // points per cluster
     s2_threads = geti("CS_TUNE_S2_THREADS");    // candidates per slab
+    s2_sort_one_block = geti("CS_TUNE_S2_SORT_ONE_BLOCK");  // 1: sort generated candidates with one block whenever they fit
     s2_min_cand = geti("CS_TUNE_S2_MIN_CAND");  // fewest candidates the slab search is used for
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
@@ -424,7 +425,11 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_scale = c.hs->scale;
     a.s2_sigma_xy = c.hs->sigma_xy;
     a.s2_sigma_theta = c.hs->sigma_theta;
-    if (a.cand_count <= CS_SORT_THREADS * CS_SORT_REG) {
+    // one block sorts a table of up to 8192 candidates out of its registers; generated (Philox) candidates are spread over
+    // the SMs, one per thread, as soon as there are more than one block's threads of them (batches: one block per session)
+    const bool one_block = a.cand_count <= CS_SORT_THREADS * CS_SORT_REG &&
+                           (a.cand_mode != CS_CAND_PHILOX || a.cand_count <= CS_SORT_THREADS || c.n_sessions > 1 || tune().s2_sort_one_block > 0);
+    if (one_block) {
       e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>, dim3(1, (unsigned)c.n_sessions),
                      dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
       if (e != cudaSuccess) return e;
