@@ -1206,6 +1206,24 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
   const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
+  const int nrounds = (n + round_cap - 1) / round_cap;
+  bool rays_resident = false;
+  int bmax[CS_RING_RPT];
+#pragma unroll
+  for (int j = 0; j < CS_RING_RPT; j++) bmax[j] = -1;
+  if (nrounds == 1) {
+    // The whole scan fits one round: its rays go to shared memory now, in the same L2 round trip as the per-batch maxima
+    // below instead of one trip later.  (Written during this kernel by the preparing blocks and not read by anybody
+    // before their count was seen — L1 is invalidated at kernel start — so the default L1-allocating load is coherent,
+    // and the blocks of one SM share one L2 fetch of lines that every block of the grid wants at the same moment.)
+    for (int i = tid; i < n; i += nthreads) s_rays[i] = rays[i];
+#pragma unroll
+    for (int j = 0; j < CS_RING_RPT; j++) {
+      const int bu = warp * CS_RING_RPT + j;
+      bmax[j] = (bu * 32 < n) ? batch_max[bu] : -1;
+    }
+    rays_resident = true;
+  }
   {  // max_ring = largest dxc of a valid ray (-1: nothing to draw), from the per-batch maxima
     int m = -1;
     for (int i = tid; i < (n + 31) / 32; i += nthreads) m = max(m, batch_max[i]);
@@ -1218,13 +1236,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // session alone (a.ring_dynamic) the grid is at most one resident wave and every further unit is drawn from a
   // ticket counter in ascending ring order, so the dense inner rings start first and the blocks stay busy until the
   // rings run out.  In a batch of sessions every block owns exactly one unit.
-  const int nrounds = (n + round_cap - 1) / round_cap;
   unsigned* ticket = &S.ring_ticket[a.step_id & 1u];
   __shared__ int sh_next_unit;
-  bool rays_resident = false;
-  int bmax[CS_RING_RPT];
-#pragma unroll
-  for (int j = 0; j < CS_RING_RPT; j++) bmax[j] = -1;
   for (int unit = blockIdx.x;;) {
   const int k_begin = unit * span;
   if (k_begin > max_ring) break;
