@@ -314,6 +314,21 @@ def parallel_monte_carlo_search(hm, points, search_pose, offsets, iterations, th
     return best_pose, best_distance
 
 
+def scan_segments_to_cloud(segments, odometry_pose):
+    """:187-207.  segments: iterable of (pose (x, y, theta), rays [(angle, radius), ...]); returns the cloud's points as an
+    (n, 2) float32 array in the order cloud.Points.Add (:203) builds them."""
+    odo = tuple(F(v) for v in odometry_pose)
+    points = []
+    for seg_pose, rays in segments:  # :191
+        pose = tuple(F(seg_pose[k]) - odo[k] for k in range(3))  # :194 Vector3 subtraction, per component
+        for angle, radius in rays:  # :196
+            a = F(angle) + pose[2]
+            x = pose[0] + F(radius) * cosf(a)  # :200
+            y = pose[1] + F(radius) * sinf(a)  # :201
+            points.append((x, y))
+    return np.array(points, dtype=np.float32).reshape(-1, 2)
+
+
 class ProcessorT:
     """ctor :119-162, Reset :167-175, Update :717-752"""
 
@@ -357,3 +372,11 @@ class ProcessorT:
         update_hole_map(self.HoleMap, points, self.Pose, self.HoleWidth, self.Quality)
         if self.ObstacleMap is not None:
             update_obstacle_map(self.ObstacleMap, points, self.Pose, self.MaxObstacleHits)  # :751
+
+    def UpdateSegments(self, segments, offsets):
+        """Update(List<ScanSegment>) as declared (:717-723): odoPose = segments.Last().Pose, cloud from ScanSegmentsToCloud."""
+        segments = list(segments)
+        if not segments:
+            raise ValueError("Sequence contains no elements")  # segments.Last() (:719)
+        odo = segments[-1][0]
+        self.Update(scan_segments_to_cloud(segments, odo), odo, offsets)
