@@ -90,6 +90,13 @@ struct cs_processor {
   size_t stage_bytes = 0;
   uint8_t* h_stage = nullptr;  // pinned
   uint8_t* d_stage = nullptr;
+  // cs_update's staging runs ahead of the stream: the H2D copy of scan k goes through a copy stream into the buffer scan
+  // k-1 is NOT using (d_stage / d_stage_b alternate), so it overlaps the integration of scan k-1 instead of queueing
+  // behind it; the main stream only waits for the copy's event.  ev_stage_free[i]: last step that reads buffer i is enqueued.
+  uint8_t* d_stage_b = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_copy = nullptr, ev_stage_free[2] = {nullptr, nullptr};
+  int stage_flip = 0, stage_cur = 0;
 
   // mapped result slot
   uint8_t* h_slot = nullptr;  // pinned+mapped: CsDevResult at 0, seq flag at 64
@@ -224,7 +231,7 @@ double max_range_of(const float* points, int n) {
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0;
-  int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0;
+  int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -232,6 +239,7 @@ struct Tune {
     s2_points = geti("CS_TUNE_S2_POINTS");      // points per cluster
     s2_threads = geti("CS_TUNE_S2_THREADS");    // candidates per slab
     s2_sort_one_block = geti("CS_TUNE_S2_SORT_ONE_BLOCK");  // 1: sort generated candidates with one block whenever they fit
+    copy_stream = geti("CS_TUNE_COPY_STREAM");  // -1: cs_update stages its inputs on the main stream
     s2_min_cand = geti("CS_TUNE_S2_MIN_CAND");  // fewest candidates the slab search is used for
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
@@ -554,6 +562,7 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
     CS_CUDA(h, launch_obstacle_update(c.stream, h->d_sess, h->d_obst, h->ho, a, n_points, 1, c.num_sms, &h->launches));
   }
   if (c.ev_done) cudaEventRecord(h->tm.ev[ev_base + 2], h->stream);
+  if (h->copy_stream) CS_CUDA(h, cudaEventRecord(h->ev_stage_free[h->stage_cur], h->stream));  // this step's readers of its staging buffer are enqueued
   return CS_OK;
 }
 
@@ -711,6 +720,12 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_cloud, (size_t)max_points * sizeof(float2)));
   CS_CREATE_CUDA(cudaHostAlloc(&h->h_stage, h->stage_bytes, cudaHostAllocDefault));
   CS_CREATE_CUDA(cudaMalloc(&h->d_stage, h->stage_bytes));
+  if (tune().copy_stream >= 0) {
+    CS_CREATE_CUDA(cudaMalloc(&h->d_stage_b, h->stage_bytes));
+    CS_CREATE_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CS_CREATE_CUDA(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    for (auto& e : h->ev_stage_free) CS_CREATE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   CS_CREATE_CUDA(cudaHostAlloc(&h->h_slot, 128, cudaHostAllocMapped));
   CS_CREATE_CUDA(cudaHostGetDevicePointer((void**)&h->d_slot, h->h_slot, 0));
   memset(h->h_slot, 0, 128);
@@ -817,6 +832,11 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_s2_acc);
   cudaFree(h->d_s2_ghist);
   cudaFree(h->d_stage);
+  cudaFree(h->d_stage_b);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
+  for (auto& e : h->ev_stage_free)
+    if (e) cudaEventDestroy(e);
   cudaFree(h->ho.pixels);
   cudaFree(h->ho.no_hit);
   cudaFree(h->ho.touched);
@@ -992,6 +1012,7 @@ cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, cons
   if (!cand_poses && n_cand != h->n_cand) return fail(h, CS_ERR_INVALID_ARGUMENT, "Philox mode evaluates exactly T*I candidates");
 
   StagePlan sp = plan_stage(n_points, n_cand, cand_cs != nullptr);
+  h->stage_cur = 0;
   CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h->h_stage);
   memset(hdr, 0, kHdrBytes);
   hdr->odo[0] = search_pose[0]; hdr->odo[1] = search_pose[1]; hdr->odo[2] = search_pose[2];
@@ -1049,6 +1070,7 @@ cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, c
   // flag, which the device writes after that call's H2D copy completed; the device-side block is
   // protected by stream order.
   StagePlan sp = plan_stage(n_points, 0, false);
+  h->stage_cur = 0;
   CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h->h_stage);
   memset(hdr, 0, kHdrBytes);
   hdr->odo[0] = pose[0]; hdr->odo[1] = pose[1]; hdr->odo[2] = pose[2];
@@ -1149,9 +1171,22 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   if (with_offsets) memcpy(h->h_stage + sp.off_cand, cand_offsets, (size_t)h->n_cand * 12);
 
   if (timing) cudaEventRecord(h->tm.ev[0], h->stream);
-  CS_CUDA(h, cudaMemcpyAsync(h->d_stage, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+  uint8_t* d_base = h->d_stage;
+  if (h->copy_stream) {
+    // run ahead of the stream: copy into the buffer the scan in flight is not reading, behind nothing but that buffer's
+    // last readers (two scans ago); the main stream picks the copy up through its event
+    h->stage_cur = (h->stage_flip ^= 1);
+    d_base = h->stage_cur ? h->d_stage_b : h->d_stage;
+    CS_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->ev_stage_free[h->stage_cur], 0));
+    CS_CUDA(h, cudaMemcpyAsync(d_base, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->copy_stream));
+    CS_CUDA(h, cudaEventRecord(h->ev_copy, h->copy_stream));
+    CS_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_copy, 0));
+  } else {
+    h->stage_cur = 0;
+    CS_CUDA(h, cudaMemcpyAsync(d_base, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
+  }
   if (seg) {  // ScanSegmentsToCloud (:723) on the device; the step's first kernel must not start before it is complete
-    cs_status cst = launch_cloud(h, h->d_stage + sp.off_points, h->d_stage + off_first, h->d_stage + off_poses, n_points,
+    cs_status cst = launch_cloud(h, d_base + sp.off_points, d_base + off_first, d_base + off_poses, n_points,
                                  seg->n_segments, odometry_pose);
     if (cst != CS_OK) return cst;
     g_next_launch_plain = true;
@@ -1159,9 +1194,9 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   if (timing) cudaEventRecord(h->tm.ev[1], h->stream);
 
   CsStepArgs a{};
-  a.hdr = reinterpret_cast<const CsStepHeader*>(h->d_stage);
-  a.points = seg ? h->d_cloud : reinterpret_cast<const float2*>(h->d_stage + sp.off_points);
-  a.cand = with_offsets ? reinterpret_cast<const float*>(h->d_stage + sp.off_cand) : nullptr;
+  a.hdr = reinterpret_cast<const CsStepHeader*>(d_base);
+  a.points = seg ? h->d_cloud : reinterpret_cast<const float2*>(d_base + sp.off_points);
+  a.cand = with_offsets ? reinterpret_cast<const float*>(d_base + sp.off_cand) : nullptr;
   a.result = reinterpret_cast<CsDevResult*>(h->d_slot);
   a.seq_flag = reinterpret_cast<volatile unsigned*>(h->d_slot + 64);
   a.seq_value = ++h->seq;
