@@ -268,3 +268,28 @@ def test_slab_batch_replay_shared_log_philox():
         assert np.array_equal(b.map_download(j), np.array(o.map.pixels))
     log.close()
     b.close()
+
+
+def test_slab_cfg2_back_to_back_equals_scan_by_scan():
+    """cfg2 geometry: 150 scans queued back to back (programmatic dependent launches: the next scan's sort and search
+    prologue run while the previous scan is still being integrated, map lines cached in L1 by one search are rewritten by
+    the integration before the next search) must end exactly where the same scans end when every one is waited for."""
+    n = 150
+    rp = synth.make_replay(n, 1024, 40.0, seed=91)
+    log = sn.ScanLog(n, 1024, n_offsets=4096)
+    for k in range(n):
+        log.set(k, rp.points[k], rp.odometry[k], synth.candidate_offsets(91, k, 4096, 0.1, 0.17))
+    log.upload()
+    out = []
+    for chunk in (n, 1):
+        p = sn.Processor(40.0, 2048, rp.odometry[0], 0.1, 0.17, 1024, 4, max_points=1024)
+        assert p.search_plan(1024)["slab"]
+        res = []
+        for first in range(0, n, chunk):
+            res += p.replay(log, first, chunk)  # want_results: waits for the chunk
+        out.append((res, p.map_checksum(), p.get_pose()))
+        p.close()
+    (ra, ca, pa), (rb, cb, pb) = out
+    assert ca == cb and np.array_equal(pa, pb)
+    assert all(np.array_equal(x.pose, y.pose) and (x.distance, x.index) == (y.distance, y.index) for x, y in zip(ra, rb))
+    log.close()
