@@ -230,7 +230,7 @@ double max_range_of(const float* points, int n) {
 // Experiment knobs (environment, read once): CS_TUNE_SEARCH_WARPS (2/4/8), CS_TUNE_RING_SPAN, CS_TUNE_RING_THREADS.
 // Unset = the built-in choice.  They change launch shapes only, never results.
 struct Tune {
-  int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0;
+  int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
@@ -244,6 +244,7 @@ struct Tune {
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
     ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
+    ring_small = geti("CS_TUNE_RING_SMALL");  // -1: batches use the 512-thread instance of the rings kernel too
     ring_blocks_per_sm = geti("CS_TUNE_RING_BLOCKS_PER_SM");  // resident blocks per SM the one-session rings grid is capped at
   }
 };
@@ -486,9 +487,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (threads > CS_RING_MAX_THREADS) threads = CS_RING_MAX_THREADS;
     if (rings < 1) rings = 1;
     // One session alone: a grid of at most one resident wave (2 blocks per SM) whose blocks draw work units of
-    // `span` rings from a ticket counter.  A batch of sessions: one unit of 32 rings per block, grid.y = sessions (measured on cfg5: 8 -> 32 rings per unit and a 2048-entry slot table take a step from 8.6 to 5.1 ms).
+    // `span` rings from a ticket counter.  A batch of sessions: one unit of 64 rings per block, grid.y = sessions (measured on cfg5: 8 -> 64 rings per unit, a 2048-entry slot table and the small-block instance of the kernel take the rings from 4.8 to 2.8 ms per step).
     const bool dynamic = c.n_sessions == 1;
-    int span = dynamic ? 1 : 32;
+    int span = dynamic ? 1 : 64;
     if (tune().ring_span > 0) span = tune().ring_span;
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
@@ -508,8 +509,10 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.prep_group = group;
     const int nprep = (n_points + group - 1) / group;
     if (blocks < nprep) blocks = nprep;
+    const bool small_rings = !dynamic && threads <= CS_RING_SMALL_THREADS && tune().ring_small >= 0;
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(cs_rings_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
+      e = launch_pdl(small_rings ? cs_rings_kernel<decltype(T)::value, true> : cs_rings_kernel<decltype(T)::value, false>,
+                     dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
                      CS_RING_SMEM(threads, a.ring_slot_bits), c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
@@ -700,9 +703,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, (size_t)kRayCopies * h->batch_stride * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_prep_words, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaMemset(h->d_prep_words, 0, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
-  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
-  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
@@ -1994,9 +1997,9 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
   if (!ok) {
     cudaError_t e = cudaGetLastError();

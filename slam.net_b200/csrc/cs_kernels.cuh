@@ -1104,8 +1104,11 @@ __device__ __forceinline__ bool cs_ring_visit(const CsRay& r, int k, int x1, int
   return true;
 }
 
-template <bool TILED>
-__global__ void __launch_bounds__(CS_RING_MAX_THREADS, 2)
+// SMALL = true: the instance for blocks of at most CS_RING_SMALL_THREADS threads (the sessions of a batch, short scans):
+// compiled for more resident blocks per SM (fewer registers per thread) than the 512-thread instance of a session alone.
+#define CS_RING_SMALL_THREADS 256
+template <bool TILED, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? CS_RING_SMALL_THREADS : CS_RING_MAX_THREADS, SMALL ? 5 : 2)
 cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   extern __shared__ int4 cs_ring_smem[];
 
