@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — CoreSLAM scan-to-map hot path on B200: scan-point map lookups/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5]
 
 A *step* is one CoreSLAMProcessor.Update of the replay: Monte-Carlo pose search over C+1 candidate
 poses x P scan points (the lookups) followed by the HoleMap integration of the same scan.  The N=1
@@ -43,6 +43,9 @@ WORKLOADS = {
                  desc="CoreSLAM 360-point scans, 4x1000 search iterations, HoleMap 1600x1600 @2.5 cm"),
     "cfg2": dict(points=1024, threads=4, iters=1024, size=2048, phys=40.0,
                  desc="CoreSLAM synthetic replay, 4096 candidates x 1024-point scans, HoleMap 2048x2048, verification mode"),
+    "cfg3": dict(points=8192, threads=1, iters=1, size=4096, phys=40.96,
+                 desc="HoleMap integration stress: 8192-ray scans at 1 cm into a 4096x4096 map (UpdateHoleMap only, no search), "
+                      "map checksum bit-exact vs the oracle"),
     "cfg4": dict(points=1024, threads=64, iters=1024, size=8192, phys=81.92,
                  desc="Large-map HBM regime: HoleMap 8192x8192 @1 cm (128 MB), 65536 candidates x 1024-point scans, candidates split "
                       "across the GPUs with one 8-byte arg-min exchange (NCCL MIN all-reduce) per scan"),
@@ -297,6 +300,188 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
     return 0
 
 
+def run_cpu_cfg3(wl, rp, first, count, min_s=10.0):
+    """The oracle's UpdateHoleMap (serial, like the reference: CoreSLAMProcessor.cs:515-533) over scans [0, first+count) at their
+    odometry poses; scans [first, first+count) are timed, then integrated again back and forth until the sample holds `min_s`
+    seconds.  Returns (visits, seconds, calls timed, checksum of the map after the first pass)."""
+    from oracle import oracle as orc
+    import slam.net_b200 as sn
+    S = wl["size"]
+    m = orc.HoleMap(S, wl["phys"])
+    m.fill(32750)
+
+    def one(k):
+        pose = rp.odometry[k].copy()
+        pose[2] = orc.normalize_angle(float(pose[2]))  # :746
+        ta = time.perf_counter()
+        v = orc.update_hole_map(m, rp.points[k], pose, 0.6, 50)
+        return v, time.perf_counter() - ta
+
+    visits, secs, done = 0, 0.0, 0
+    for k in range(first + count):
+        v, dt = one(k)
+        if k >= first:
+            visits, secs, done = visits + v, secs + dt, done + 1
+    checksum = int(sn.host_map_checksum(np.array(m.pixels), S))
+    k, step = first + count - 1, -1
+    while secs < min_s and done < 100000 and count > 1:
+        v, dt = one(k)
+        visits, secs, done = visits + v, secs + dt, done + 1
+        if not first <= k + step < first + count:
+            step = -step
+        k += step
+    return visits, secs, done, checksum
+
+
+def run_cfg3(args, wl, config, rank, world, local, K, W):
+    """configs[2]: the integration half alone.  A step = UpdateHoleMap (CoreSLAMProcessor.cs:496-534) of one 8192-ray scan
+    into the 4096x4096 map at the scan's odometry pose — `Update` with the search gated off (PositionSearchBeginning out of
+    reach, :726-742), so the replay runs cs_setup_kernel + cs_rings_kernel only.  Metric: HoleMap cell visits/s (one visit =
+    one iteration of the draw loop :404-442 = one 2-byte read + one 2-byte write)."""
+    import torch
+    import torch.distributed as dist
+    import slam.net_b200 as sn
+    from slam.net_b200 import _native as N
+    from slam.net_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    P, S = wl["points"], wl["size"]
+    Kb = min(K, 100)
+    n_total = W + K + Kb + W + K
+    rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed + 7919 * rank)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        proc = sn.Processor(wl["phys"], S, rp.odometry[0], SIGMA_XY, SIGMA_THETA, 1, 1, device=local, max_points=P,
+                            seed=args.seed, stream=stream.cuda_stream)
+        proc.set_position_search_beginning(2 ** 31 - 1)  # map-only scans: newPose = odoPose (:740-743)
+        log = sn.ScanLog(n_total, P, n_offsets=0, device=local)
+        for k in range(n_total):
+            log.set(k, rp.points[k], rp.odometry[k])
+        log.upload()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        cur = 0
+        proc.replay(log, cur, W, want_results=False)
+        cur += W
+
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        sampler = ClockSampler(local)
+        launches0 = proc.launch_count()
+        barrier()
+        sampler.start()
+        wall0 = time.perf_counter()
+        for i in range(K):
+            flush.fill_(i & 0xFF)
+            ev0[i].record(stream)
+            proc.replay(log, cur + i, 1, want_results=False)
+            ev1[i].record(stream)
+        barrier()
+        wall_region = time.perf_counter() - wall0
+        clocks = sampler.stop()
+        launches = proc.launch_count() - launches0
+        total_ms = float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(K)))
+        cur += K
+        checksum_after_timed = int(proc.map_checksum())
+
+        # per-kernel pass: events around the rings kernel, visits counted by the device
+        proc.set_flags(N.FLAG_TIMING)
+        i_ms, visits = [], []
+        for i in range(Kb):
+            flush.fill_(i & 0xFF)
+            r = proc.replay(log, cur + i, 1, want_results=True)
+            i_ms.append(proc.timing().integrate_ms)
+            visits.append(r[0].visits)
+        proc.set_flags(0)
+        cur += Kb
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        proc.replay(log, cur, W, want_results=False)
+        e1.record(stream)
+        barrier()
+        warm_ms = e0.elapsed_time(e1) / W
+        cur += W
+
+        # e2e: cs_integrate through the C ABI, host points in, visit count out, wall clock
+        L = sn.lib()
+        fp = C.POINTER(C.c_float)
+        pts_p = [rp.points[cur + i].ctypes.data_as(fp) for i in range(K)]
+        pose_c = [np.ascontiguousarray(rp.odometry[cur + i]) for i in range(K)]
+        v64 = C.c_int64(0)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            st = L.cs_integrate(proc._h, pts_p[i], rp.points[cur + i].shape[0], pose_c[i].ctypes.data_as(fp), None, C.byref(v64))
+            if st != 0:
+                N.check(st, proc._h)
+        proc.sync()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+
+    mean_visits = float(np.mean(visits))
+    t_all = torch.tensor([total_ms, e2e_s * 1e3, warm_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    total_ms_max, e2e_ms_max, warm_ms_max = (float(x) for x in t_all.tolist())
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        launch_ms = float(np.mean(i_ms))
+        alg_bytes = 4.0 * mean_visits + 8.0 * P
+        achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
+        value = world * mean_visits * K / (total_ms_max * 1e-3)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu_visits, t_cpu, done, cpu_checksum = run_cpu_cfg3(wl, rp, W, K)
+            parity = bool(cpu_checksum == checksum_after_timed)
+            cpu = {"value": cpu_visits / t_cpu, "unit": "visits/s", "cores": 1, "kind": "port",
+                   "sample": "%d UpdateHoleMap calls (the %d timed scans of the same replay first, then the same scans again until >= 10 s), "
+                             "%.1f s, 1 thread (the reference integrates serially, CoreSLAMProcessor.cs:515-533)" % (done, K, t_cpu),
+                   "map_checksum_bit_exact_vs_gpu": parity}
+        line = {"metric": "HoleMap cell visits/sec", "value": value, "unit": "visits/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 ray set-up -> i32 closed-form walk -> u16 blend", "data": "synthetic",
+                "config": dict(config, candidates_per_scan=0, prime_scans=0, mode="integration only (search gated off)",
+                               l2="flushed (256 MB write) before every timed step",
+                               timing="per-step CUDA events on the launching stream, summed; max over ranks"),
+                "visits_per_step": mean_visits, "rays_per_s": value / mean_visits * P, "clocks": clocks,
+                "e2e": {"value": world * mean_visits * K / (e2e_ms_max * 1e-3), "unit": "visits/s", "h2d_bytes_per_step": 64 + 8 * P,
+                        "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms_max / K,
+                        "api": "cs_integrate (C ABI, host points, visit count read back)"},
+                "gpu_launches": int(launches),
+                "replay_l2_warm": {"ms_per_step": warm_ms_max, "value": world * mean_visits / (warm_ms_max * 1e-3),
+                                   "note": "same replay without L2 flushes, %d scans back to back (the 32 MB map stays in L2)" % W},
+                "roofline": {"bound": "hbm", "kernel": "cs_rings_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
+                             "note": "4 B (2 B read + 2 B write) per visited cell + the scan's points; per-cell ray order is kept, so the kernel "
+                                     "is a chain of per-ring phases (latency), not a stream"},
+                "cpu_baseline": cpu, "wall_s_timed_region": wall_region, "map_checksum": checksum_after_timed}
+        print(json.dumps(line))
+    proc.close()
+    log.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,6 +511,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        if args.workload == "cfg3":
+            from slam.net_b200 import synth
+            rp = synth.make_replay(W + K, P, wl["phys"], seed=args.seed)
+            visits, secs, done, _ = run_cpu_cfg3(wl, rp, W, K)
+            v = visits / secs
+            line = {"impl": "reference", "metric": "HoleMap cell visits/sec", "value": v, "unit": "visits/s", "n_gpus": args.gpus, "steps": K,
+                    "updates_timed": done, "warmup": W, "ms_per_step": secs / max(done, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32 ray set-up -> i32 walk -> u16 blend", "data": "synthetic",
+                    "config": dict(config, candidates_per_scan=0, prime_scans=0, mode="integration only (search gated off)"),
+                    "cpu_baseline": {"value": v, "unit": "visits/s", "cores": 1, "kind": "port",
+                                     "sample": "%d UpdateHoleMap calls over the %d requested scans (again back and forth until >= 10 s), %.1f s"
+                                               % (done, K, secs),
+                                     "note": "reference is C#/.NET (no runtime here): CPU oracle port; the reference integrates on one thread"},
+                    "e2e": {"value": v, "unit": "visits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            print(json.dumps(line))
+            return 0
         n_total = PRIME_SCANS + W + K
         rp, offs, n_cand = build_workload(wl, n_total, args.seed)
         first = PRIME_SCANS + W
@@ -343,6 +544,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if args.workload == "cfg3":
+        return run_cfg3(args, wl, config, rank, world, local, K, W)
     if args.workload in ("cfg4", "cfg5"):
         return run_sharded(args, wl, metric, config, rank, world, local, K, W)
 
