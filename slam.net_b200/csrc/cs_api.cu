@@ -207,6 +207,17 @@ StagePlan plan_stage(int n_points, int n_cand_floats3, bool with_cs) {
 }
 
 // Upper bound on the ring count of a scan: |rotated, scaled point| + half the hole width, plus rounding slack.
+// The 512-thread instances of the rings kernel use more dynamic shared memory than the default limit.
+cudaError_t rings_allow_shared_memory() {
+  const int one = (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS, 0);
+  const int two = (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS, 1);
+  cudaError_t e = cudaFuncSetAttribute(cs_rings_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_rings_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, one);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_rings_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_rings_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, two);
+  return e;
+}
+
 int rings_hint_of(int size, float scale, float hole_width, double max_range) {
   if (!(max_range == max_range) || max_range > 1e30) return size;
   double cells = max_range * (double)scale * 1.00001 + 0.5 * (double)hole_width * (double)scale + 4.0;
@@ -489,7 +500,10 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     // One session alone: a grid of at most one resident wave (2 blocks per SM) whose blocks draw work units of
     // `span` rings from a ticket counter.  A batch of sessions: one unit of 64 rings per block, grid.y = sessions (measured on cfg5: 8 -> 64 rings per unit, a 2048-entry slot table and the small-block instance of the kernel take the rings from 4.8 to 2.8 ms per step).
     const bool dynamic = c.n_sessions == 1;
-    int span = dynamic ? 1 : 64;
+    // scans of several rounds (more rays than 2 x threads): two rings per unit, so that a round's rays serve two rings and
+    // the second ring's evaluation hides the first one's map loads (cfg3: 208 -> 183 us; 4 and more rings per unit lose to imbalance)
+    const bool multi_round = n_points > threads * CS_RING_RPT;
+    int span = dynamic ? (multi_round ? 2 : 1) : 64;
     if (tune().ring_span > 0) span = tune().ring_span;
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
@@ -509,11 +523,13 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.prep_group = group;
     const int nprep = (n_points + group - 1) / group;
     if (blocks < nprep) blocks = nprep;
-    const bool small_rings = !dynamic && threads <= CS_RING_SMALL_THREADS && tune().ring_small >= 0;
+    const bool small_rings = !dynamic && !multi_round && threads <= CS_RING_SMALL_THREADS && tune().ring_small >= 0;
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(small_rings ? cs_rings_kernel<decltype(T)::value, true> : cs_rings_kernel<decltype(T)::value, false>,
+      constexpr bool tiled = decltype(T)::value;
+      e = launch_pdl(small_rings ? cs_rings_kernel<tiled, true, false>
+                                 : (multi_round ? cs_rings_kernel<tiled, false, true> : cs_rings_kernel<tiled, false, false>),
                      dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(threads),
-                     CS_RING_SMEM(threads, a.ring_slot_bits), c.stream, c.d_sess, a);
+                     CS_RING_SMEM(threads, a.ring_slot_bits, multi_round), c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -703,10 +719,7 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_batch_max, (size_t)kRayCopies * h->batch_stride * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_prep_words, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaMemset(h->d_prep_words, 0, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
-  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
-  CS_CREATE_CUDA(cudaFuncSetAttribute(cs_rings_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)));
+  CS_CREATE_CUDA(rings_allow_shared_memory());
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
@@ -1997,10 +2010,7 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
-  ok = ok && cudaFuncSetAttribute(cs_rings_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)CS_RING_SMEM(CS_RING_MAX_THREADS, CS_RING_MAX_SLOT_BITS)) == cudaSuccess;
+  ok = ok && rings_allow_shared_memory() == cudaSuccess;
   if (!ok) {
     cudaError_t e = cudaGetLastError();
     bfail(nullptr, e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "cs_batch_create: %s", cudaGetErrorString(e));

@@ -1056,7 +1056,16 @@ cs_setup_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 #define CS_RING_MAX_SLOT_BITS 13        // largest slot table: 8192 entries, rings up to k = 1024 in one window
 #define CS_RING_MAX_SPAN 256
 // dynamic shared memory for a block of `threads` threads
-#define CS_RING_SMEM(threads, slot_bits) (((size_t)8 << (slot_bits)) + (size_t)(threads) * CS_RING_RPT * (16 + 4))
+// (prefetch = 1: scans of more than one round keep a second ray buffer, filled by cp.async while the current round is drawn)
+#define CS_RING_SMEM(threads, slot_bits, prefetch) \
+  (((size_t)8 << (slot_bits)) + (size_t)(threads) * CS_RING_RPT * (16 + 4 + ((prefetch) ? 16 : 0)))
+#define CS_RING_MAX_ROUNDS 64           // rounds with their own "largest ring" entry; later rounds share the last entry
+
+__device__ __forceinline__ void cs_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cs_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ int cs_blend(int old, int pixval, int alpha) {
   return (int)(uint16_t)(((256 - alpha) * old + alpha * pixval) >> 8);  // :431
@@ -1107,7 +1116,9 @@ __device__ __forceinline__ bool cs_ring_visit(const CsRay& r, int k, int x1, int
 // SMALL = true: the instance for blocks of at most CS_RING_SMALL_THREADS threads (the sessions of a batch, short scans):
 // compiled for more resident blocks per SM (fewer registers per thread) than the 512-thread instance of a session alone.
 #define CS_RING_SMALL_THREADS 256
-template <bool TILED, bool SMALL>
+// MULTI = true: the instance for scans of more rays than one round holds (2 x threads): rounds that do not reach a ring are
+// skipped and the next round's rays are prefetched; the other instances are compiled without any of it (n <= one round).
+template <bool TILED, bool SMALL, bool MULTI>
 __global__ void __launch_bounds__(SMALL ? CS_RING_SMALL_THREADS : CS_RING_MAX_THREADS, SMALL ? 5 : 2)
 cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   extern __shared__ int4 cs_ring_smem[];
@@ -1124,6 +1135,7 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   unsigned* s_c = s_w + n_slots;                                         // slot -> contested visits | mixed marks << 16; later: hand-off word
   int4* s_rays = reinterpret_cast<int4*>(s_c + n_slots);                 // this round's packed rays
   int* s_lpv = reinterpret_cast<int*>(s_rays + round_cap);               // pixvals of the visits of mixed cells
+  int4* s_rays2 = reinterpret_cast<int4*>(s_lpv + round_cap);            // second ray buffer (scans of several rounds only)
   {  // the counters start at zero; done before the dependency wait, so it overlaps the previous kernel's tail
     uint4* c4 = reinterpret_cast<uint4*>(s_c);
     for (int i = tid; i < n_slots / 4; i += nthreads) c4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -1196,6 +1208,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     }
   }
   __shared__ int sh_max_ring;
+  __shared__ int sh_round_max[CS_RING_MAX_ROUNDS];  // largest dxc of the rays of round r: later rings skip the round
+  if (MULTI && tid < CS_RING_MAX_ROUNDS) sh_round_max[tid] = -1;
   if (tid == 0) {
     sh_max_ring = -1;
     volatile unsigned long long* pw = prep_words + (size_t)copy * 16;
@@ -1209,7 +1223,7 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
   const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
-  const int nrounds = (n + round_cap - 1) / round_cap;
+  const int nrounds = MULTI ? (n + round_cap - 1) / round_cap : 1;
   bool rays_resident = false;
   int bmax[CS_RING_RPT];
 #pragma unroll
@@ -1229,7 +1243,11 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   }
   {  // max_ring = largest dxc of a valid ray (-1: nothing to draw), from the per-batch maxima
     int m = -1;
-    for (int i = tid; i < (n + 31) / 32; i += nthreads) m = max(m, batch_max[i]);
+    for (int i = tid; i < (n + 31) / 32; i += nthreads) {
+      const int bm = batch_max[i];
+      m = max(m, bm);
+      if (MULTI && nrounds > 1 && bm >= 0) atomicMax(&sh_round_max[min((i * 32) / round_cap, CS_RING_MAX_ROUNDS - 1)], bm);
+    }
     m = __reduce_max_sync(0xffffffffu, m);
     if (lane == 0 && m >= 0) atomicMax(&sh_max_ring, m);
   }
@@ -1241,6 +1259,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // rings run out.  In a batch of sessions every block owns exactly one unit.
   unsigned* ticket = &S.ring_ticket[a.step_id & 1u];
   __shared__ int sh_next_unit;
+  int pf_round0 = -1;   // round whose rays are in flight into the other ray buffer
+  int cur_round0 = -1;  // round whose rays the current buffer holds (scans of several rounds)
   for (int unit = blockIdx.x;;) {
   const int k_begin = unit * span;
   if (k_begin > max_ring) break;
@@ -1250,20 +1270,50 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
   for (int round0 = 0; round0 < n; round0 += round_cap) {
     const int round_n = min(round_cap, n - round0);
-    if (nrounds > 1 || !rays_resident) {
-      if (rays_resident) __syncthreads();  // previous round: stores done, shared arrays free
-      // Written during this kernel by the preparing blocks, and not read by anybody before their count was seen
-      // (L1 is invalidated at kernel start), so the default L1-allocating load is coherent here — and the blocks
-      // of one SM share one L2 fetch of lines that every block of the grid wants at the same moment.
-      for (int i = tid; i < round_n; i += nthreads) s_rays[i] = rays[round0 + i];
+    if (MULTI && nrounds > 1) {
+      // Scans of several rounds.  A round none of whose rays reaches this unit's first ring is skipped (block-uniform).
+      // The rays of the next round to be drawn are fetched with cp.async into the second buffer while this round is
+      // drawn, so that only the unit's first round waits for its rays.  (The rays were written during this kernel by the
+      // preparing blocks and are not read by anybody before their count was seen — L1 is invalidated at kernel start —
+      // so L1-allocating loads are coherent, and the blocks of one SM share one L2 fetch.)
+      if (sh_round_max[min(round0 / round_cap, CS_RING_MAX_ROUNDS - 1)] < k_begin) continue;
+      if (cur_round0 != round0) {  // (a unit of one live round often follows another one of the same round)
+        if (pf_round0 == round0) {
+          cs_cp_async_wait_all();
+          int4* t = s_rays; s_rays = s_rays2; s_rays2 = t;
+        } else {
+          if (rays_resident) __syncthreads();  // previous round: the current buffer is free
+          for (int i = tid; i < round_n; i += nthreads) s_rays[i] = rays[round0 + i];
+        }
 #pragma unroll
-      for (int j = 0; j < CS_RING_RPT; j++) {
-        const int bu = warp * CS_RING_RPT + j;
-        bmax[j] = (bu * 32 < round_n) ? batch_max[(round0 >> 5) + bu] : -1;
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          const int bu = warp * CS_RING_RPT + j;
+          bmax[j] = (bu * 32 < round_n) ? batch_max[(round0 >> 5) + bu] : -1;
+        }
+        cur_round0 = round0;
       }
+      pf_round0 = -1;  // whatever was fetched is either current now or was not wanted
       rays_resident = true;
+      __syncthreads();  // everybody's part of the buffer has landed; the previous round's reads of the other one are over
+      int next0 = round0 + round_cap;
+      while (next0 < n && sh_round_max[min(next0 / round_cap, CS_RING_MAX_ROUNDS - 1)] < k_begin) next0 += round_cap;
+      if (next0 < n) {
+        const int next_n = min(round_cap, n - next0);
+        for (int i = tid; i < next_n; i += nthreads) cs_cp_async16(s_rays2 + i, rays + next0 + i);
+        pf_round0 = next0;
+      }
+    } else {
+      if (!rays_resident) {
+        for (int i = tid; i < round_n; i += nthreads) s_rays[i] = rays[round0 + i];
+#pragma unroll
+        for (int j = 0; j < CS_RING_RPT; j++) {
+          const int bu = warp * CS_RING_RPT + j;
+          bmax[j] = (bu * 32 < round_n) ? batch_max[(round0 >> 5) + bu] : -1;
+        }
+        rays_resident = true;
+      }
+      __syncthreads();
     }
-    __syncthreads();
     if (tl && round0 == 0 && unit == (int)blockIdx.x) tl[5] = cs_globaltimer();
 
     // read-modify-writes whose load is in flight (see 3a)
