@@ -240,42 +240,67 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
             h2d, d2h = 64 + 8 * P, 32
             proc.close()
         else:
-            n_sessions = wl["sessions"]
+            n_sessions = args.sessions if args.sessions > 0 else wl["sessions"]
             mine = par.session_shard(n_sessions, world, rank)
-            # parameter grid over sigma_xy, sigma_theta, HoleWidth, Quality, seed
-            sxy = np.array([0.05 + 0.025 * (s % 5) for s in mine], dtype=np.float32)
-            sth = np.array([0.0873 + 0.0436 * ((s // 5) % 4) for s in mine], dtype=np.float32)
-            batch = sn.Batch(len(mine), wl["phys"], wl["size"], rp.odometry[0], sxy, sth, wl["iters"], wl["threads"], device=local,
-                             max_points=P, seeds=[args.seed + s for s in mine], stream=stream.cuda_stream)
-            for j, s in enumerate(mine):
-                batch.set_params(j, 30 + 20 * ((s // 20) % 6), 0.4 + 0.2 * ((s // 120) % 4))
+            # The rank's sessions run as `n_sub` independent batches on their own streams (sessions share nothing): with few
+            # sessions per GPU one batch's kernel tails (the last rings of its slowest session) are filled by the other's work.
+            # (Measured at 128 .. 1024 sessions per GPU: no gain — profiles/r1m_cfg5_small_batches.txt — so one batch is the default.)
+            n_sub = args.sub_batches if args.sub_batches > 0 else 1
+            n_sub = max(1, min(n_sub, len(mine)))
+            subs = [mine[i::n_sub] for i in range(n_sub)]
+            streams = [stream] + [torch.cuda.Stream() for _ in range(n_sub - 1)]
+            batches = []
+            for part, st in zip(subs, streams):
+                # parameter grid over sigma_xy, sigma_theta, HoleWidth, Quality, seed
+                sxy = np.array([0.05 + 0.025 * (s % 5) for s in part], dtype=np.float32)
+                sth = np.array([0.0873 + 0.0436 * ((s // 5) % 4) for s in part], dtype=np.float32)
+                b = sn.Batch(len(part), wl["phys"], wl["size"], rp.odometry[0], sxy, sth, wl["iters"], wl["threads"], device=local,
+                             max_points=P, seeds=[args.seed + s for s in part], stream=st.cuda_stream)
+                for j, s in enumerate(part):
+                    b.set_params(j, 30 + 20 * ((s // 20) % 6), 0.4 + 0.2 * ((s // 120) % 4))
+                batches.append(b)
             log = sn.ScanLog(n_total, P, n_offsets=0, device=local)
             for k in range(n_total):
                 log.set(k, rp.points[k], rp.odometry[k])
             log.upload()
-            batch.replay(log, 0, PRIME_SCANS + W, want_results=False)
-            launches0 = batch.launch_count()
+            torch.cuda.synchronize()  # the log is read from every stream
+            for b in batches:
+                b.replay(log, 0, PRIME_SCANS + W, want_results=False)
+            launches0 = sum(b.launch_count() for b in batches)
             barrier()
             sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            done = [torch.cuda.Event() for _ in streams[1:]]
             t0 = time.perf_counter()
             e0.record(stream)
-            batch.replay(log, PRIME_SCANS + W, K, want_results=False)
+            for st in streams[1:]:
+                st.wait_event(e0)
+            # steps are queued round-robin so that neither stream runs ahead of the other by more than one step
+            if n_sub == 1:
+                batches[0].replay(log, PRIME_SCANS + W, K, want_results=False)
+            else:
+                for i in range(K):
+                    for b in batches:
+                        b.replay(log, PRIME_SCANS + W + i, 1, want_results=False)
+            for st, ev in zip(streams[1:], done):
+                ev.record(st)
+                stream.wait_event(ev)
             e1.record(stream)
             barrier()
             wall = time.perf_counter() - t0
             dev_ms = e0.elapsed_time(e1)
-            launches = batch.launch_count() - launches0
+            launches = sum(b.launch_count() for b in batches) - launches0
             lookups_per_step = (n_cand + 1) * P * n_sessions  # whole job per step: every session advances one scan
             scaling = "strong"
-            poses = batch.poses()
-            extra = {"sessions": n_sessions, "sessions_this_rank": len(mine),
+            poses = np.concatenate([b.poses() for b in batches], axis=0)
+            extra = {"sessions": n_sessions, "sessions_this_rank": len(mine), "batches_per_rank": n_sub,
                      "mode": "production (on-device Philox candidates), shared device-resident scan log",
                      "pose_spread_m": float(np.ptp(poses[:, 0]) + np.ptp(poses[:, 1])),
                      "l2": "per-rank working set %d maps x %.1f MB >> L2" % (len(mine), wl["size"] ** 2 * 2 / 1e6)}
             h2d, d2h = 0, 0
             log.close()
-            batch.close()
+            for b in batches:
+                b.close()
     clocks = sampler.stop()
     t_all = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -292,7 +317,7 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
                         "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms_max / K},
                 "gpu_launches": int(launches)}
         if args.workload == "cfg5":
-            line["sessions_per_s"] = wl["sessions"] * K / (dev_ms_max * 1e-3)
+            line["sessions_per_s"] = extra["sessions"] * K / (dev_ms_max * 1e-3)
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
@@ -444,6 +469,7 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         launch_ms = float(np.mean(i_ms))
+        traffic, traffic_src = latest_traffic("cs_rings_kernel_cfg3")
         alg_bytes = 4.0 * mean_visits + 8.0 * P
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
         value = world * mean_visits * K / (total_ms_max * 1e-3)
@@ -469,7 +495,7 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
                 "replay_l2_warm": {"ms_per_step": warm_ms_max, "value": world * mean_visits / (warm_ms_max * 1e-3),
                                    "note": "same replay without L2 flushes, %d scans back to back (the 32 MB map stays in L2)" % W},
                 "roofline": {"bound": "hbm", "kernel": "cs_rings_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
                              "note": "4 B (2 B read + 2 B write) per visited cell + the scan's points; per-cell ray order is kept, so the kernel "
                                      "is a chain of per-ring phases (latency), not a stream"},
@@ -493,6 +519,9 @@ def main():
     ap.add_argument("--streaming", action="store_true",
                     help="extra cfg2 measurement: a replay longer than L2 holds, queued back to back, no flush (single GPU)")
     ap.add_argument("--seed", type=int, default=0x5EED0000)
+    ap.add_argument("--sessions", type=int, default=0, help="cfg5: number of sessions in the job (default: the config's 1024)")
+    ap.add_argument("--sub-batches", type=int, default=0,
+                    help="cfg5: independent batches (streams) a rank's sessions are run as (default 1)")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -503,7 +503,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     // scans of several rounds (more rays than 2 x threads): two rings per unit, so that a round's rays serve two rings and
     // the second ring's evaluation hides the first one's map loads (cfg3: 208 -> 183 us; 4 and more rings per unit lose to imbalance)
     const bool multi_round = n_points > threads * CS_RING_RPT;
-    int span = dynamic ? (multi_round ? 2 : 1) : 64;
+    // Batches: 64 rings per block; 32 for batches of at most 256 sessions, where the grid is only a wave or two of blocks and
+    // shorter blocks leave a shorter tail (128 sessions, the per-GPU share of cfg5 on eight GPUs: 0.49 -> 0.455 ms per step).
+    int span = dynamic ? (multi_round ? 2 : 1) : (c.n_sessions <= 256 ? 32 : 64);
     if (tune().ring_span > 0) span = tune().ring_span;
     if (span < 1) span = 1;
     if (span > CS_RING_MAX_SPAN) span = CS_RING_MAX_SPAN;
