@@ -375,6 +375,39 @@ def test_cfg3_integration_stress_8192_rays_4096_map():
     p.close()
 
 
+@pytest.mark.parametrize("n_rays", [2500, 4096])
+def test_integrate_large_map_several_rounds_sorted_and_unsorted(n_rays):
+    """Scans of several rounds (more rays than 2 x 512) on a map whose outer rings are longer than the slot table (k > 1024):
+    the several-rounds instance of the rings kernel claims all windows of such a ring in one pass when the rays come in
+    angular order, and must fall back to window-by-window claims when an unsorted scan aliases two cells onto one slot.
+    Sorted, permuted, reversed and wall-hugging scans, all bit-exact against the cell-by-cell oracle."""
+    size, phys = 4096, 40.96
+    rng = np.random.default_rng(n_rays)
+    p = _mk(size, phys, 1, 1, max_points=n_rays)
+    m = orc.HoleMap(size, phys)
+    m.fill(32750)
+    for k in range(5):
+        ang = np.linspace(0, 2 * np.pi, n_rays, endpoint=False) + rng.uniform(0, 0.01)
+        rad = rng.uniform(8.0, 19.0, n_rays)
+        if k == 1:
+            ang = rng.permutation(ang)       # unordered: rays of one round lie all around the ring
+        if k == 2:
+            ang = ang[::-1].copy()
+        if k == 3:
+            ang = rng.permutation(ang)
+            rad = np.where(rng.random(n_rays) < 0.5, rng.uniform(0.05, 2.0, n_rays), rad)  # contested inner cells too
+        if k == 4:
+            rad = rng.uniform(11.0, 30.0, n_rays)  # far ends clipped at the map border
+        pts = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1).astype(np.float32)
+        pose = np.array([20.0 + rng.uniform(-1, 1), 20.0 + rng.uniform(-1, 1), rng.uniform(-3, 3)], dtype=np.float32)
+        vo = orc.update_hole_map(m, pts, pose, 0.6, 50)
+        vg = p.integrate(pts, pose)
+        assert vg == vo, k
+        got = p.map_download()
+        assert np.array_equal(got, np.array(m.pixels)), "scan %d: %d cells differ" % (k, np.count_nonzero(got != m.pixels))
+    p.close()
+
+
 def test_cfg4_large_map_search_8192():
     """configs[3] single-GPU part: 8192x8192 map (128 MB), large candidate set, distances bit-exact."""
     size, phys = 8192, 81.92
