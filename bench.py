@@ -125,7 +125,7 @@ def pow2_threads(n_cand, cores):
     return t
 
 
-def run_cpu(wl, rp, offs, n_cand, first, count, budget_s=25.0, min_s=10.0):
+def run_cpu(wl, rp, offs, n_cand, first, count, budget_s=25.0, min_s=10.0, threads=None):
     """The oracle port (reference algorithm, ParallelWorker-style threads) over scans [first, first+count).
     The first pass is the parity sample (same scans as the GPU arm); when it ends before `min_s` seconds the
     same scans are replayed back and forth (count-1 .. 0 .. count-1, so odometry stays continuous) until the
@@ -133,7 +133,7 @@ def run_cpu(wl, rp, offs, n_cand, first, count, budget_s=25.0, min_s=10.0):
     pose after the first pass, whether the first pass was complete)."""
     from oracle import oracle as orc
     cores = os.cpu_count() or 1
-    T = pow2_threads(n_cand, cores)
+    T = pow2_threads(n_cand, cores if threads is None else min(threads, cores))
     o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, n_cand // T, T)
     w = orc.Worker(T)
     for k in range(first):  # bring the map to the same state as the GPU arm (untimed)
@@ -796,6 +796,10 @@ def main():
                    "sample": "%d Updates over the %d timed scans of the same replay (replayed back and forth until >= 10 s) after %d "
                              "untimed scans, %.1f s, %d threads (search) + 1 thread (integration)" % (done, K, first, dt, T),
                    "pose_bit_exact_vs_gpu": parity if complete else None}
+            # the simulator's own setting: 4 search threads (Simulation/MainWindow.xaml.cs:69), a shorter sample of the same scans
+            v4, done4, T4, dt4, _, _ = run_cpu(wl, rp, offs, n_cand, first, min(K, 100), budget_s=8.0, min_s=4.0, threads=4)
+            cpu["simulator_setting"] = {"value": v4, "unit": "lookups/s", "cores": T4,
+                                        "sample": "%d Updates of the same replay, %.1f s, %d search threads as in the reference's simulator" % (done4, dt4, T4)}
 
         line = {"metric": metric, "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
