@@ -771,7 +771,7 @@ def main():
             gather_peak = None
         search_rate = lookups_per_step / (search_ms * 1e-3)
         kname = "cs_search2_kernel" if plan["slab"] else "cs_search_kernel"
-        traffic, traffic_src = latest_traffic(kname)
+        traffic, traffic_src = latest_traffic(kname) if args.workload == "cfg2" else (None, None)  # the captures are cfg2's
         roofline = {"bound": "hbm", "kernel": plan["kernel"] + " (+ the Update glue and pose hand-off in its last warp/block)",
                     "launch_shape": plan, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
