@@ -57,6 +57,14 @@ PRIME_SCANS = 5  # PositionSearchBeginning: the first 5 scans only build the map
 SIGMA_XY, SIGMA_THETA = 0.1, 0.17453292  # 0.1 m, 10 degrees (Simulation/MainWindow.xaml.cs:69)
 
 
+def cpu_min_seconds(default=10.0):
+    """Shortest CPU sample of the reference arm / cpu_baseline (CS_BENCH_CPU_MIN_S shortens it for the CPU test-suite)."""
+    try:
+        return float(os.environ.get("CS_BENCH_CPU_MIN_S", default))
+    except ValueError:
+        return default
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -576,7 +584,7 @@ def main():
         if args.workload == "cfg3":
             from slam.net_b200 import synth
             rp = synth.make_replay(W + K, P, wl["phys"], seed=args.seed)
-            visits, secs, done, _ = run_cpu_cfg3(wl, rp, W, K)
+            visits, secs, done, _ = run_cpu_cfg3(wl, rp, W, K, min_s=cpu_min_seconds())
             v = visits / secs
             line = {"impl": "reference", "metric": "HoleMap cell visits/sec", "value": v, "unit": "visits/s", "n_gpus": args.gpus, "steps": K,
                     "updates_timed": done, "warmup": W, "ms_per_step": secs / max(done, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -592,7 +600,7 @@ def main():
         n_total = PRIME_SCANS + W + K
         rp, offs, n_cand = build_workload(wl, n_total, args.seed)
         first = PRIME_SCANS + W
-        v, done, T, dt, _, _ = run_cpu(wl, rp, offs, n_cand, first, K, budget_s=120.0, min_s=10.0)
+        v, done, T, dt, _, _ = run_cpu(wl, rp, offs, n_cand, first, K, budget_s=120.0, min_s=cpu_min_seconds())
         sample = "%d Updates over the %d requested scans of the %s replay (replayed back and forth until >= 10 s; after %d untimed " \
                  "priming/warm-up scans), %.1f s" % (done, K, args.workload, first, dt)
         line = {"impl": "reference", "metric": metric, "value": v, "unit": "lookups/s", "n_gpus": args.gpus, "steps": K, "updates_timed": done,
