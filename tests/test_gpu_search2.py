@@ -245,6 +245,30 @@ def test_slab_batch_update_matches_oracle_per_session(flags):
     b.close()
 
 
+def test_batch_with_scans_of_several_rounds():
+    """A batch whose sessions carry more rays than one round of the rings kernel holds (2 x 512), with ragged point counts —
+    one session stays below a round: the batch runs the several-rounds instance (grid.y = session, fixed units), every
+    session must still equal the oracle (poses, winners, maps)."""
+    n_sess, n_scans, P, size, phys, iters, threads = 3, 8, 2600, 512, 40.0, 40, 2
+    rps = [synth.make_replay(n_scans, P, phys, seed=150 + j) for j in range(n_sess)]
+    sxy, sth = [0.05, 0.07, 0.09], [0.10, 0.11, 0.12]
+    b = sn.Batch(n_sess, phys, size, [rp.odometry[0] for rp in rps], sxy, sth, iters, threads, max_points=P)
+    os_ = [orc.Processor(phys, size, rps[j].odometry[0], sxy[j], sth[j], iters, threads) for j in range(n_sess)]
+    keep = [P, 1500, 700]  # three rounds, two rounds, one round
+    for k in range(n_scans):
+        offs = np.stack([synth.candidate_offsets(170 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        pts = [rps[j].points[k][: keep[j]] for j in range(n_sess)]
+        res = b.update(pts, np.stack([rps[j].odometry[k] for j in range(n_sess)]), offs)
+        for j in range(n_sess):
+            os_[j].update(pts[j], rps[j].odometry[k], offs[j])
+            assert np.array_equal(res[j].pose, os_[j].pose), (k, j)
+            if k >= 5:
+                assert (res[j].distance, res[j].index) == (os_[j].last_distance, os_[j].last_index), (k, j)
+    for j in range(n_sess):
+        assert np.array_equal(b.map_download(j), np.array(os_[j].map.pixels)), j
+    b.close()
+
+
 def test_slab_batch_replay_shared_log_philox():
     """Parameter sweep in production mode: one shared device-resident log, per-session seeds and sigmas, on-device Philox
     candidates sorted per session; equal to the oracle fed the host twin's deviates."""
