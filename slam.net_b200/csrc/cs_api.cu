@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
+#include <limits>
 #include <cstring>
 #include <atomic>
 #include <string>
@@ -226,14 +227,31 @@ int rings_hint_of(int size, float scale, float hole_width, double max_range) {
 }
 int rings_hint(const cs_processor* h, double max_range) { return rings_hint_of(h->size, h->scale, h->hs.hole_width, max_range); }
 
+// Largest range of a scan (for the rings hint: an upper bound on the rings the scan can reach; NaN sticks, overflow gives
+// +inf, both mean "all rings").  Four independent running maxima: a batch update calls this for every session on one host
+// thread (1024 x 360 points per cfg5 step), where a single dependent chain cost as much as the staging copy itself.
 double max_range_of(const float* points, int n) {
-  double m = 0.0;
-  for (int i = 0; i < n; i++) {
-    double x = points[2 * i], y = points[2 * i + 1];
-    double r2 = x * x + y * y;
-    if (!(r2 <= m)) m = r2;  // NaN sticks
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  bool nan_seen = false;
+  int i = 0;
+  for (; i + 4 <= n; i += 4) {
+    const float* p = points + 2 * (size_t)i;
+    const float r0 = p[0] * p[0] + p[1] * p[1], r1 = p[2] * p[2] + p[3] * p[3];
+    const float r2 = p[4] * p[4] + p[5] * p[5], r3 = p[6] * p[6] + p[7] * p[7];
+    nan_seen |= (r0 != r0) | (r1 != r1) | (r2 != r2) | (r3 != r3);
+    m0 = r0 > m0 ? r0 : m0;
+    m1 = r1 > m1 ? r1 : m1;
+    m2 = r2 > m2 ? r2 : m2;
+    m3 = r3 > m3 ? r3 : m3;
   }
-  return std::sqrt(m);
+  for (; i < n; i++) {
+    const float r = points[2 * i] * points[2 * i] + points[2 * i + 1] * points[2 * i + 1];
+    nan_seen |= (r != r);
+    m0 = r > m0 ? r : m0;
+  }
+  if (nan_seen) return std::numeric_limits<double>::quiet_NaN();
+  const float m = std::fmax(std::fmax(m0, m1), std::fmax(m2, m3));
+  return std::sqrt((double)m) * 1.000001;  // float rounding of r^2 (2^-24 relative) stays inside the bound
 }
 
 // What a step is launched on: one processor (n_sessions = 1) or a batch of independent sessions
