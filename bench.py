@@ -207,7 +207,7 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
 
     P = wl["points"]
     n_cand = wl["threads"] * wl["iters"]
-    n_total = PRIME_SCANS + W + K + (min(K, 20) if args.workload == "cfg5" else 0)  # cfg5: + the scans of the e2e pass
+    n_total = PRIME_SCANS + W + K + (2 * min(K, 20) + 2 if args.workload == "cfg5" else 0)  # cfg5: + the scans of the two e2e passes
     from slam.net_b200 import synth
     rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed)  # same scans on every rank
     stream = torch.cuda.Stream()
@@ -312,7 +312,7 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
             packed = []
             for b, part in zip(batches, subs):
                 per_step = []
-                for i in range(Ke):
+                for i in range(2 * Ke + 2):
                     k = PRIME_SCANS + W + K + i
                     pts = np.zeros((len(part), P, 2), dtype=np.float32)
                     pts[:, :rp.points[k].shape[0]] = rp.points[k]
@@ -329,6 +329,35 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
                     if st != 0:
                         raise RuntimeError("cs_batch_update failed: %d" % st)
             barrier()
+            e2e_blocking_wall = time.perf_counter() - t0e
+            # the same through cs_batch_submit / cs_batch_collect: step k+1 is staged and queued before step k's results
+            # are collected, so the host staging overlaps the device's work; still every scan goes up and every record
+            # comes back, every step
+            def submit(i):
+                for b, (per_step, res) in zip(batches, packed):
+                    pts, npts, odo = per_step[i]
+                    st = L.cs_batch_submit(b._h, pts.ctypes.data_as(fp), npts.ctypes.data_as(ip), odo.ctypes.data_as(fp), None)
+                    if st != 0:
+                        N.check(st, batch=b._h)
+
+            def collect():
+                for b, (per_step, res) in zip(batches, packed):
+                    st = L.cs_batch_collect(b._h, res)
+                    if st != 0:
+                        N.check(st, batch=b._h)
+
+            submit(Ke)      # untimed: the two pipeline slots (pinned + device staging) are allocated on first use
+            submit(Ke + 1)
+            collect()
+            collect()
+            barrier()
+            t0e = time.perf_counter()
+            submit(Ke + 2)
+            for i in range(Ke + 3, 2 * Ke + 2):
+                submit(i)
+                collect()
+            collect()
+            barrier()
             e2e_wall = time.perf_counter() - t0e
             e2e_steps = Ke
             extra = {"sessions": n_sessions, "sessions_this_rank": len(mine), "batches_per_rank": n_sub,
@@ -336,7 +365,10 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
                      "pose_spread_m": float(np.ptp(poses[:, 0]) + np.ptp(poses[:, 1])),
                      "l2": "per-rank working set %d maps x %.1f MB >> L2" % (len(mine), wl["size"] ** 2 * 2 / 1e6)}
             h2d, d2h = n_sessions * (8 * P + 12 + 4), n_sessions * 32  # whole job: points + odometry + count in, result record out
-            extra["e2e_api"] = "cs_batch_update (C ABI, host buffers: every session's scan uploaded each step, every result read back), %d steps" % Ke
+            extra["e2e_api"] = ("cs_batch_submit + cs_batch_collect (C ABI, host buffers: every session's scan uploaded each step, every "
+                                "result record read back; step k+1 is submitted before step k is collected), %d steps" % Ke)
+            extra["e2e_blocking"] = {"api": "cs_batch_update (blocking call), %d steps" % Ke, "ms_per_step": e2e_blocking_wall / Ke * 1e3,
+                                     "sessions_per_s_this_rank": len(mine) * Ke / e2e_blocking_wall}
             log.close()
             for b in batches:
                 b.close()

@@ -81,6 +81,22 @@ namespace CoreSLAM.B200
         [DllImport(Lib)] public static extern CsStatus cs_pinned_alloc(out IntPtr ptr, ulong bytes);
         [DllImport(Lib)] public static extern CsStatus cs_pinned_free(IntPtr ptr);
 
+        // ---- batches of independent sessions on one GPU (parameter sweeps, scan-log replays); no reference counterpart:
+        // the reference would loop over CoreSLAMProcessor instances.  cfgs = nSessions CsConfig records.
+        [DllImport(Lib)] public static extern CsStatus cs_batch_create(CsConfig* cfgs, int nSessions, out IntPtr batch);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_destroy(IntPtr batch);
+        [DllImport(Lib)] public static extern IntPtr cs_batch_last_error(IntPtr batch);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_set_params(IntPtr batch, int session, int quality, float holeWidth);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_update(IntPtr batch, float* pointsXY, int* nPoints, float* odometry3,
+                                                                       float* candOffsets, CsResult* results);
+        // pipelined form: Submit(k+1) before Collect(k) overlaps the host staging with the device's work on step k
+        [DllImport(Lib)] public static extern CsStatus cs_batch_submit(IntPtr batch, float* pointsXY, int* nPoints, float* odometry3,
+                                                                       float* candOffsets);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_collect(IntPtr batch, CsResult* results);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_sync(IntPtr batch);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_get_poses(IntPtr batch, float* poses3);
+        [DllImport(Lib)] public static extern CsStatus cs_batch_map_download(IntPtr batch, int session, ushort* pixels);
+
         public static void Check(CsStatus st, IntPtr h)
         {
             if (st != CsStatus.Ok)

@@ -256,6 +256,14 @@ cs_status cs_batch_set_params(cs_batch* b, int32_t session /* <0: all */, int32_
  * n_sessions*3, cand_offsets n_sessions*T*I*3 or NULL (Philox), results optional n_sessions records. */
 cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
                           const float* cand_offsets, cs_result* results);
+/* The same Update, pipelined: cs_batch_submit stages and queues one step and returns; cs_batch_collect waits for the oldest
+ * submitted step and copies out its n_sessions result records (NULL: only wait).  At most two steps may be waiting for
+ * their collect (a third submit fails with CS_ERR_STATE).  A caller that alternates submit(k+1), collect(k) overlaps the host
+ * staging of step k+1 with the device's work on step k.  (No reference counterpart: CoreSLAMProcessor.Update is blocking,
+ * CoreSLAMProcessor.cs:717; this is the batched replay's throughput path.) */
+cs_status cs_batch_submit(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
+                          const float* cand_offsets);
+cs_status cs_batch_collect(cs_batch* b, cs_result* results);
 /* Every session replays scans [first, first+count) of one shared device-resident log; results: optional
  * n_sessions records of the last scan. */
 cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results);

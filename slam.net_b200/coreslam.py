@@ -481,6 +481,25 @@ class Batch:
         self._ck(N.lib().cs_batch_update(self._h, _ptr(buf), npts.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(odo), _ptr(off), res))
         return [_result(r) for r in res] if want_results else None
 
+    def submit(self, points: Sequence[np.ndarray], odometry, cand_offsets=None):
+        """cs_batch_submit: stage and queue one Update of every session, return at once (at most two steps may wait for
+        collect()).  Arguments as update()."""
+        buf = np.zeros((self.n, self.max_points, 2), dtype=np.float32)
+        npts = np.zeros(self.n, dtype=np.int32)
+        for j, p in enumerate(points):
+            p = _f32(p).reshape(-1, 2)
+            buf[j, :p.shape[0]] = p
+            npts[j] = p.shape[0]
+        odo = _f32(odometry).reshape(self.n, 3)
+        off = None if cand_offsets is None else _f32(cand_offsets).reshape(self.n, self.n_cand, 3)
+        self._ck(N.lib().cs_batch_submit(self._h, _ptr(buf), npts.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(odo), _ptr(off)))
+
+    def collect(self, want_results=True):
+        """cs_batch_collect: wait for the oldest submitted step; its result records."""
+        res = (N.Result * self.n)() if want_results else None
+        self._ck(N.lib().cs_batch_collect(self._h, res))
+        return [_result(r) for r in res] if want_results else None
+
     def replay(self, log: ScanLog, first: int = 0, count: Optional[int] = None, want_results=True):
         count = log.n_scans - first if count is None else count
         res = (N.Result * self.n)() if want_results else None

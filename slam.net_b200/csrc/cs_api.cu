@@ -1893,6 +1893,13 @@ struct cs_batch {
   unsigned update_count = 0;
   uint64_t launches = 0;
   unsigned step_counter = 0;
+  // cs_batch_submit / cs_batch_collect: two staging + result slots, so that the host stages step k+1 while step k runs
+  uint8_t* pipe_h_stage[2] = {nullptr, nullptr};
+  uint8_t* pipe_d_stage[2] = {nullptr, nullptr};
+  CsDevResult* pipe_d_results[2] = {nullptr, nullptr};
+  CsDevResult* pipe_h_results[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_done[2] = {nullptr, nullptr};
+  unsigned pipe_submitted = 0, pipe_collected = 0;
   std::string error;
   bool poisoned = false;
 };
@@ -2099,6 +2106,13 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_results);
   if (b->h_stage) cudaFreeHost(b->h_stage);
   if (b->h_results) cudaFreeHost(b->h_results);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(b->pipe_d_stage[i]);
+    cudaFree(b->pipe_d_results[i]);
+    if (b->pipe_h_stage[i]) cudaFreeHost(b->pipe_h_stage[i]);
+    if (b->pipe_h_results[i]) cudaFreeHost(b->pipe_h_results[i]);
+    if (b->pipe_done[i]) cudaEventDestroy(b->pipe_done[i]);
+  }
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   cudaGetLastError();
   delete b;
@@ -2137,14 +2151,12 @@ static float batch_max_hole_width(const cs_batch* b) {
 //   odometry      n_sessions * (x, y, theta)
 //   cand_offsets  n_sessions * T*I * (dx, dy, dtheta) verification tables, or NULL: per-session Philox streams
 //   results       optional, n_sessions records (blocks until the poses are back)
-cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
-                          const float* cand_offsets, cs_result* results) {
-  CS_CHECK_BATCH(b);
-  if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_update: null argument");
+namespace {
+// Stages one Update of every session into (h_stage -> d_stage) and launches its kernels; the result records go to d_results.
+cs_status batch_stage_and_launch(cs_batch* b, uint8_t* h_stage, uint8_t* d_stage, CsDevResult* d_results, const float* points,
+                                 const int32_t* n_points, const float* odometry, const float* cand_offsets) {
   const bool do_search = b->scan_count >= b->search_begin;
   const bool with_offsets = cand_offsets != nullptr && do_search;
-  // the pinned block may still be the source of the previous call's copy
-  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
   int max_n = 0;
   double max_range = 0.0;
   for (int j = 0; j < b->n; j++) {
@@ -2152,28 +2164,28 @@ cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_poi
     if (np <= 0 || np > b->max_points) return bfail(b, CS_ERR_CAPACITY, "session %d: n_points %d outside 1..%d", j, np, b->max_points);
     const float* odo = odometry + 3 * (size_t)j;
     if (!finite3(odo)) return bfail(b, CS_ERR_INVALID_ARGUMENT, "session %d: odometry pose is NaN", j);
-    CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(b->h_stage) + j;
+    CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h_stage) + j;
     memset(hdr, 0, sizeof(CsStepHeader));
     hdr->odo[0] = odo[0]; hdr->odo[1] = odo[1]; hdr->odo[2] = odo[2];
     hdr->n_points = np;
     const float* src = points + (size_t)j * b->max_points * 2;
-    memcpy(b->h_stage + b->off_points + (size_t)j * b->max_points * 8, src, (size_t)np * 8);
+    memcpy(h_stage + b->off_points + (size_t)j * b->max_points * 8, src, (size_t)np * 8);
     const double r = max_range_of(src, np);
     if (!(r <= max_range)) max_range = r;
     if (np > max_n) max_n = np;
   }
-  if (with_offsets) memcpy(b->h_stage + b->off_cand, cand_offsets, (size_t)b->n * b->n_cand * 12);
+  if (with_offsets) memcpy(h_stage + b->off_cand, cand_offsets, (size_t)b->n * b->n_cand * 12);
   const size_t bytes = with_offsets ? b->stage_bytes : b->off_cand;
-  CS_BCUDA(b, cudaMemcpyAsync(b->d_stage, b->h_stage, bytes, cudaMemcpyHostToDevice, b->stream));
+  CS_BCUDA(b, cudaMemcpyAsync(d_stage, h_stage, bytes, cudaMemcpyHostToDevice, b->stream));
 
   CsStepArgs a{};
-  a.hdr = reinterpret_cast<const CsStepHeader*>(b->d_stage);
+  a.hdr = reinterpret_cast<const CsStepHeader*>(d_stage);
   a.hdr_stride = 1;
-  a.points = reinterpret_cast<const float2*>(b->d_stage + b->off_points);
+  a.points = reinterpret_cast<const float2*>(d_stage + b->off_points);
   a.points_stride = (size_t)b->max_points;
-  a.cand = with_offsets ? reinterpret_cast<const float*>(b->d_stage + b->off_cand) : nullptr;
+  a.cand = with_offsets ? reinterpret_cast<const float*>(d_stage + b->off_cand) : nullptr;
   a.cand_stride = (size_t)b->n_cand * 3;
-  a.result = b->d_results;
+  a.result = d_results;
   a.result_stride = 1;
   a.scan_index = b->update_count;
   a.cand_mode = with_offsets ? CS_CAND_OFFSETS : CS_CAND_PHILOX;
@@ -2188,6 +2200,18 @@ cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_poi
   b->parity ^= 1;
   b->update_count++;
   if (!do_search) b->scan_count++;
+  return CS_OK;
+}
+}  // namespace
+
+cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
+                          const float* cand_offsets, cs_result* results) {
+  CS_CHECK_BATCH(b);
+  if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_update: null argument");
+  // the pinned block may still be the source of the previous call's copy
+  CS_BCUDA(b, cudaStreamSynchronize(b->stream));
+  cs_status st = batch_stage_and_launch(b, b->h_stage, b->d_stage, b->d_results, points, n_points, odometry, cand_offsets);
+  if (st != CS_OK) return st;
   if (results) {
     CS_BCUDA(b, cudaMemcpyAsync(b->h_results, b->d_results, sizeof(CsDevResult) * (size_t)b->n, cudaMemcpyDeviceToHost, b->stream));
     CS_BCUDA(b, cudaStreamSynchronize(b->stream));
@@ -2196,6 +2220,51 @@ cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_poi
       results[j].visits = -1;
     }
   }
+  return CS_OK;
+}
+
+// The same Update, pipelined: cs_batch_submit stages and queues a step and returns; cs_batch_collect waits for the oldest
+// submitted step and hands out its result records.  At most two steps may be waiting for their collect, so a caller that
+// alternates submit(k+1), collect(k) has the host staging of step k+1 (pinned copy, range scan, H2D) running while the device
+// works on step k, and consecutive steps stay chained on the stream (no host round trip between them).
+cs_status cs_batch_submit(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
+                          const float* cand_offsets) {
+  CS_CHECK_BATCH(b);
+  if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_submit: null argument");
+  if (b->pipe_submitted - b->pipe_collected >= 2u)
+    return bfail(b, CS_ERR_STATE, "cs_batch_submit: two submitted steps are waiting for cs_batch_collect");
+  const int slot = (int)(b->pipe_submitted & 1u);
+  if (!b->pipe_h_stage[slot]) {
+    CS_BCUDA(b, cudaHostAlloc(&b->pipe_h_stage[slot], b->stage_bytes, cudaHostAllocDefault));
+    CS_BCUDA(b, cudaMalloc(&b->pipe_d_stage[slot], b->stage_bytes));
+    CS_BCUDA(b, cudaMalloc(&b->pipe_d_results[slot], sizeof(CsDevResult) * (size_t)b->n));
+    CS_BCUDA(b, cudaHostAlloc(&b->pipe_h_results[slot], sizeof(CsDevResult) * (size_t)b->n, cudaHostAllocDefault));
+    CS_BCUDA(b, cudaEventCreateWithFlags(&b->pipe_done[slot], cudaEventDisableTiming));
+  }
+  // The slot's pinned block was the source of the copy two submits ago; that step has been collected (its pipe_done event,
+  // recorded after the copy, was waited for), so the block is free.  The device block is protected by stream order.
+  cs_status st = batch_stage_and_launch(b, b->pipe_h_stage[slot], b->pipe_d_stage[slot], b->pipe_d_results[slot], points, n_points,
+                                        odometry, cand_offsets);
+  if (st != CS_OK) return st;
+  CS_BCUDA(b, cudaMemcpyAsync(b->pipe_h_results[slot], b->pipe_d_results[slot], sizeof(CsDevResult) * (size_t)b->n,
+                              cudaMemcpyDeviceToHost, b->stream));
+  CS_BCUDA(b, cudaEventRecord(b->pipe_done[slot], b->stream));
+  b->pipe_submitted++;
+  return CS_OK;
+}
+
+cs_status cs_batch_collect(cs_batch* b, cs_result* results /* n_sessions records, or NULL to only wait */) {
+  CS_CHECK_BATCH(b);
+  if (b->pipe_collected == b->pipe_submitted) return bfail(b, CS_ERR_STATE, "cs_batch_collect: nothing was submitted");
+  const int slot = (int)(b->pipe_collected & 1u);
+  CS_BCUDA(b, cudaEventSynchronize(b->pipe_done[slot]));
+  if (results) {
+    for (int j = 0; j < b->n; j++) {
+      copy_result(results + j, b->pipe_h_results[slot] + j);
+      results[j].visits = -1;
+    }
+  }
+  b->pipe_collected++;
   return CS_OK;
 }
 

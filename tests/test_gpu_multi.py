@@ -177,3 +177,38 @@ def test_batch_parity_with_other_rings_per_block(span):
                         "tests/test_gpu_multi.py::test_batch_replay_shared_log_philox_equals_single_handles"],
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+
+
+def test_batch_submit_collect_pipeline_equals_blocking_updates():
+    """cs_batch_submit / cs_batch_collect (two steps in flight, host staging overlapped with the previous step) must give the
+    records and maps of the blocking cs_batch_update, and refuse a third step in flight / a collect with nothing submitted."""
+    n_sess, n_scans, P, size, phys, iters, threads = 4, 14, 300, 256, 40.0, 120, 2
+    rps = [synth.make_replay(n_scans, P, phys, seed=250 + j) for j in range(n_sess)]
+    sxy, sth = [0.05, 0.07, 0.09, 0.11], [0.10, 0.11, 0.12, 0.13]
+    mk = lambda: sn.Batch(n_sess, phys, size, [rp.odometry[0] for rp in rps], sxy, sth, iters, threads, max_points=P, seeds=[9, 8, 7, 6])
+    a, b = mk(), mk()
+    args = []
+    for k in range(n_scans):
+        offs = None if k % 3 == 2 else np.stack([synth.candidate_offsets(270 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        pts = [rps[j].points[k][: P - 11 * j] for j in range(n_sess)]
+        args.append((pts, np.stack([rps[j].odometry[k] for j in range(n_sess)]), offs))
+    want = [a.update(*x) for x in args]
+    with pytest.raises(Exception):
+        b.collect()
+    got = []
+    b.submit(*args[0])
+    for k in range(1, n_scans):
+        b.submit(*args[k])
+        if k == 1:
+            with pytest.raises(Exception):
+                b.submit(*args[k])  # a third step in flight is refused and changes nothing
+        got.append(b.collect())
+    got.append(b.collect())
+    for k in range(n_scans):
+        for j in range(n_sess):
+            assert np.array_equal(got[k][j].pose, want[k][j].pose), (k, j)
+            assert (got[k][j].distance, got[k][j].index) == (want[k][j].distance, want[k][j].index), (k, j)
+    assert np.array_equal(a.map_checksums(), b.map_checksums())
+    assert np.array_equal(a.poses(), b.poses())
+    a.close()
+    b.close()
