@@ -81,6 +81,8 @@ namespace CoreSLAM.B200
         [DllImport(Lib)] public static extern CsStatus cs_pinned_alloc(out IntPtr ptr, ulong bytes);
         [DllImport(Lib)] public static extern CsStatus cs_pinned_free(IntPtr ptr);
 
+        [DllImport(Lib)] public static extern int cs_rings_hint(int sizePixels, float sizeMeters, float holeWidth, float* pointsXY, int nPoints);
+
         // ---- batches of independent sessions on one GPU (parameter sweeps, scan-log replays); no reference counterpart:
         // the reference would loop over CoreSLAMProcessor instances.  cfgs = nSessions CsConfig records.
         [DllImport(Lib)] public static extern CsStatus cs_batch_create(CsConfig* cfgs, int nSessions, out IntPtr batch);

@@ -281,6 +281,10 @@ cs_status cs_device_sincos(int32_t device, const float* angles, int32_t n, float
 float cs_host_normalize_angle(float a);
 /* Measured ceiling for the search's access pattern: random 2-byte loads over a table of `cells`
  * uint16 (L2-resident when it fits), best of `repeats`.  Used by bench.py as the gather roofline. */
+/* Host-only diagnostic: the number of rings the library sizes a scan's integration for — an upper bound of the longest clipped
+ * ray in cells, + 1 (DrawLaserRayOnHoleMap walks x = 0..dxc, CoreSLAMProcessor.cs:404), from the scan's largest range, the map
+ * scale (HoleMap.cs:20) and HoleWidth (:525).  A session batch launches exactly this many rings per session. */
+int32_t cs_rings_hint(int32_t size_pixels, float size_meters, float hole_width, const float* points, int32_t n_points);
 cs_status cs_gather_peak(int32_t device, int64_t cells, int32_t per_thread, int32_t repeats, double* lookups_per_s);
 
 #ifdef __cplusplus

@@ -173,6 +173,7 @@ SIGNATURES = {
     "cs_batch_size": (C.c_int32, [_vp]),
     "cs_batch_set_params": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_float]),
     "cs_batch_update": (C.c_int, [_vp, _fp, _ip, _fp, _fp, C.POINTER(Result)]),
+    "cs_rings_hint": (C.c_int32, [C.c_int32, C.c_float, C.c_float, _fp, C.c_int32]),
     "cs_batch_submit": (C.c_int, [_vp, _fp, _ip, _fp, _fp]),
     "cs_batch_collect": (C.c_int, [_vp, C.POINTER(Result)]),
     "cs_batch_replay": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.POINTER(Result)]),

@@ -2400,6 +2400,12 @@ __global__ void cs_gather_peak_kernel(const uint16_t* __restrict__ table, unsign
   if (acc == 0xffffffffu) atomicAdd(sink, 1ull);
 }
 
+int32_t cs_rings_hint(int32_t size_pixels, float size_meters, float hole_width, const float* points, int32_t n_points) {
+  if (size_pixels <= 0 || !points || n_points < 0) return 0;
+  const float scale = (float)size_pixels / size_meters;  // HoleMap.cs:20
+  return rings_hint_of(size_pixels, scale, hole_width, max_range_of(points, n_points));
+}
+
 cs_status cs_gather_peak(int32_t device, int64_t cells, int32_t per_thread, int32_t repeats, double* lookups_per_s) {
   if (!lookups_per_s || cells < 1024 || per_thread < 8 || repeats < 1) return CS_ERR_INVALID_ARGUMENT;
   if (cs_device_count() <= device) return fail(nullptr, CS_ERR_NO_DEVICE, "no such CUDA device");
