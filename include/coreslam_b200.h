@@ -252,8 +252,9 @@ cs_status cs_batch_destroy(cs_batch* b);
 const char* cs_batch_last_error(const cs_batch* b);
 int32_t cs_batch_size(const cs_batch* b);
 cs_status cs_batch_set_params(cs_batch* b, int32_t session /* <0: all */, int32_t quality, float hole_width);
-/* Update for every session: points n_sessions*max_points*(x,y) (session j uses n_points[j]), odometry
- * n_sessions*3, cand_offsets n_sessions*T*I*3 or NULL (Philox), results optional n_sessions records. */
+/* Update for every session: points n_sessions*max_points*(x,y) with max_points = cfgs[0].max_points exactly as passed to
+ * cs_batch_create (odd or even; 0 means 16384): session j's points start at points + j*max_points*2 and it uses the first
+ * n_points[j] of them, odometry n_sessions*3, cand_offsets n_sessions*T*I*3 or NULL (Philox), results optional n_sessions records. */
 cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
                           const float* cand_offsets, cs_result* results);
 /* The same Update, pipelined: cs_batch_submit stages and queues one step and returns; cs_batch_collect waits for the oldest

@@ -447,7 +447,7 @@ class Batch:
         self.n = n_sessions
         self.size = hole_map_size
         self.n_cand = max(num_search_threads, 1) * iterations_per_thread
-        self.max_points = ((max_points if max_points > 0 else 16384) + 1) & ~1
+        self.max_points = max_points if max_points > 0 else 16384  # stride of the points array = cfg.max_points, odd or even
         self.seeds, self.sigma_xy, self.sigma_theta = seeds, sxy, sth
 
     def _ck(self, status):

@@ -14,6 +14,7 @@
 #include <limits>
 #include <cstring>
 #include <atomic>
+#include <exception>
 #include <string>
 #include <type_traits>
 #include <vector>
@@ -432,7 +433,10 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int rings, int phases) {
-  const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search;
+  // An empty cloud (Update with segments that carry no rays): CalculateDistance returns int.MaxValue for every pose (:251-258),
+  // so searchPose wins (:630-648, strict <) without a single lookup: no search kernel, the glue decodes (MaxValue, index 0).
+  a.empty_cloud = (a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search && n_points == 0) ? 1 : 0;
+  const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search && !a.empty_cloud;
   const bool draws = a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0;
   const bool fused = searching && phases == CS_PHASE_ALL;
   a.fuse_publish = fused ? 1 : 0;
@@ -1153,7 +1157,9 @@ static cs_status launch_cloud(cs_processor* h, const uint8_t* d_rays, const uint
 
 static cs_status check_segments(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
                                 int32_t n_segments) {
-  if (!rays || !seg_first || !seg_poses || n_rays <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "segments: bad argument");
+  // n_rays == 0 is legal: segments whose Rays lists are empty still advance the processor state (:719-747, every distance
+  // is int.MaxValue and searchPose wins); only a negative count or missing tables are argument errors
+  if ((!rays && n_rays > 0) || !seg_first || !seg_poses || n_rays < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "segments: bad argument");
   if (n_segments <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "Sequence contains no elements (segments.Last(), CoreSLAMProcessor.cs:719)");
   if (n_rays > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_rays %d > max_points %d", n_rays, h->max_points);
   if (n_segments > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_segments %d > max_points %d", n_segments, h->max_points);
@@ -1166,20 +1172,22 @@ static cs_status check_segments(cs_processor* h, const float* rays, const int32_
 // upper bound of |point| over the cloud of the segments: |segment.Pose - odometry| + |radius|
 static double max_range_of_segments(const float* rays, const int32_t* seg_first, const float* seg_poses, int n_segments, const float odo[3]) {
   double m = 0.0;
+  bool nan_seen = false;  // a NaN radius or segment pose: "all rings" (rings_hint_of), whatever the other rays reach
   for (int s = 0; s < n_segments; s++) {
     const double dx = (double)seg_poses[3 * s] - odo[0], dy = (double)seg_poses[3 * s + 1] - odo[1];
     const double d0 = std::sqrt(dx * dx + dy * dy);
     for (int i = seg_first[s]; i < seg_first[s + 1]; i++) {
       const double r = d0 + std::fabs((double)rays[2 * i + 1]);
-      if (!(r <= m)) m = r;  // NaN sticks
+      if (r != r) nan_seen = true;
+      else if (r > m) m = r;
     }
   }
-  return m;
+  return nan_seen ? std::numeric_limits<double>::quiet_NaN() : m;
 }
 
 static cs_status stage_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
                               const float* cand_offsets, bool timing, CsStepArgs* out_args, const SegInput* seg = nullptr) {
-  if ((!points && !seg) || !odometry_pose || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
+  if ((!points && !seg && n_points > 0) || !odometry_pose || n_points < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
   if (!finite3(odometry_pose)) return fail(h, CS_ERR_INVALID_ARGUMENT, "odometry pose is NaN");
   if (h->pending) return fail(h, CS_ERR_STATE, "a split-phase update is in flight: call cs_update_finish first");
@@ -1195,13 +1203,13 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   hdr->n_points = n_points;
   size_t off_first = 0, off_poses = 0;
   if (seg) {  // the points slot carries the raw rays; the segment tables go behind the candidate table
-    memcpy(h->h_stage + sp.off_points, seg->rays, (size_t)n_points * 8);
+    if (n_points > 0) memcpy(h->h_stage + sp.off_points, seg->rays, (size_t)n_points * 8);
     off_first = sp.total;
     off_poses = align_up(off_first + (size_t)(seg->n_segments + 1) * 4, 16);
     sp.total = align_up(off_poses + (size_t)seg->n_segments * 12, 16);
     memcpy(h->h_stage + off_first, seg->seg_first, (size_t)(seg->n_segments + 1) * 4);
     memcpy(h->h_stage + off_poses, seg->seg_poses, (size_t)seg->n_segments * 12);
-  } else {
+  } else if (n_points > 0) {
     memcpy(h->h_stage + sp.off_points, points, (size_t)n_points * 8);
   }
   if (with_offsets) memcpy(h->h_stage + sp.off_cand, cand_offsets, (size_t)h->n_cand * 12);
@@ -1221,7 +1229,7 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
     h->stage_cur = 0;
     CS_CUDA(h, cudaMemcpyAsync(d_base, h->h_stage, sp.total, cudaMemcpyHostToDevice, h->stream));
   }
-  if (seg) {  // ScanSegmentsToCloud (:723) on the device; the step's first kernel must not start before it is complete
+  if (seg && n_points > 0) {  // ScanSegmentsToCloud (:723) on the device; the step's first kernel must not start before it is complete
     cs_status cst = launch_cloud(h, d_base + sp.off_points, d_base + off_first, d_base + off_poses, n_points,
                                  seg->n_segments, odometry_pose);
     if (cst != CS_OK) return cst;
@@ -1614,15 +1622,22 @@ cs_status cs_scanlog_create(int32_t device, int32_t n_scans, int32_t max_points,
     return fail(nullptr, CS_ERR_INVALID_ARGUMENT, "cs_scanlog_create: bad argument");
   *out = nullptr;
   if (cs_device_count() <= device) return fail(nullptr, CS_ERR_NO_DEVICE, "no such CUDA device");
-  cs_scanlog* log = new cs_scanlog();
-  log->device = device;
-  log->n_scans = n_scans;
-  log->max_points = (max_points + 1) & ~1;  // keep every scan's points 16-byte aligned
-  log->n_offsets = n_offsets;
-  log->h_hdr.assign((size_t)n_scans, CsStepHeader{});
-  log->h_points.assign((size_t)n_scans * log->max_points * 2, 0.f);
-  log->h_offsets.assign((size_t)n_scans * n_offsets * 3, 0.f);
-  log->h_max_range.assign((size_t)n_scans, 0.0);
+  cs_scanlog* log = nullptr;
+  try {  // a file header with a huge n_scans must come back as a status, not as std::bad_alloc through the C boundary
+    log = new cs_scanlog();
+    log->device = device;
+    log->n_scans = n_scans;
+    log->max_points = (max_points + 1) & ~1;  // keep every scan's points 16-byte aligned
+    log->n_offsets = n_offsets;
+    log->h_hdr.assign((size_t)n_scans, CsStepHeader{});
+    log->h_points.assign((size_t)n_scans * log->max_points * 2, 0.f);
+    log->h_offsets.assign((size_t)n_scans * n_offsets * 3, 0.f);
+    log->h_max_range.assign((size_t)n_scans, 0.0);
+  } catch (const std::exception&) {  // bad_alloc, length_error
+    delete log;
+    return fail(nullptr, CS_ERR_OUT_OF_MEMORY, "cs_scanlog_create: host allocation failed (%d scans x %d points, %d offsets)", n_scans,
+                max_points, n_offsets);
+  }
   cudaSetDevice(device);
   bool ok = cudaMalloc(&log->d_hdr, sizeof(CsStepHeader) * n_scans) == cudaSuccess &&
             cudaMalloc(&log->d_points, sizeof(float2) * (size_t)n_scans * log->max_points) == cudaSuccess &&
@@ -1767,7 +1782,14 @@ cs_status cs_scanlog_load(int32_t device, const char* path, cs_scanlog** out) {
   cs_scanlog* log = nullptr;
   st = cs_scanlog_create(device, (int32_t)hd.n_scans, (int32_t)hd.max_points, (int32_t)hd.n_offsets, &log);
   if (st != CS_OK) return st;
-  std::vector<float> pts((size_t)hd.max_points * 2), off((size_t)hd.n_offsets * 3);
+  std::vector<float> pts, off;
+  try {
+    pts.resize((size_t)hd.max_points * 2);
+    off.resize((size_t)hd.n_offsets * 3);
+  } catch (const std::exception&) {
+    cs_scanlog_destroy(log);
+    return fail(nullptr, CS_ERR_OUT_OF_MEMORY, "cs_scanlog_load: host allocation failed");
+  }
   for (uint32_t k = 0; k < hd.n_scans; k++) {
     int32_t n = 0;
     float odo[3];
@@ -1868,6 +1890,8 @@ struct cs_batch {
   cudaStream_t stream = nullptr;
   bool own_stream = false, tiled = true;
   int size = 0, pitch_tiles = 0, max_points = 0, n_cand = 0;
+  int user_max_points = 0;  // the caller's cfg.max_points: stride of the caller's `points` array (max_points above is the
+                            // internal stride of the staging / device blocks, rounded up to even for 16-byte alignment)
   float scale = 0.f;
   size_t map_cells = 0;
   std::vector<CsSession> hs;
@@ -2003,6 +2027,7 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   b->tiled = !(c0.flags & CS_FLAG_ROW_MAJOR_MAP);
   b->size = c0.hole_map_size;
   b->pitch_tiles = (b->size + 7) / 8;
+  b->user_max_points = max_points;
   b->max_points = (max_points + 1) & ~1;
   b->n_cand = (int)n_cand;
   b->scale = (float)c0.hole_map_size / c0.physical_map_size;
@@ -2159,21 +2184,25 @@ cs_status batch_stage_and_launch(cs_batch* b, uint8_t* h_stage, uint8_t* d_stage
   const bool with_offsets = cand_offsets != nullptr && do_search;
   int max_n = 0;
   double max_range = 0.0;
+  bool range_nan = false;  // a NaN point anywhere in the batch: every ring is launched (NaN does not order, so it is tracked apart)
   for (int j = 0; j < b->n; j++) {
     const int np = n_points[j];
-    if (np <= 0 || np > b->max_points) return bfail(b, CS_ERR_CAPACITY, "session %d: n_points %d outside 1..%d", j, np, b->max_points);
+    if (np <= 0 || np > b->user_max_points)
+      return bfail(b, CS_ERR_CAPACITY, "session %d: n_points %d outside 1..%d", j, np, b->user_max_points);
     const float* odo = odometry + 3 * (size_t)j;
     if (!finite3(odo)) return bfail(b, CS_ERR_INVALID_ARGUMENT, "session %d: odometry pose is NaN", j);
     CsStepHeader* hdr = reinterpret_cast<CsStepHeader*>(h_stage) + j;
     memset(hdr, 0, sizeof(CsStepHeader));
     hdr->odo[0] = odo[0]; hdr->odo[1] = odo[1]; hdr->odo[2] = odo[2];
     hdr->n_points = np;
-    const float* src = points + (size_t)j * b->max_points * 2;
+    const float* src = points + (size_t)j * b->user_max_points * 2;  // the caller's stride is the caller's cfg.max_points
     memcpy(h_stage + b->off_points + (size_t)j * b->max_points * 8, src, (size_t)np * 8);
     const double r = max_range_of(src, np);
-    if (!(r <= max_range)) max_range = r;
+    if (r != r) range_nan = true;
+    else if (r > max_range) max_range = r;
     if (np > max_n) max_n = np;
   }
+  if (range_nan) max_range = std::numeric_limits<double>::quiet_NaN();
   if (with_offsets) memcpy(h_stage + b->off_cand, cand_offsets, (size_t)b->n * b->n_cand * 12);
   const size_t bytes = with_offsets ? b->stage_bytes : b->off_cand;
   CS_BCUDA(b, cudaMemcpyAsync(d_stage, h_stage, bytes, cudaMemcpyHostToDevice, b->stream));
@@ -2234,12 +2263,26 @@ cs_status cs_batch_submit(cs_batch* b, const float* points, const int32_t* n_poi
   if (b->pipe_submitted - b->pipe_collected >= 2u)
     return bfail(b, CS_ERR_STATE, "cs_batch_submit: two submitted steps are waiting for cs_batch_collect");
   const int slot = (int)(b->pipe_submitted & 1u);
-  if (!b->pipe_h_stage[slot]) {
-    CS_BCUDA(b, cudaHostAlloc(&b->pipe_h_stage[slot], b->stage_bytes, cudaHostAllocDefault));
-    CS_BCUDA(b, cudaMalloc(&b->pipe_d_stage[slot], b->stage_bytes));
-    CS_BCUDA(b, cudaMalloc(&b->pipe_d_results[slot], sizeof(CsDevResult) * (size_t)b->n));
-    CS_BCUDA(b, cudaHostAlloc(&b->pipe_h_results[slot], sizeof(CsDevResult) * (size_t)b->n, cudaHostAllocDefault));
-    CS_BCUDA(b, cudaEventCreateWithFlags(&b->pipe_done[slot], cudaEventDisableTiming));
+  if (!b->pipe_done[slot]) {  // first use of the slot: all five resources or none (the event, created last, is the guard)
+    uint8_t *hs = nullptr, *ds = nullptr;
+    CsDevResult *dr = nullptr, *hr = nullptr;
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaHostAlloc(&hs, b->stage_bytes, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&ds, b->stage_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&dr, sizeof(CsDevResult) * (size_t)b->n);
+    if (e == cudaSuccess) e = cudaHostAlloc(&hr, sizeof(CsDevResult) * (size_t)b->n, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      if (hs) cudaFreeHost(hs);
+      if (hr) cudaFreeHost(hr);
+      cudaFree(ds);
+      cudaFree(dr);
+      cudaGetLastError();
+      return bfail(b, e == cudaErrorMemoryAllocation ? CS_ERR_OUT_OF_MEMORY : CS_ERR_CUDA, "cs_batch_submit: staging slot: %s",
+                   cudaGetErrorString(e));
+    }
+    b->pipe_h_stage[slot] = hs; b->pipe_d_stage[slot] = ds; b->pipe_d_results[slot] = dr; b->pipe_h_results[slot] = hr;
+    b->pipe_done[slot] = ev;
   }
   // The slot's pinned block was the source of the copy two submits ago; that step has been collected (its pipe_done event,
   // recorded after the copy, was waited for), so the block is free.  The device block is protected by stream order.

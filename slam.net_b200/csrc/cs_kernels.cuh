@@ -165,6 +165,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned long long s2_seed;
   int s2_size, s2_pitch_tiles;
   float s2_scale, s2_sigma_xy, s2_sigma_theta;
+  int empty_cloud;               // 1: the scan has no points and the step searches: no search kernel ran, the arg-min is
+                                 // (int.MaxValue, searchPose) by definition (:251-258, :630-648)
   int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values
                                  // above come from CsSession instead, hdr / points / cand / result are strided per session
 };
@@ -478,7 +480,7 @@ __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr
   if (d) d[0] = cs_globaltimer();
   const bool need_key = a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search;
   unsigned long long key = 0ull;
-  if (need_key) key = atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
+  if (need_key) key = a.empty_cloud ? (0x7fffffffull << 32) : atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
   CsGlue g;
   if (have_guess && need_key) {
     // The arg-min as this thread last saw it is almost always the final one: the glue arithmetic runs on it while

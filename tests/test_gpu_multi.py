@@ -212,3 +212,49 @@ def test_batch_submit_collect_pipeline_equals_blocking_updates():
     assert np.array_equal(a.poses(), b.poses())
     a.close()
     b.close()
+
+
+def test_batch_odd_max_points_stride_is_the_callers():
+    """the stride of the caller's points array is cfg.max_points as passed — also when it is odd (a 361-ray
+    lidar); only the internal staging stride is rounded up.  Every session j >= 1 must read its own points."""
+    n_sess, n_scans, P, size, phys, iters, threads = 4, 9, 181, 256, 40.0, 40, 2
+    rps = [synth.make_replay(n_scans, P, phys, seed=350 + j) for j in range(n_sess)]
+    sxy, sth = [0.05, 0.07, 0.09, 0.11], [0.10, 0.11, 0.12, 0.13]
+    b = sn.Batch(n_sess, phys, size, [rp.odometry[0] for rp in rps], sxy, sth, iters, threads, max_points=P)
+    assert b.max_points == P and P % 2 == 1
+    os_ = [orc.Processor(phys, size, rps[j].odometry[0], sxy[j], sth[j], iters, threads) for j in range(n_sess)]
+    for k in range(n_scans):
+        offs = np.stack([synth.candidate_offsets(370 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        assert all(rps[j].points[k].shape[0] == P for j in range(n_sess))  # full rows: a shifted stride would read a neighbour's points
+        res = b.update([rps[j].points[k] for j in range(n_sess)], np.stack([rps[j].odometry[k] for j in range(n_sess)]), offs)
+        for j in range(n_sess):
+            os_[j].update(rps[j].points[k], rps[j].odometry[k], offs[j])
+            assert np.array_equal(res[j].pose, os_[j].pose), (k, j)
+    sums = b.map_checksums()
+    for j in range(n_sess):
+        assert int(sums[j]) == sn.host_map_checksum(np.array(os_[j].map.pixels), size), j
+    b.close()
+
+
+def test_batch_nan_point_in_one_session_does_not_truncate_the_others():
+    """the rings a batch is launched with are the maximum over its sessions; a NaN point in one session
+    (which the reference handles through cvttss2si) must neither hide an earlier, longer scan nor be forgotten itself."""
+    n_sess, n_scans, P, size, phys, iters, threads = 3, 8, 120, 512, 40.0, 24, 1
+    rp = synth.make_replay(n_scans, P, phys, seed=390)
+    sxy, sth = [0.05] * n_sess, [0.1] * n_sess
+    b = sn.Batch(n_sess, phys, size, rp.odometry[0], sxy, sth, iters, threads, max_points=P)
+    os_ = [orc.Processor(phys, size, rp.odometry[0], sxy[j], sth[j], iters, threads) for j in range(n_sess)]
+    for k in range(n_scans):
+        long_pts = rp.points[k].copy()                    # session 0: the full-range scan
+        nan_pts = (rp.points[k] * 0.3).astype(np.float32)  # session 1: short rays and one NaN point
+        nan_pts[3, 0] = np.nan
+        short_pts = (rp.points[k] * 0.1).astype(np.float32)  # session 2: very short rays (the last r the reduction sees)
+        pts = [long_pts, nan_pts, short_pts]
+        offs = np.stack([synth.candidate_offsets(395 + j, k, iters * threads, sxy[j], sth[j]) for j in range(n_sess)])
+        res = b.update(pts, np.tile(rp.odometry[k], (n_sess, 1)), offs)
+        for j in range(n_sess):
+            os_[j].update(pts[j], rp.odometry[k], offs[j])
+            assert np.array_equal(res[j].pose, os_[j].pose), (k, j)
+    for j in range(n_sess):
+        assert np.array_equal(b.map_download(j), np.array(os_[j].map.pixels)), j
+    b.close()

@@ -88,3 +88,35 @@ def test_multi_segment_update_replay_bit_exact(search):
     assert np.array_equal(p.map_download(), np.array(o.map.pixels))
     assert np.array_equal(p.obstacle_map_download(), o.obstacle_map.pixels)
     p.close()
+
+
+def test_update_with_segments_that_carry_no_rays_advances_the_state_like_the_reference():
+    """Update(List<ScanSegment>) with non-empty segments whose Rays lists are empty still runs in the
+    reference (:719-747): lastOdometryPose / scanCount advance, every distance is int.MaxValue, searchPose wins.  The drop-in
+    must do the same (and the next scan's searchPose must agree with the oracle's)."""
+    n_scans, P, size, phys, iters, threads = 12, 90, 256, 40.0, 30, 2
+    rp = synth.make_replay(n_scans, P, phys, seed=77)
+    p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P)
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    ang = (np.arange(P) * (2 * np.pi / P)).astype(np.float32)
+    empty = np.zeros((0, 2), dtype=np.float32)
+    for k in range(n_scans):
+        off = synth.candidate_offsets(78, k, iters * threads, 0.1, 0.17)
+        odo = rp.odometry[k]
+        if k in (2, 7, 8):  # one map-only scan and two searched scans arrive without a single ray
+            segs = [sn.ScanSegment(Rays=empty, Pose=odo), sn.ScanSegment(Rays=empty, Pose=odo, IsLast=True)]
+            cloud = empty
+        else:
+            rad = np.hypot(rp.points[k][:, 0], rp.points[k][:, 1]).astype(np.float32)
+            n = rad.shape[0]
+            segs = [sn.ScanSegment(Rays=np.stack([ang[:n], rad], axis=1), Pose=odo, IsLast=True)]
+            cloud = orc.segment_to_cloud(segs[0].rays_array(), np.asarray(odo, dtype=np.float32), np.asarray(odo, dtype=np.float32))
+        r = p.update_segments(segs, off)
+        o.update(cloud, odo, off)
+        assert np.array_equal(r.pose, o.pose), k
+        if k >= 5:
+            assert (r.distance, r.index) == (o.last_distance, o.last_index), k
+            if k in (7, 8):
+                assert (r.distance, r.index) == (2147483647, 0)
+    assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+    p.close()
