@@ -184,129 +184,110 @@ def latest_traffic(kernel):
     return None, None
 
 
-def run_sharded(args, wl, metric, config, rank, world, local, K, W):
-    """cfg4 (candidate split, strong scaling, one 8-byte exchange per scan) and cfg5 (session batches, strong
-    scaling over a fixed set of 1024 sessions, no collective)."""
+def cfg5_session_params(s, seed):
+    """Parameter grid of session s: sigma_xy, sigma_theta, Quality, HoleWidth, seed."""
+    return (0.05 + 0.025 * (s % 5), 0.0873 + 0.0436 * ((s // 5) % 4), 30 + 20 * ((s // 20) % 6), 0.4 + 0.2 * ((s // 120) % 4), seed + s)
+
+
+def measure_cfg5(args, rank, world, local, K, W, n_sessions=None, sub_batches=0, e2e=True, parity_sessions=3):
+    """configs[4]: n_sessions independent CoreSLAM replays (cfg1 geometry, production mode) sharded session i -> rank i mod world,
+    strong scaling, no collective.  Returns (on every rank) the reduced numbers; `parity` = pose and map checksum of a sample
+    of sessions after the timed steps equal the CPU oracle's (fed the host twin of each session's Philox stream)."""
     import torch
     import torch.distributed as dist
     import slam.net_b200 as sn
     from slam.net_b200 import _native as N
     from slam.net_b200 import parallel as par
+    from slam.net_b200 import synth
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    wl = WORKLOADS["cfg5"]
+    P = wl["points"]
+    n_cand = wl["threads"] * wl["iters"]
+    n_sessions = n_sessions or wl["sessions"]
+    Ke = min(K, 20) if e2e else 0
+    n_total = PRIME_SCANS + W + K + (2 * Ke + 2 if e2e else 0)
+    rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed)  # same scans on every rank
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    P = wl["points"]
-    n_cand = wl["threads"] * wl["iters"]
-    n_total = PRIME_SCANS + W + K + (2 * min(K, 20) + 2 if args.workload == "cfg5" else 0)  # cfg5: + the scans of the two e2e passes
-    from slam.net_b200 import synth
-    rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed)  # same scans on every rank
+    mine = par.session_shard(n_sessions, world, rank)
+    n_sub = max(1, min(sub_batches if sub_batches > 0 else 1, max(len(mine), 1)))
+    subs = [mine[i::n_sub] for i in range(n_sub)]
     stream = torch.cuda.Stream()
+    streams = [stream] + [torch.cuda.Stream() for _ in range(n_sub - 1)]
     sampler = ClockSampler(local)
-    extra = {}
+    out = {}
     with torch.cuda.stream(stream):
-        if args.workload == "cfg4":
-            proc = sn.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"],
-                                device=local, max_points=P, seed=args.seed, stream=stream.cuda_stream)
-            ss = par.SplitSearch(proc, rank, world, local, torch_stream=stream)
-            for k in range(PRIME_SCANS + W):
-                ss.update(rp.points[k], rp.odometry[k], None)
-            proc.sync()
-            launches0 = proc.launch_count()
-            lat = np.zeros(K)
-            barrier()
-            sampler.start()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            t0 = time.perf_counter()
+        batches = []
+        for part, st in zip(subs, streams):
+            prm = [cfg5_session_params(s, args.seed) for s in part]
+            b = sn.Batch(len(part), wl["phys"], wl["size"], rp.odometry[0], np.array([q[0] for q in prm], dtype=np.float32),
+                         np.array([q[1] for q in prm], dtype=np.float32), wl["iters"], wl["threads"], device=local,
+                         max_points=P, seeds=[q[4] for q in prm], stream=st.cuda_stream)
+            for j, q in enumerate(prm):
+                b.set_params(j, q[2], q[3])
+            batches.append(b)
+        log = sn.ScanLog(n_total, P, n_offsets=0, device=local)
+        for k in range(n_total):
+            log.set(k, rp.points[k], rp.odometry[k])
+        log.upload()
+        torch.cuda.synchronize()  # the log is read from every stream
+        for b in batches:
+            b.replay(log, 0, PRIME_SCANS + W, want_results=False)
+        launches0 = sum(b.launch_count() for b in batches)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = [torch.cuda.Event() for _ in streams[1:]]
+        e0.record(stream)
+        for st in streams[1:]:
+            st.wait_event(e0)
+        if n_sub == 1:
+            batches[0].replay(log, PRIME_SCANS + W, K, want_results=False)
+        else:  # steps are queued round-robin so that no stream runs ahead of another by more than one step
             for i in range(K):
-                k = PRIME_SCANS + W + i
-                ta = time.perf_counter()
-                r = ss.update(rp.points[k], rp.odometry[k], None)
-                lat[i] = time.perf_counter() - ta
-            e1.record(stream)
-            proc.sync()
-            barrier()
-            wall = time.perf_counter() - t0
-            dev_ms = e0.elapsed_time(e1)
-            launches = proc.launch_count() - launches0
-            lookups_per_step = (n_cand + 1) * P  # whole job: all ranks together evaluate every candidate once
-            work_scale = 1
-            scaling = "strong"
-            extra = {"scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3)},
-                     "final_pose": [float(x) for x in r.pose], "map_checksum": int(proc.map_checksum()),
-                     "exchange": "torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world,
-                     "mode": "production (on-device Philox candidates; nothing but the scan is uploaded)"}
-            h2d, d2h = 64 + 8 * P, 32
-            e2e_wall, e2e_steps = wall, K  # the timed loop already goes through the host-buffer call
-            proc.close()
-        else:
-            n_sessions = args.sessions if args.sessions > 0 else wl["sessions"]
-            mine = par.session_shard(n_sessions, world, rank)
-            # The rank's sessions run as `n_sub` independent batches on their own streams (sessions share nothing): with few
-            # sessions per GPU one batch's kernel tails (the last rings of its slowest session) are filled by the other's work.
-            # (Measured at 128 .. 1024 sessions per GPU: no gain — profiles/r1m_cfg5_small_batches.txt — so one batch is the default.)
-            n_sub = args.sub_batches if args.sub_batches > 0 else 1
-            n_sub = max(1, min(n_sub, len(mine)))
-            subs = [mine[i::n_sub] for i in range(n_sub)]
-            streams = [stream] + [torch.cuda.Stream() for _ in range(n_sub - 1)]
-            batches = []
-            for part, st in zip(subs, streams):
-                # parameter grid over sigma_xy, sigma_theta, HoleWidth, Quality, seed (SURVEY 8d)
-                sxy = np.array([0.05 + 0.025 * (s % 5) for s in part], dtype=np.float32)
-                sth = np.array([0.0873 + 0.0436 * ((s // 5) % 4) for s in part], dtype=np.float32)
-                b = sn.Batch(len(part), wl["phys"], wl["size"], rp.odometry[0], sxy, sth, wl["iters"], wl["threads"], device=local,
-                             max_points=P, seeds=[args.seed + s for s in part], stream=st.cuda_stream)
-                for j, s in enumerate(part):
-                    b.set_params(j, 30 + 20 * ((s // 20) % 6), 0.4 + 0.2 * ((s // 120) % 4))
-                batches.append(b)
-            log = sn.ScanLog(n_total, P, n_offsets=0, device=local)
-            for k in range(n_total):
-                log.set(k, rp.points[k], rp.odometry[k])
-            log.upload()
-            torch.cuda.synchronize()  # the log is read from every stream
-            for b in batches:
-                b.replay(log, 0, PRIME_SCANS + W, want_results=False)
-            launches0 = sum(b.launch_count() for b in batches)
-            barrier()
-            sampler.start()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            done = [torch.cuda.Event() for _ in streams[1:]]
-            t0 = time.perf_counter()
-            e0.record(stream)
-            for st in streams[1:]:
-                st.wait_event(e0)
-            # steps are queued round-robin so that neither stream runs ahead of the other by more than one step
-            if n_sub == 1:
-                batches[0].replay(log, PRIME_SCANS + W, K, want_results=False)
-            else:
-                for i in range(K):
-                    for b in batches:
-                        b.replay(log, PRIME_SCANS + W + i, 1, want_results=False)
-            for st, ev in zip(streams[1:], done):
-                ev.record(st)
-                stream.wait_event(ev)
-            e1.record(stream)
-            barrier()
-            wall = time.perf_counter() - t0
-            dev_ms = e0.elapsed_time(e1)
-            launches = sum(b.launch_count() for b in batches) - launches0
-            lookups_per_step = (n_cand + 1) * P * n_sessions  # whole job per step: every session advances one scan
-            scaling = "strong"
-            poses = np.concatenate([b.poses() for b in batches], axis=0)
-            # e2e: the same step through cs_batch_update with HOST buffers — every session's scan (here: the same scan for
-            # all, but uploaded per session as independent replays would be) goes host -> device inside the timed region
-            # and every session's result record comes back.
-            Ke = min(K, 20)
+                for b in batches:
+                    b.replay(log, PRIME_SCANS + W + i, 1, want_results=False)
+        for st, ev in zip(streams[1:], done):
+            ev.record(st)
+            stream.wait_event(ev)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        dev_ms = e0.elapsed_time(e1)
+        launches = sum(b.launch_count() for b in batches) - launches0
+        poses = np.concatenate([b.poses() for b in batches], axis=0) if mine else np.zeros((0, 3), dtype=np.float32)
+        sums = np.concatenate([b.map_checksums() for b in batches], axis=0) if mine else np.zeros(0, dtype=np.uint64)
+        order = [s for part in subs for s in part]
+
+        # ---- parity: a sample of sessions against the CPU oracle (the oracle only checks; it is not timed here)
+        parity_ok, checked = True, []
+        if parity_sessions > 0:
+            from oracle import oracle as orc
+            sample = sorted(set([0, n_sessions // 2, n_sessions - 1][:parity_sessions]))
+            for s in sample:
+                if s not in order:
+                    continue
+                sxy, sth, q, hw, seed = cfg5_session_params(s, args.seed)
+                o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], np.float32(sxy), np.float32(sth), wl["iters"], wl["threads"])
+                o.quality, o.hole_width = q, np.float32(hw)
+                wk = orc.Worker(1)
+                for k in range(PRIME_SCANS + W + K):
+                    off = sn.philox_offsets(seed, k, n_cand, np.float32(sxy), np.float32(sth)) if k >= PRIME_SCANS else None
+                    o.update(rp.points[k], rp.odometry[k], off, worker=wk)
+                wk.close()
+                j = order.index(s)
+                ok = bool(np.array_equal(poses[j], o.pose) and int(sums[j]) == int(sn.host_map_checksum(np.array(o.map.pixels), wl["size"])))
+                parity_ok = parity_ok and ok
+                checked.append(s)
+
+        e2e_wall, e2e_blocking_wall = 0.0, 0.0
+        if e2e and mine:
+            # the same step through the C ABI with HOST buffers: every session's scan goes host -> device inside the timed
+            # region and every session's result record comes back
             L = sn.lib()
             fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
             packed = []
@@ -330,9 +311,7 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
                         raise RuntimeError("cs_batch_update failed: %d" % st)
             barrier()
             e2e_blocking_wall = time.perf_counter() - t0e
-            # the same through cs_batch_submit / cs_batch_collect: step k+1 is staged and queued before step k's results
-            # are collected, so the host staging overlaps the device's work; still every scan goes up and every record
-            # comes back, every step
+
             def submit(i):
                 for b, (per_step, res) in zip(batches, packed):
                     pts, npts, odo = per_step[i]
@@ -359,39 +338,164 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
             collect()
             barrier()
             e2e_wall = time.perf_counter() - t0e
-            e2e_steps = Ke
-            extra = {"sessions": n_sessions, "sessions_this_rank": len(mine), "batches_per_rank": n_sub,
-                     "mode": "production (on-device Philox candidates), shared device-resident scan log",
-                     "pose_spread_m": float(np.ptp(poses[:, 0]) + np.ptp(poses[:, 1])),
-                     "l2": "per-rank working set %d maps x %.1f MB >> L2" % (len(mine), wl["size"] ** 2 * 2 / 1e6)}
-            h2d, d2h = n_sessions * (8 * P + 12 + 4), n_sessions * 32  # whole job: points + odometry + count in, result record out
-            extra["e2e_api"] = ("cs_batch_submit + cs_batch_collect (C ABI, host buffers: every session's scan uploaded each step, every "
-                                "result record read back; step k+1 is submitted before step k is collected), %d steps" % Ke)
-            extra["e2e_blocking"] = {"api": "cs_batch_update (blocking call), %d steps" % Ke, "ms_per_step": e2e_blocking_wall / Ke * 1e3,
-                                     "sessions_per_s_this_rank": len(mine) * Ke / e2e_blocking_wall}
-            log.close()
-            for b in batches:
-                b.close()
-    clocks = sampler.stop()
-    t_all = torch.tensor([dev_ms, e2e_wall * 1e3], dtype=torch.float64, device="cuda")
+        elif e2e:
+            barrier(); barrier(); barrier(); barrier()
+        log.close()
+        for b in batches:
+            b.close()
+    t_all = torch.tensor([dev_ms, e2e_wall * 1e3, e2e_blocking_wall * 1e3, 0.0 if parity_ok else 1.0, float(len(checked)), float(launches)],
+                         dtype=torch.float64, device="cuda")
+    t_sum = t_all.clone()
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_sum, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, e2e_blk_max, bad, _, _ = (float(x) for x in t_all.tolist())
+    n_checked, launches_all = int(t_sum[4].item()), int(t_sum[5].item())
+    lookups_per_step = (n_cand + 1) * P * n_sessions
+    out = {"sessions": n_sessions, "sessions_this_rank": len(mine), "batches_per_rank": n_sub, "steps": K, "warmup": W,
+           "ms_per_step": dev_ms_max / K, "sessions_per_s": n_sessions * K / (dev_ms_max * 1e-3),
+           "lookups_per_s": lookups_per_step * K / (dev_ms_max * 1e-3), "scaling": "strong",
+           "parity": {"sessions_checked": n_checked, "pose_and_map_checksum_equal_oracle": bool(bad == 0.0 and n_checked > 0),
+                      "how": "sessions 0, n/2, n-1 replayed by the CPU oracle fed the host twin of their Philox streams"},
+           "gpu_launches": launches_all, "clocks": clocks,
+           "pose_spread_m": float(np.ptp(poses[:, 0]) + np.ptp(poses[:, 1])) if len(poses) else 0.0,
+           "mode": "production (on-device Philox candidates), shared device-resident scan log",
+           "l2": "per-rank working set %d maps x %.1f MB >> L2" % (len(mine), wl["size"] ** 2 * 2 / 1e6)}
+    if e2e:
+        out["e2e"] = {"value": lookups_per_step * Ke / (e2e_ms_max * 1e-3), "unit": "lookups/s", "ms_per_step": e2e_ms_max / Ke,
+                      "sessions_per_s": n_sessions * Ke / (e2e_ms_max * 1e-3),
+                      "h2d_bytes_per_step": n_sessions * (8 * P + 12 + 4), "d2h_bytes_per_step": n_sessions * 32,
+                      "api": "cs_batch_submit + cs_batch_collect (C ABI, host buffers: every session's scan uploaded each step, every "
+                             "result record read back; step k+1 is submitted before step k is collected), %d steps" % Ke,
+                      "blocking": {"api": "cs_batch_update (blocking call), %d steps" % Ke, "ms_per_step": e2e_blk_max / Ke}}
+    return out
+
+
+def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
+    """configs[3]: one session, 8192x8192 map (128 MB), 65536 candidates split over the ranks (flat indices
+    [g*C/G, (g+1)*C/G)), replicated map, one 8-byte MIN exchange per scan; production mode.  `parity`: every rank ends with the
+    same pose and map checksum, equal to an unsplit handle's on rank 0 and (oracle_check) to the CPU oracle's."""
+    import torch
+    import torch.distributed as dist
+    import slam.net_b200 as sn
+    from slam.net_b200 import parallel as par
+    from slam.net_b200 import synth
+
+    wl = WORKLOADS["cfg4"]
+    P = wl["points"]
+    n_cand = wl["threads"] * wl["iters"]
+    n_total = PRIME_SCANS + W + K
+    rp = synth.make_replay(n_total, P, wl["phys"], seed=args.seed)  # same scans on every rank
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    sampler = ClockSampler(local)
+    with torch.cuda.stream(stream):
+        proc = sn.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"],
+                            device=local, max_points=P, seed=args.seed, stream=stream.cuda_stream)
+        ss = par.SplitSearch(proc, rank, world, local, torch_stream=stream)
+        for k in range(PRIME_SCANS + W):
+            ss.update(rp.points[k], rp.odometry[k], None)
+        proc.sync()
+        launches0 = proc.launch_count()
+        lat = np.zeros(K)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for i in range(K):
+            k = PRIME_SCANS + W + i
+            ta = time.perf_counter()
+            r = ss.update(rp.points[k], rp.odometry[k], None)
+            lat[i] = time.perf_counter() - ta
+        e1.record(stream)
+        proc.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        dev_ms = e0.elapsed_time(e1)
+        launches = proc.launch_count() - launches0
+        pose = np.array(r.pose, dtype=np.float32)
+        checksum = int(proc.map_checksum())
+        proc.close()
+        # rank 0: the same replay on one unsplit handle (what N = 1 computes), and the CPU oracle
+        ref_ok, oracle_ok = None, None
+        if rank == 0:
+            if world > 1:
+                q = sn.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"],
+                                 device=local, max_points=P, seed=args.seed, stream=stream.cuda_stream)
+                for k in range(n_total):
+                    rq = q.update(rp.points[k], rp.odometry[k], None)
+                ref_ok = bool(np.array_equal(rq.pose, pose) and int(q.map_checksum()) == checksum)
+                q.close()
+            if oracle_check:
+                from oracle import oracle as orc
+                o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"])
+                wk = orc.Worker(pow2_threads(n_cand, os.cpu_count() or 1))
+                for k in range(n_total):
+                    off = sn.philox_offsets(args.seed, k, n_cand, SIGMA_XY, SIGMA_THETA) if k >= PRIME_SCANS else None
+                    o.update(rp.points[k], rp.odometry[k], off, worker=wk)
+                wk.close()
+                oracle_ok = bool(np.array_equal(o.pose, pose) and int(sn.host_map_checksum(np.array(o.map.pixels), wl["size"])) == checksum)
+    # all ranks: same pose, same map
+    sig = torch.tensor([float(pose[0]), float(pose[1]), float(pose[2]), float(checksum & 0xFFFFFF), float((checksum >> 24) & 0xFFFFFF),
+                        float(checksum >> 48)], dtype=torch.float64, device="cuda")
+    lo, hi = sig.clone(), sig.clone()
+    t_all = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    ranks_equal = bool(torch.equal(lo, hi))
     dev_ms_max, wall_ms_max = (float(x) for x in t_all.tolist())
+    lookups_per_step = (n_cand + 1) * P  # whole job: all ranks together evaluate every candidate once
+    return {"candidates": n_cand + 1, "points": P, "map": "%dx%d u16 (%.0f MB, replicated)" % (wl["size"], wl["size"], wl["size"] ** 2 * 2 / 1e6),
+            "steps": K, "warmup": W, "us_per_update": dev_ms_max / K * 1e3, "ms_per_step": dev_ms_max / K,
+            "lookups_per_s": lookups_per_step * K / (dev_ms_max * 1e-3), "scaling": "strong",
+            "e2e": {"value": lookups_per_step * K / (wall_ms_max * 1e-3), "unit": "lookups/s", "ms_per_step": wall_ms_max / K,
+                    "h2d_bytes_per_step": 64 + 8 * P, "d2h_bytes_per_step": 32,
+                    "api": "cs_update_begin -> exchange -> cs_update_finish with host points (the timed loop itself)"},
+            "scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3)},
+            "exchange": "torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world,
+            "nvlink_bytes_per_step": 8 * max(world - 1, 0) * 2,
+            "parity": {"pose_and_map_checksum_equal_on_all_ranks": ranks_equal, "equal_to_unsplit_handle_rank0": ref_ok,
+                       "equal_to_cpu_oracle": oracle_ok},
+            "final_pose": [float(x) for x in pose], "map_checksum": checksum, "gpu_launches": int(launches), "clocks": clocks,
+            "mode": "production (on-device Philox candidates; nothing but the scan is uploaded)"}
+
+
+def run_sharded(args, wl, metric, config, rank, world, local, K, W):
+    """--workload cfg4 / cfg5 as the line's headline (the default cfg2 line carries both as its `sharded` block)."""
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    P = wl["points"]
+    if args.workload == "cfg4":
+        m = measure_cfg4(args, rank, world, local, K, W)
+    else:
+        m = measure_cfg5(args, rank, world, local, K, W, n_sessions=args.sessions if args.sessions > 0 else None,
+                         sub_batches=args.sub_batches)
     if rank == 0:
-        value = lookups_per_step * K / (dev_ms_max * 1e-3)
+        value = m["lookups_per_s"]
+        e2e = m.pop("e2e")
         line = {"metric": metric, "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32 transform -> u16 gather -> i64 sum", "data": "synthetic",
-                "config": dict(config, mode=extra.pop("mode"), timing="CUDA events on the launching stream around the K steps; max over ranks"),
-                "candidate_poses_per_s": value / P, "clocks": clocks,
-                "e2e": {"value": lookups_per_step * e2e_steps / (wall_ms_max * 1e-3), "unit": "lookups/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": wall_ms_max / e2e_steps},
-                "gpu_launches": int(launches)}
-        if args.workload == "cfg5":
-            line["sessions_per_s"] = extra["sessions"] * K / (dev_ms_max * 1e-3)
-            line["e2e"]["api"] = extra.pop("e2e_api")
-            line["e2e"]["sessions_per_s"] = extra["sessions"] * e2e_steps / (wall_ms_max * 1e-3)
-        line.update(extra)
+                "config": dict(config, mode=m.pop("mode")),
+                "timing": "CUDA events on the launching stream around the K steps; max over ranks",
+                "candidate_poses_per_s": value / P, "clocks": m.pop("clocks"), "e2e": e2e, "gpu_launches": m.pop("gpu_launches")}
+        line.update(m)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

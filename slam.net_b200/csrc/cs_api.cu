@@ -22,6 +22,7 @@
 #include "../../include/coreslam_b200.h"
 #include "cs_kernels.cuh"
 #include "cs_obstacle.cuh"
+#include "cs_wedge.cuh"
 
 static_assert(sizeof(CsDevResult) == sizeof(cs_result), "cs_result layout");
 static_assert(sizeof(cs_config) == 72, "cs_config layout (ctypes / P/Invoke mirror it)");
@@ -64,6 +65,11 @@ struct cs_processor {
   int ray_stride = 0, batch_stride = 0;
   int* d_ray_dbg = nullptr;
   int* d_distances = nullptr;
+  // wedge integration scratch (CsSession::w_*)
+  int2* d_w_rk = nullptr;
+  float2* d_w_bkey = nullptr;
+  int* d_w_alive = nullptr;
+  int w_slot = 0;
   long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
 
@@ -262,6 +268,7 @@ double max_range_of(const float* points, int n) {
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
+  int integrate = 0, w_general = 0, w_blocks = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -271,6 +278,9 @@ struct Tune {
     s2_sort_one_block = geti("CS_TUNE_S2_SORT_ONE_BLOCK");  // 1: sort generated candidates with one block whenever they fit
     copy_stream = geti("CS_TUNE_COPY_STREAM");  // -1: cs_update stages its inputs on the main stream
     s2_min_cand = geti("CS_TUNE_S2_MIN_CAND");  // fewest candidates the slab search is used for
+    integrate = geti("CS_TUNE_INTEGRATE");      // 1: the rings kernel draws the scan instead of the wedge kernel (A/B runs)
+    w_general = geti("CS_TUNE_W_GENERAL");      // 1: every task of the wedge kernel takes its general path (tests)
+    w_blocks = geti("CS_TUNE_W_BLOCKS");        // blocks of the wedge kernel per session
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
     ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
@@ -391,6 +401,7 @@ struct LaunchCtx {
   int n_sessions;
   uint64_t* launches;
   unsigned* step_counter;  // source of CsStepArgs::step_id
+  int* w_slot = nullptr;   // which half of CsSession::w_alive the next drawn step counts into
   long long* diag;
   int diag_rings;
   cudaEvent_t ev_pose;   // optional: recorded once the pose is out
@@ -435,7 +446,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int rings, int phases) {
   // An empty cloud (Update with segments that carry no rays): CalculateDistance returns int.MaxValue for every pose (:251-258),
   // so searchPose wins (:630-648, strict <) without a single lookup: no search kernel, the glue decodes (MaxValue, index 0).
-  a.empty_cloud = (a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search && n_points == 0) ? 1 : 0;
+  // (a.empty_cloud is set by the caller that knows the scan: stage_update.)
   const bool searching = (a.step_mode != CS_STEP_INTEGRATE_ONLY) && a.do_search && !a.empty_cloud;
   const bool draws = a.step_mode != CS_STEP_SEARCH_ONLY && n_points > 0;
   const bool fused = searching && phases == CS_PHASE_ALL;
@@ -513,7 +524,27 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   }
   // the pose is out once this kernel has finished
   if (c.ev_pose) cudaEventRecord(c.ev_pose, c.stream);
-  if (draws) {
+  if (draws && tune().integrate != 1 && c.w_slot) {
+    // The wedge kernel: (ring range x angular wedge) tasks, one warp each (cs_wedge.cuh).  The first blocks prepare the rays,
+    // 128 each (big scans: bigger groups, so that at most 64 blocks prepare); every warp of the grid then takes tasks
+    // round-robin.  One session alone gets four blocks per SM (all resident: the kernel is a latency chain pose -> rays ->
+    // tasks), a session of a batch a few blocks.
+    int group = (((n_points + 63) / 64) + 31) / 32 * 32;
+    if (group < 128) group = 128;
+    a.prep_group = group;
+    const int nprep = (n_points + group - 1) / group;
+    int blocks = c.n_sessions == 1 ? 4 * c.num_sms : 4;
+    if (tune().w_blocks > 0) blocks = tune().w_blocks;
+    if (blocks < nprep) blocks = nprep;
+    a.w_slot = (*c.w_slot ^= 1);
+    a.w_general = tune().w_general > 0 ? 1 : 0;
+    dispatch_layout(c.tiled, [&](auto T) {
+      e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS), 0, c.stream,
+                     c.d_sess, a);
+    });
+    if (e != cudaSuccess) return e;
+    (*c.launches)++;
+  } else if (draws) {
     int threads = ((n_points + CS_RING_RPT - 1) / CS_RING_RPT + 31) / 32 * 32;
     if (tune().ring_threads >= 32) threads = tune().ring_threads / 32 * 32;
     if (threads < 32) threads = 32;
@@ -589,6 +620,7 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.n_sessions = 1;
   c.launches = &h->launches;
   c.step_counter = &h->step_counter;
+  c.w_slot = &h->w_slot;
   c.diag = h->d_ring_cycles;
   c.diag_rings = h->size;
   c.s2_cap = h->s2_cap;
@@ -744,6 +776,10 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_prep_words, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(cudaMemset(h->d_prep_words, 0, (size_t)2 * kRayCopies * 16 * sizeof(unsigned long long)));
   CS_CREATE_CUDA(rings_allow_shared_memory());
+  CS_CREATE_CUDA(cudaMalloc(&h->d_w_rk, (size_t)h->ray_stride * sizeof(int2)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_w_bkey, (size_t)(h->ray_stride / 32 + 1) * sizeof(float2)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_w_alive, (size_t)2 * (CS_W_LEVELS + 1) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMemset(h->d_w_alive, 0, (size_t)2 * (CS_W_LEVELS + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
@@ -828,6 +864,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   s.ray_stride = h->ray_stride;
   s.batch_stride = h->batch_stride;
   s.prep_words = h->d_prep_words;
+  s.w_rk = h->d_w_rk;
+  s.w_bkey = h->d_w_bkey;
+  s.w_alive = h->d_w_alive;
   s.s2_sorted = h->d_s2_sorted;
   s.s2_tmp = h->d_s2_tmp;
   s.s2_meta = h->d_s2_meta;
@@ -857,6 +896,9 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_batch_max);
   cudaFree(h->d_prep_words);
   cudaFree(h->d_ray_dbg);
+  cudaFree(h->d_w_rk);
+  cudaFree(h->d_w_bkey);
+  cudaFree(h->d_w_alive);
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
@@ -1253,6 +1295,7 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   a.cand_first = 0;
   a.cand_count = h->n_cand + 1;
   a.s2_host_points = n_points;
+  a.empty_cloud = (do_search && n_points == 0) ? 1 : 0;
   *out_args = a;
   return CS_OK;
 }
@@ -1902,6 +1945,11 @@ struct cs_batch {
   int* d_batch_max = nullptr;
   unsigned long long* d_prep_words = nullptr;
   unsigned long long* d_checksum = nullptr;
+  // wedge integration scratch of all sessions (CsSession::w_*)
+  int2* d_w_rk = nullptr;
+  float2* d_w_bkey = nullptr;
+  int* d_w_alive = nullptr;
+  int w_slot = 0;
   // slab-search scratch of all sessions (CsSession::s2_*): per session 2*cap sorted + cap tmp entries, cap meta + cap acc words
   float4* d_s2_entries = nullptr;
   unsigned long long* d_s2_words = nullptr;
@@ -1964,6 +2012,7 @@ LaunchCtx batch_ctx(cs_batch* b) {
   c.n_sessions = b->n;
   c.launches = &b->launches;
   c.step_counter = &b->step_counter;
+  c.w_slot = &b->w_slot;
   c.s2_cap = b->s2_cap;
   c.s2_min_cand = cs_s2_min_cand(b->flags, b->n);
   c.s2_toggle = &b->s2_toggle;
@@ -2047,6 +2096,10 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_prep_words, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMemset(b->d_prep_words, 0, (size_t)n_sessions * 2 * 16 * sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_w_rk, (size_t)b->max_points * sizeof(int2) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_w_bkey, ((size_t)b->max_points / 32 + 1) * sizeof(float2) * (size_t)n_sessions) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_w_alive, (size_t)n_sessions * 2 * (CS_W_LEVELS + 1) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemset(b->d_w_alive, 0, (size_t)n_sessions * 2 * (CS_W_LEVELS + 1) * sizeof(int)) == cudaSuccess;
   b->flags = c0.flags;
   {
     const int min_cand = cs_s2_min_cand(c0.flags, n_sessions);
@@ -2091,6 +2144,9 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
     s.ray_stride = b->max_points;
     s.batch_stride = b->max_points / 32 + 1;
     s.prep_words = b->d_prep_words + (size_t)j * 2 * 16;
+    s.w_rk = b->d_w_rk + (size_t)j * b->max_points;
+    s.w_bkey = b->d_w_bkey + (size_t)j * ((size_t)b->max_points / 32 + 1);
+    s.w_alive = b->d_w_alive + (size_t)j * 2 * (CS_W_LEVELS + 1);
     if (b->s2_cap > 0) {
       const size_t cap = (size_t)b->s2_cap;
       s.s2_sorted = b->d_s2_entries + (size_t)j * 3 * cap;
@@ -2125,6 +2181,9 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_batch_max);
   cudaFree(b->d_prep_words);
   cudaFree(b->d_checksum);
+  cudaFree(b->d_w_rk);
+  cudaFree(b->d_w_bkey);
+  cudaFree(b->d_w_alive);
   cudaFree(b->d_s2_entries);
   cudaFree(b->d_s2_words);
   cudaFree(b->d_stage);

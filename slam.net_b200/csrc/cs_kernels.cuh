@@ -119,6 +119,11 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   unsigned long long* s2_acc;   // [s2_cap] per sorted position: cell sum | in-bounds count << 32 | clusters arrived << 49; zero between steps
   int s2_cap, pad3;
   unsigned* s2_ghist;           // [CS_SORT_BINS + 1] histogram of the multi-block sort + its arrival counter; zero between steps
+  // ---- scratch of the wedge integration (cs_wedge.cuh)
+  int2* w_rk;                   // per ray: (angular key as float bits, dxc or -1 for a ray that draws nothing)
+  float2* w_bkey;               // per 32 consecutive rays: (smallest, largest) key of a valid ray
+  int* w_alive;                 // [2][CS_W_LEVELS + 1]: valid rays that reach the first ring of each level (+ all valid rays);
+                                // slot = CsStepArgs::w_slot, the other slot is zeroed by the step that uses this one
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
@@ -165,6 +170,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned long long s2_seed;
   int s2_size, s2_pitch_tiles;
   float s2_scale, s2_sigma_xy, s2_sigma_theta;
+  int w_slot;                    // which half of CsSession::w_alive this step counts into (alternates per drawn step)
+  int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
   int empty_cloud;               // 1: the scan has no points and the step searches: no search kernel ran, the arg-min is
                                  // (int.MaxValue, searchPose) by definition (:251-258, :630-648)
   int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values
@@ -422,40 +429,60 @@ __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader
   }
 }
 
+// The pose-dependent constants of UpdateHoleMap (:499-512), shared by every ray of the scan.
+struct CsRayFrame {
+  float px, py, c, s, hw, scale;
+  int x1, y1, size;
+  bool on_map;
+};
+__device__ __forceinline__ CsRayFrame cs_ray_frame(const CsSession& S, const float pose[3], const float cs[2]) {
+  CsRayFrame f;
+  f.scale = S.scale;
+  f.size = S.size;
+  f.px = __fadd_rn(__fmul_rn(pose[0], f.scale), 0.5f);  // :499
+  f.py = __fadd_rn(__fmul_rn(pose[1], f.scale), 0.5f);  // :500
+  f.c = __fmul_rn(cs[0], f.scale);                       // :501
+  f.s = __fmul_rn(cs[1], f.scale);                       // :502
+  f.x1 = cs_cvt_i32(f.px); f.y1 = cs_cvt_i32(f.py);      // :505-506
+  f.on_map = !(f.x1 < 0 || f.x1 >= f.size || f.y1 < 0 || f.y1 >= f.size);  // :509-512
+  f.hw = S.hole_width;
+  return f;
+}
+
+// One ray of UpdateHoleMap (:517-530) + ClipRay + the prologue of DrawLaserRayOnHoleMap; d6 (optional) receives
+// (x1,y1,x2,y2,xp,yp).
+__device__ __forceinline__ CsRay cs_ray_from_point(const CsRayFrame& f, const float2 p, int* d6) {
+  CsRay r;
+  r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
+  int x2 = 0, y2 = 0, xp = 0, yp = 0;
+  if (f.on_map) {
+    float x2p = __fsub_rn(__fmul_rn(f.c, p.x), __fmul_rn(f.s, p.y));  // :519
+    float y2p = __fadd_rn(__fmul_rn(f.s, p.x), __fmul_rn(f.c, p.y));  // :520
+    xp = cs_cvt_i32(__fadd_rn(f.px, x2p));                            // :521
+    yp = cs_cvt_i32(__fadd_rn(f.py, y2p));                            // :522
+    float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(x2p, x2p), __fmul_rn(y2p, y2p)));  // :524
+    float add = __fdiv_rn(__fdiv_rn(__fmul_rn(f.hw, f.scale), 2.0f), dist);        // :525
+    float k1 = __fadd_rn(1.0f, add);
+    x2p = __fmul_rn(x2p, k1);                                         // :527
+    y2p = __fmul_rn(y2p, k1);                                         // :528
+    x2 = cs_cvt_i32(__fadd_rn(f.px, x2p));                            // :529
+    y2 = cs_cvt_i32(__fadd_rn(f.py, y2p));                            // :530
+    r = cs_make_ray(f.size, f.x1, f.y1, x2, y2, xp, yp);
+  }
+  if (d6) { d6[0] = f.x1; d6[1] = f.y1; d6[2] = x2; d6[3] = y2; d6[4] = xp; d6[5] = yp; }
+  return r;
+}
+
 // Per-ray part of UpdateHoleMap (:517-530) + ClipRay + the prologue of DrawLaserRayOnHoleMap for rays
 // first, first+stride, ... < n.  Returns this thread's (max dxc, visits) contribution.
 __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __restrict__ points, float2 p_first, int n, int first,
                                                 int stride, const float pose[3], const float cs[2], bool write_dbg,
                                                 long long& visits) {
-  const float scale = S.scale;
-  const int size = S.size;
-  const float px = __fadd_rn(__fmul_rn(pose[0], scale), 0.5f);  // :499
-  const float py = __fadd_rn(__fmul_rn(pose[1], scale), 0.5f);  // :500
-  const float c = __fmul_rn(cs[0], scale);                       // :501
-  const float s = __fmul_rn(cs[1], scale);                       // :502
-  const int x1 = cs_cvt_i32(px), y1 = cs_cvt_i32(py);            // :505-506
-  const bool on_map = !(x1 < 0 || x1 >= size || y1 < 0 || y1 >= size);  // :509-512
-  const float hw = S.hole_width;
+  const CsRayFrame f = cs_ray_frame(S, pose, cs);
   for (int i = first; i < n; i += stride) {
-    CsRay r;
-    r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
-    int x2 = 0, y2 = 0, xp = 0, yp = 0;
     const float2 p = (i == first) ? p_first : points[i];  // the first one was loaded while the pose was awaited
-    if (on_map) {
-      float x2p = __fsub_rn(__fmul_rn(c, p.x), __fmul_rn(s, p.y));  // :519
-      float y2p = __fadd_rn(__fmul_rn(s, p.x), __fmul_rn(c, p.y));  // :520
-      xp = cs_cvt_i32(__fadd_rn(px, x2p));                          // :521
-      yp = cs_cvt_i32(__fadd_rn(py, y2p));                          // :522
-      float dist = __fsqrt_rn(__fadd_rn(__fmul_rn(x2p, x2p), __fmul_rn(y2p, y2p)));  // :524
-      float add = __fdiv_rn(__fdiv_rn(__fmul_rn(hw, scale), 2.0f), dist);            // :525
-      float k1 = __fadd_rn(1.0f, add);
-      x2p = __fmul_rn(x2p, k1);                                     // :527
-      y2p = __fmul_rn(y2p, k1);                                     // :528
-      x2 = cs_cvt_i32(__fadd_rn(px, x2p));                          // :529
-      y2 = cs_cvt_i32(__fadd_rn(py, y2p));                          // :530
-      r = cs_make_ray(size, x1, y1, x2, y2, xp, yp);
-      if (r.flags & 1) visits += (long long)r.dxc + 1;
-    }
+    const CsRay r = cs_ray_from_point(f, p, (write_dbg && S.ray_dbg) ? S.ray_dbg + 6 * (size_t)i : nullptr);
+    if (r.flags & 1) visits += (long long)r.dxc + 1;
     {
       const int4 q = cs_pack_ray(r);
       for (int c = 0; c < S.ray_copies; c++) S.rays[(size_t)c * S.ray_stride + i] = q;
@@ -465,10 +492,6 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
       bm = __reduce_max_sync(__activemask(), bm);
       if ((i & 31) == 0)
         for (int c = 0; c < S.ray_copies; c++) S.batch_max[(size_t)c * S.batch_stride + (i >> 5)] = bm;
-    }
-    if (write_dbg && S.ray_dbg) {
-      int* d = S.ray_dbg + 6 * (size_t)i;
-      d[0] = x1; d[1] = y1; d[2] = x2; d[3] = y2; d[4] = xp; d[5] = yp;
     }
   }
 }
