@@ -699,6 +699,8 @@ def main():
     ap.add_argument("--sessions", type=int, default=0, help="cfg5: number of sessions in the job (default: the config's 1024)")
     ap.add_argument("--sub-batches", type=int, default=0,
                     help="cfg5: independent batches (streams) a rank's sessions are run as (default 1)")
+    ap.add_argument("--no-sharded", action="store_true",
+                    help="default (cfg2) line: skip the `sharded` block (cfg5 session batches and the cfg4 candidate split over the ranks)")
     args = ap.parse_args()
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
@@ -1001,10 +1003,20 @@ def main():
                 "cpu_baseline": cpu,
                 "wall_s_timed_region": wall_region,
                 "final_pose": [float(x) for x in final_pose]}
-        print(json.dumps(line))
 
     proc.close()
     log.close()
+    # ---- the configs that shard (BASELINE configs[3], [4]), measured in the same run over the same ranks so that the
+    # driver's --gpus N lines carry them: cfg5 = 1024 session replays sharded i mod N (strong scaling, no collective),
+    # cfg4 = 65536 candidates split over the ranks with one 8-byte MIN exchange per scan
+    sharded = None
+    if not args.no_sharded:
+        Ks = min(K, 20)
+        sharded = {"cfg5": measure_cfg5(args, rank, world, local, Ks, 3, sub_batches=args.sub_batches),
+                   "cfg4": measure_cfg4(args, rank, world, local, Ks, 3)}
+    if rank == 0:
+        line["sharded"] = sharded
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

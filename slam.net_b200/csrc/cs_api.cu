@@ -68,7 +68,7 @@ struct cs_processor {
   // wedge integration scratch (CsSession::w_*)
   int2* d_w_rk = nullptr;
   float2* d_w_bkey = nullptr;
-  int* d_w_alive = nullptr;
+  int* d_w_top = nullptr;
   int w_slot = 0;
   long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
@@ -226,6 +226,23 @@ cudaError_t rings_allow_shared_memory() {
   return e;
 }
 
+// Wedge integration (cs_wedge.cuh): levels a ray of a size x size map can reach, the words of one half of CsSession::w_top,
+// and the dynamic shared memory of the kernel (one 16-bit count per level and key sector).
+int wedge_levels(int size) {
+  const int k = size > 1 ? size - 1 : 1;
+  int L = 0;
+  if (k < 64) { while ((2 << L) <= k) L++; } else L = 5 + (k >> 6);
+  return L + 1;
+}
+size_t wedge_top_words(int size) { return (size_t)wedge_levels(size) * (CS_W_SECTORS + 1) + 1; }
+size_t wedge_smem(int) { return 0; }
+cudaError_t wedge_allow_shared_memory() {
+  const int most = (int)(CS_W_LEVELS * CS_W_SECTORS * sizeof(unsigned short));
+  cudaError_t e = cudaFuncSetAttribute(cs_wedge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+  return e;
+}
+
 int rings_hint_of(int size, float scale, float hole_width, double max_range) {
   if (!(max_range == max_range) || max_range > 1e30) return size;
   double cells = max_range * (double)scale * 1.00001 + 0.5 * (double)hole_width * (double)scale + 4.0;
@@ -268,7 +285,7 @@ double max_range_of(const float* points, int n) {
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
-  int integrate = 0, w_general = 0, w_blocks = 0;
+  int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -281,6 +298,8 @@ struct Tune {
     integrate = geti("CS_TUNE_INTEGRATE");      // 1: the rings kernel draws the scan instead of the wedge kernel (A/B runs)
     w_general = geti("CS_TUNE_W_GENERAL");      // 1: every task of the wedge kernel takes its general path (tests)
     w_blocks = geti("CS_TUNE_W_BLOCKS");        // blocks of the wedge kernel per session
+    w_prefetch = geti("CS_TUNE_W_PREFETCH");    // -1: no L2 prefetch of the map around the pose
+    w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
     ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
@@ -401,7 +420,7 @@ struct LaunchCtx {
   int n_sessions;
   uint64_t* launches;
   unsigned* step_counter;  // source of CsStepArgs::step_id
-  int* w_slot = nullptr;   // which half of CsSession::w_alive the next drawn step counts into
+  int* w_slot = nullptr;   // which half of CsSession::w_top the next drawn step counts into
   long long* diag;
   int diag_rings;
   cudaEvent_t ev_pose;   // optional: recorded once the pose is out
@@ -538,9 +557,11 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (blocks < nprep) blocks = nprep;
     a.w_slot = (*c.w_slot ^= 1);
     a.w_general = tune().w_general > 0 ? 1 : 0;
+    a.w_sub_max = tune().w_sub;
+    a.w_prefetch = (c.n_sessions == 1 && tune().w_prefetch >= 0) ? 1 : 0;  // batches hide the latency with their sessions
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS), 0, c.stream,
-                     c.d_sess, a);
+      e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS),
+                     wedge_smem(c.hs->size), c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -778,8 +799,9 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(rings_allow_shared_memory());
   CS_CREATE_CUDA(cudaMalloc(&h->d_w_rk, (size_t)h->ray_stride * sizeof(int2)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_w_bkey, (size_t)(h->ray_stride / 32 + 1) * sizeof(float2)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_w_alive, (size_t)2 * (CS_W_LEVELS + 1) * sizeof(int)));
-  CS_CREATE_CUDA(cudaMemset(h->d_w_alive, 0, (size_t)2 * (CS_W_LEVELS + 1) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_w_top, (size_t)2 * wedge_top_words(h->size) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMemset(h->d_w_top, 0, (size_t)2 * wedge_top_words(h->size) * sizeof(int)));
+  CS_CREATE_CUDA(wedge_allow_shared_memory());
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
@@ -866,7 +888,8 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   s.prep_words = h->d_prep_words;
   s.w_rk = h->d_w_rk;
   s.w_bkey = h->d_w_bkey;
-  s.w_alive = h->d_w_alive;
+  s.w_top = h->d_w_top;
+  s.w_levels = wedge_levels(h->size);
   s.s2_sorted = h->d_s2_sorted;
   s.s2_tmp = h->d_s2_tmp;
   s.s2_meta = h->d_s2_meta;
@@ -898,7 +921,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_ray_dbg);
   cudaFree(h->d_w_rk);
   cudaFree(h->d_w_bkey);
-  cudaFree(h->d_w_alive);
+  cudaFree(h->d_w_top);
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);
@@ -1948,7 +1971,7 @@ struct cs_batch {
   // wedge integration scratch of all sessions (CsSession::w_*)
   int2* d_w_rk = nullptr;
   float2* d_w_bkey = nullptr;
-  int* d_w_alive = nullptr;
+  int* d_w_top = nullptr;
   int w_slot = 0;
   // slab-search scratch of all sessions (CsSession::s2_*): per session 2*cap sorted + cap tmp entries, cap meta + cap acc words
   float4* d_s2_entries = nullptr;
@@ -2098,8 +2121,9 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_w_rk, (size_t)b->max_points * sizeof(int2) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_w_bkey, ((size_t)b->max_points / 32 + 1) * sizeof(float2) * (size_t)n_sessions) == cudaSuccess;
-  ok = ok && cudaMalloc(&b->d_w_alive, (size_t)n_sessions * 2 * (CS_W_LEVELS + 1) * sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMemset(b->d_w_alive, 0, (size_t)n_sessions * 2 * (CS_W_LEVELS + 1) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_w_top, (size_t)n_sessions * 2 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemset(b->d_w_top, 0, (size_t)n_sessions * 2 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
+  ok = ok && wedge_allow_shared_memory() == cudaSuccess;
   b->flags = c0.flags;
   {
     const int min_cand = cs_s2_min_cand(c0.flags, n_sessions);
@@ -2146,7 +2170,8 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
     s.prep_words = b->d_prep_words + (size_t)j * 2 * 16;
     s.w_rk = b->d_w_rk + (size_t)j * b->max_points;
     s.w_bkey = b->d_w_bkey + (size_t)j * ((size_t)b->max_points / 32 + 1);
-    s.w_alive = b->d_w_alive + (size_t)j * 2 * (CS_W_LEVELS + 1);
+    s.w_top = b->d_w_top + (size_t)j * 2 * wedge_top_words(b->size);
+    s.w_levels = wedge_levels(b->size);
     if (b->s2_cap > 0) {
       const size_t cap = (size_t)b->s2_cap;
       s.s2_sorted = b->d_s2_entries + (size_t)j * 3 * cap;
@@ -2183,7 +2208,7 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_checksum);
   cudaFree(b->d_w_rk);
   cudaFree(b->d_w_bkey);
-  cudaFree(b->d_w_alive);
+  cudaFree(b->d_w_top);
   cudaFree(b->d_s2_entries);
   cudaFree(b->d_s2_words);
   cudaFree(b->d_stage);

@@ -122,8 +122,10 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   // ---- scratch of the wedge integration (cs_wedge.cuh)
   int2* w_rk;                   // per ray: (angular key as float bits, dxc or -1 for a ray that draws nothing)
   float2* w_bkey;               // per 32 consecutive rays: (smallest, largest) key of a valid ray
-  int* w_alive;                 // [2][CS_W_LEVELS + 1]: valid rays that reach the first ring of each level (+ all valid rays);
-                                // slot = CsStepArgs::w_slot, the other slot is zeroed by the step that uses this one
+  int* w_top;                   // [2][w_levels * (CS_W_SECTORS + 1) + 1]: valid rays that reach (level, key sector), that reach each
+                                // level, and all valid rays; slot = CsStepArgs::w_slot, the other slot is zeroed by the step that
+                                // uses this one
+  int w_levels, pad4;           // levels a ray of this map can reach (cs_w_level_of(size - 1) + 1)
 };
 
 struct CsStepArgs {  // by-value kernel argument; session j uses element j of every array
@@ -172,6 +174,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   float s2_scale, s2_sigma_xy, s2_sigma_theta;
   int w_slot;                    // which half of CsSession::w_alive this step counts into (alternates per drawn step)
   int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
+  int w_sub_max;                 // most warps the rings of one task are split over (0: 8)
+  int w_prefetch;                // 1: the wedge kernel prefetches the map around the pose into L2 while it waits for the pose
   int empty_cloud;               // 1: the scan has no points and the step searches: no search kernel ran, the arg-min is
                                  // (int.MaxValue, searchPose) by definition (:251-258, :630-648)
   int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values

@@ -33,6 +33,10 @@
 #define CS_W_CAP 256      // cells of a wedge staged per pass of the general path
 #define CS_W_G 4          // rings in flight per lane on the fast path
 #define CS_W_MAX_WEDGES 8192
+#define CS_W_SECTORS 64   // key sectors of width 1/8: the rays that reach a level are counted per sector, and each sector is
+                          // cut into wedges of its own (long rays cluster in a few directions: a uniform cut would leave some
+                          // wedges with several times the candidates a warp holds)
+#define CS_W_OWN 26       // candidates a wedge is sized for (own rays + the rays of its margins)
 
 __device__ __forceinline__ int cs_w_level_first(int L) { return L < 6 ? (1 << L) : 64 * (L - 5); }
 __device__ __forceinline__ int cs_w_level_last(int L) { return L < 6 ? (2 << L) - 1 : 64 * (L - 5) + 63; }
@@ -67,8 +71,8 @@ struct CsWTask {
 };
 
 // ---- ray preparation by the first blocks (UpdateHoleMap :517-530, ClipRay, the prologue of DrawLaserRayOnHoleMap), one ray
-// per lane: packed ray, (key, dxc), the warp's key range and largest dxc, and the per-level counts.
-__device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, const float2 p, int i, bool in_range, int* alive,
+// per lane: packed ray, (key, dxc), the warp's key range and largest dxc, and the per (level, sector) counts.
+__device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, const float2 p, int i, bool in_range, int* top,
                                              long long& visits) {
   const unsigned full = 0xffffffffu;
   CsRay r;
@@ -96,38 +100,60 @@ __device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, 
     S.batch_max[i >> 5] = bm;
     S.w_bkey[i >> 5] = make_float2(__uint_as_float(kmin), __uint_as_float(kmax));
   }
-  // per level: rays of this warp that reach its first ring
+  // counts: every valid ray; per level the rays that reach it, in all and per key sector.  The lanes of a sector add as one
+  // (the 32 consecutive rays of a warp span a sector or two of a lidar scan).
   const unsigned nvalid = __popc(__ballot_sync(full, valid));
-  if (lane == 0 && nvalid) atomicAdd(&alive[CS_W_LEVELS], (int)nvalid);
-  if (bm >= 1) {
-    const int top = cs_w_level_of(bm);
-    for (int L = 0; L <= top; L++) {
-      const unsigned m = __ballot_sync(full, valid && r.dxc >= cs_w_level_first(L));
-      if (lane == 0 && m) atomicAdd(&alive[L], (int)__popc(m));
+  int* tot = top + (size_t)S.w_levels * CS_W_SECTORS;
+  if (lane == 0 && nvalid) atomicAdd(&tot[S.w_levels], (int)nvalid);
+  const bool counted = valid && r.dxc >= 1;
+  const unsigned cm = __ballot_sync(full, counted);
+  if (cm) {
+    const int sector = min(CS_W_SECTORS - 1, (int)(key * (CS_W_SECTORS / 8.0f)));
+    unsigned same = 0u;
+    if (counted) same = __match_any_sync(cm, sector);
+    const bool leader = counted && lane == __ffs(same) - 1;
+    const int top_level = cs_w_level_of(max(bm, 1));
+    for (int L = 0; L <= top_level; L++) {
+      const unsigned here = __ballot_sync(full, counted && r.dxc >= cs_w_level_first(L));
+      if (leader && (here & same)) atomicAdd(&top[L * CS_W_SECTORS + sector], (int)__popc(here & same));
+      if (lane == 0 && here) atomicAdd(&tot[L], (int)__popc(here));
     }
   }
 }
 
-// for every batch of 32 consecutive rays that can hold a candidate of task t (by its key range and largest dxc): f(batch)
-template <typename F>
-__device__ __forceinline__ void cs_w_for_batches(const CsSession& S, const CsWTask& t, int n, F&& f) {
+// The batches of 32 consecutive rays that can hold a candidate of task t (by their key range and largest dxc), as a bitmap
+// in shared memory (bit b of word b / 32); returns the number of words in use.
+#define CS_W_BMAP_WORDS 64  // 65536 rays / 32 / 32
+__device__ __forceinline__ int cs_w_batch_map(const CsSession& S, const CsWTask& t, int n, unsigned* s_bmap) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int nb = (n + 31) >> 5;
-  for (int b0 = 0; b0 < nb; b0 += 32) {
-    const int bi = b0 + lane;
+  const int nw = (nb + 31) >> 5;
+  __syncwarp();  // (readers of the previous map are done)
+  for (int w = 0; w < nw; w++) {
+    const int bi = w * 32 + lane;
     bool ov = false;
-    if (bi < nb && __ldcg(S.batch_max + bi) >= t.k0) {
-      const float2 kk = __ldcg(S.w_bkey + bi);
-      ov = (kk.y >= t.flo && kk.x < t.fhi) || kk.y >= t.wrap_lo;
+    if (bi < nb) {
+      const int bm = S.batch_max[bi];  // (both loads in flight together)
+      const float2 kk = S.w_bkey[bi];
+      ov = bm >= t.k0 && ((kk.y >= t.flo && kk.x < t.fhi) || kk.y >= t.wrap_lo);
     }
-    unsigned om = __ballot_sync(full, ov);
-    while (om) {
-      const int b = b0 + __ffs(om) - 1;
-      om &= om - 1;
-      f(b);
-    }
+    const unsigned om = __ballot_sync(full, ov);
+    if (lane == 0) s_bmap[w] = om;
   }
+  __syncwarp();
+  return nw;
+}
+// next batch at or after `from` in the bitmap, or -1
+__device__ __forceinline__ int cs_w_next_batch(const unsigned* s_bmap, int nw, int from) {
+  int w = from >> 5;
+  if (w >= nw) return -1;
+  unsigned m = s_bmap[w] & (0xffffffffu << (from & 31));
+  while (m == 0u) {
+    if (++w >= nw) return -1;
+    m = s_bmap[w];
+  }
+  return w * 32 + __ffs(m) - 1;
 }
 __device__ __forceinline__ bool cs_w_is_candidate(const CsWTask& t, const int2 rk) {
   const float key = __int_as_float(rk.x);
@@ -142,6 +168,45 @@ __device__ __forceinline__ void cs_w_pos_to_xy(int p, int k, int x1, int y1, int
   else { y = y1 - k; x = x1 + (p - 7 * k); }
 }
 
+// One ray's walk, carried from ring to ring: the incremental form of cs_ring_visit (cell, position on the ring) and the
+// closed form of the pixval.  init(k) puts the state ON ring k (k >= 0); step() advances it by one ring.
+struct CsWWalk {
+  int dxc;            // last ring of the ray; -1: this lane has no ray
+  int den2, dy2, rem; // Bresenham: (2 dyc k + dxc - 1) = q * 2 dxc + rem
+  int x, y, pos, k;
+  int cside, g, dxM, dyM, dxN, dyN;
+  int a0, b0, c0, incv, kc, ndt;
+  __device__ __forceinline__ void init(const CsRay& r, bool have, int k_, int x1, int y1) {
+    dxc = have ? r.dxc : -1;
+    const int dyc = min(r.dyc, r.dxc);  // a clipped dyc > dxc walks the diagonal (m = k), like dyc = dxc
+    den2 = 2 * max(dxc, 1); dy2 = 2 * max(dyc, 0);
+    cs_w_side(r.flags, cside, g);
+    const bool steep = (r.flags & 2) != 0;
+    const int smaj = (r.flags & 4) ? -1 : 1, smin = (r.flags & 8) ? -1 : 1;
+    dxM = steep ? 0 : smaj; dyM = steep ? smaj : 0;  // per ring
+    dxN = steep ? smin : 0; dyN = steep ? 0 : smin;  // per minor step
+    k = k_;
+    int q = (k == 0 || dxc < 1) ? 0 : cs_ray_minor(r, k);
+    rem = dy2 * k + max(dxc, 1) - 1 - q * den2;
+    x = x1 + dxM * k + dxN * q; y = y1 + dyM * k + dyN * q;
+    pos = cside * k + g * q;
+    a0 = r.a0; b0 = r.b0; c0 = max(r.a0, r.b0 + 1); incv = r.incv; kc = r.kc; ndt = r.nd_total;
+  }
+  __device__ __forceinline__ void step() {
+    k++;
+    rem += dy2;
+    if (rem >= den2) { rem -= den2; x += dxN; y += dyN; pos += g; }
+    x += dxM; y += dyM; pos += cside;
+  }
+  __device__ __forceinline__ int posn() const { return pos == 8 * k ? 0 : pos; }  // the corner 8k is position 0
+  __device__ __forceinline__ int pixval() const {  // closed form of :402-428 (cs_ray_pixval)
+    if (k <= b0) return CS_TS_NO_OBSTACLE + max(k - a0 + 1, 0) * incv;
+    if (k < c0) return CS_TS_NO_OBSTACLE;
+    const int j = k - c0 + 1;
+    return CS_TS_NO_OBSTACLE + (ndt - j) * incv + min(j, kc);
+  }
+};
+
 // ---- ring 0: the start cell, visited by every valid ray, in ray order (one warp)
 template <bool TILED>
 __device__ void cs_w_ring0(const CsSession& S, uint16_t* __restrict__ map, int n, int x1, int y1, int size, int pitch_tiles, int alpha) {
@@ -151,12 +216,16 @@ __device__ void cs_w_ring0(const CsSession& S, uint16_t* __restrict__ map, int n
   CsBlendState st;
   st.val = 0; st.last_pv = -1; st.fixed = false;
   bool loaded = false;
+  int4 q_next = make_int4(0, 0, 0, 0);
+  if (lane < n) q_next = S.rays[lane];
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
+    const int4 q = q_next;
+    if (i + 32 < n) q_next = S.rays[i + 32];  // the next batch's rays are in flight while this one is applied
     int pv = 0;
     bool valid = false;
     if (i < n) {
-      const CsRay r = cs_unpack_ray(__ldcg(S.rays + i));
+      const CsRay r = cs_unpack_ray(q);
       valid = (r.flags & 1) != 0;
       if (valid) pv = cs_ray_pixval(r, 0);
     }
@@ -179,106 +248,150 @@ __device__ void cs_w_ring0(const CsSession& S, uint16_t* __restrict__ map, int n
   if (loaded && lane == 0) __stcg(map + cell, (uint16_t)st.val);
 }
 
-// ---- general path: any number of candidates
-template <bool TILED>
-__device__ void cs_w_general(const CsSession& S, uint16_t* __restrict__ map, const CsWTask& t, int n, int x1, int y1, int size,
-                             int pitch_tiles, int alpha, unsigned* s_val, uint32_t* s_cell) {
+// Folds the visits of one ring held by the lanes of a warp (inw lanes: position posn, pixval pv) into the staged cells:
+// lanes on one cell form a group, its lowest lane applies the group in lane (= ray) order — as a count when the group has
+// one pixval (blends of one value commute with themselves; exact fixed-point early-out).
+__device__ __forceinline__ void cs_w_fold(bool inw, int posn, int pv, int slot, unsigned* s_val, int alpha) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  for (int k = t.k0; k <= t.k1; k++) {
-    const int lo = cs_w_bound(k, t.blo), hi = cs_w_bound(k, t.bhi);
-    for (int c0 = lo; c0 < hi; c0 += CS_W_CAP) {
-      const int cn = min(CS_W_CAP, hi - c0);
-      for (int i = lane; i < cn; i += 32) {  // stage the wedge's cells of this ring
+  const unsigned act = __ballot_sync(full, inw);
+  if (!act) return;
+  unsigned rest = 0u;  // leaders of groups with several pixvals: the other members, applied in lane order below
+  bool lead = false;
+  int v = 0;
+  if (inw) {
+    const unsigned grp = __match_any_sync(act, posn);
+    lead = lane == __ffs(grp) - 1;
+    unsigned same = grp;
+    const bool multi = (grp & (grp - 1)) != 0u;  // every lane of a group sees the same grp
+    const unsigned mm = __ballot_sync(act, multi);
+    if (multi) same = __match_any_sync(mm, ((unsigned long long)(unsigned)posn << 32) | (unsigned)pv);
+    if (lead) {
+      v = (int)(s_val[slot] & 0xffffu);
+      if (same == grp) {
+        CsBlendState st;
+        st.val = v; st.last_pv = -1; st.fixed = false;
+        st.apply_n(pv, __popc(grp), alpha);
+        v = st.val;
+      } else {
+        v = cs_blend(v, pv, alpha);
+        rest = grp & ~(1u << lane);
+      }
+    }
+  }
+  unsigned any_rest = __ballot_sync(full, rest != 0u);
+  while (any_rest) {  // warp-uniform: every leader with members left fetches its next one
+    const int src = rest ? __ffs(rest) - 1 : lane;
+    const int pvj = __shfl_sync(full, pv, src);
+    if (rest) { v = cs_blend(v, pvj, alpha); rest &= rest - 1; }
+    any_rest = __ballot_sync(full, rest != 0u);
+  }
+  if (lead) s_val[slot] = (unsigned)v | 0x10000u;  // touched
+}
+
+// ---- general path: any number of candidates.  The rings of the task are taken a few at a time (as many as fit the staged
+// cells, at most CS_W_CHUNK): the wedge's cells of those rings go to shared memory, then the batches of 32 consecutive rays
+// that can hold candidates are walked in ray order — each lane carries its ray through the rings of the chunk — and fold
+// into the staged cells; the touched cells go back at the end of the chunk.  The next batch's rays are in flight while the
+// current one is walked.
+#define CS_W_CHUNK 8
+template <bool TILED>
+__device__ void cs_w_general(const CsSession& S, uint16_t* __restrict__ map, const CsWTask& t, int n, int x1, int y1, int size,
+                             int pitch_tiles, int alpha, unsigned* s_val, uint32_t* s_cell, unsigned* s_bmap, int nw) {
+  const int lane = threadIdx.x & 31;
+  int ka = t.k0;
+  while (ka <= t.k1) {
+    // rings ka .. kb of this chunk and where their cells start in the staging arrays
+    int off[CS_W_CHUNK + 1];
+    int kb = ka - 1, cells = 0;
+    off[0] = 0;
+#pragma unroll
+    for (int j = 0; j < CS_W_CHUNK; j++) {
+      const int k = ka + j;
+      int cnt = 0;
+      if (k <= t.k1 && kb == k - 1) {
+        cnt = cs_w_bound(k, t.bhi) - cs_w_bound(k, t.blo);
+        if (off[j] + cnt <= CS_W_CAP || j == 0) kb = k;
+        else cnt = 0;
+      }
+      off[j + 1] = off[j] + cnt;
+      cells += cnt;
+    }
+    // (a single ring wider than the staging arrays is taken in pieces of CS_W_CAP positions)
+    const int first_lo = cs_w_bound(ka, t.blo);
+    const int pieces = (kb == ka && off[1] > CS_W_CAP) ? (off[1] + CS_W_CAP - 1) / CS_W_CAP : 1;
+    for (int piece = 0; piece < pieces; piece++) {
+      const int p_lo = piece * CS_W_CAP;                       // positions [p_lo, p_hi) of the (single) ring, relative to first_lo
+      const int total = pieces > 1 ? min(CS_W_CAP, off[1] - p_lo) : cells;
+      for (int i = lane; i < total; i += 32) {  // stage the cells
+        int j = 0, obase = 0;
+#pragma unroll
+        for (int jj = 1; jj < CS_W_CHUNK; jj++)
+          if (pieces == 1 && jj <= kb - ka && i >= off[jj]) { j = jj; obase = off[jj]; }
+        const int k = ka + j;
+        const int p = (pieces > 1) ? first_lo + p_lo + i : cs_w_bound(k, t.blo) + (i - obase);
         int x, y;
-        cs_w_pos_to_xy(c0 + i, k, x1, y1, x, y);
+        cs_w_pos_to_xy(p, k, x1, y1, x, y);
         const bool on = (unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size;
         const uint32_t cell = on ? cs_cell_offset<TILED>(x, y, size, pitch_tiles) : 0xffffffffu;
         s_cell[i] = cell;
         s_val[i] = on ? (unsigned)__ldcg(map + cell) : 0u;
       }
       __syncwarp();
-      cs_w_for_batches(S, t, n, [&](int b) {
+      int b = cs_w_next_batch(s_bmap, nw, 0);
+      int2 rk_next = make_int2(0, -1);
+      int4 q_next = make_int4(0, 0, 0, 0);
+      if (b >= 0 && b * 32 + lane < n) { rk_next = S.w_rk[b * 32 + lane]; q_next = S.rays[b * 32 + lane]; }
+      while (b >= 0) {
+        const int2 rk = rk_next;
+        const int4 q = q_next;
         const int i = b * 32 + lane;
-        bool inw = false;
-        int pos = 0, pv = 0;
-        uint32_t cell = 0;
-        if (i < n && cs_w_is_candidate(t, __ldcg(S.w_rk + i))) {
-          const CsRay r = cs_unpack_ray(__ldcg(S.rays + i));
-          inw = cs_ring_visit<TILED>(r, k, x1, y1, size, pitch_tiles, pos, cell, pv) && pos >= c0 && pos < c0 + cn;
-        }
-        const unsigned act = __ballot_sync(full, inw);
-        if (!act) return;
-        unsigned rest = 0u;   // leaders of groups with several pixvals: the other members, applied in lane order below
-        bool lead = false;
-        int v = 0;
-        if (inw) {
-          const unsigned grp = __match_any_sync(act, pos);
-          const unsigned same = __match_any_sync(act, ((unsigned long long)(unsigned)pos << 32) | (unsigned)pv);
-          lead = lane == __ffs(grp) - 1;
-          if (lead) {
-            v = (int)(s_val[pos - c0] & 0xffffu);
-            if (same == grp) {  // one pixval: blends of one value commute with themselves — apply it as a count
-              CsBlendState st;
-              st.val = v; st.last_pv = -1; st.fixed = false;
-              st.apply_n(pv, __popc(grp), alpha);
-              v = st.val;
-            } else {
-              v = cs_blend(v, pv, alpha);
-              rest = grp & ~(1u << lane);
-            }
+        b = cs_w_next_batch(s_bmap, nw, b + 1);
+        rk_next = make_int2(0, -1);
+        if (b >= 0 && b * 32 + lane < n) { rk_next = S.w_rk[b * 32 + lane]; q_next = S.rays[b * 32 + lane]; }
+        const bool cand = i < n && cs_w_is_candidate(t, rk);
+        if (__ballot_sync(0xffffffffu, cand) == 0u) continue;
+        const CsRay r = cs_unpack_ray(q);
+        CsWWalk w;
+        w.init(r, cand, ka - 1, x1, y1);
+        unsigned accl = (unsigned)(ka - 1) * t.blo, acch = (unsigned)(ka - 1) * t.bhi;
+#pragma unroll
+        for (int j = 0; j < CS_W_CHUNK; j++) {
+          if (ka + j <= kb) {  // warp-uniform
+            w.step();
+            accl += t.blo; acch += t.bhi;
+            int lo = (int)((accl + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX), hi = (int)((acch + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX);
+            if (pieces > 1) { lo += p_lo; hi = min(hi, lo + CS_W_CAP); }
+            const int posn = w.posn();
+            const bool inw = w.k <= w.dxc && posn >= lo && posn < hi && (unsigned)w.x < (unsigned)size && (unsigned)w.y < (unsigned)size;
+            cs_w_fold(inw, posn, w.pixval(), (pieces > 1 ? 0 : off[j]) + posn - lo, s_val, alpha);
           }
         }
-        unsigned any_rest = __ballot_sync(full, rest != 0u);
-        while (any_rest) {  // warp-uniform: every leader with members left fetches its next one
-          const int src = rest ? __ffs(rest) - 1 : lane;
-          const int pvj = __shfl_sync(full, pv, src);
-          if (rest) { v = cs_blend(v, pvj, alpha); rest &= rest - 1; }
-          any_rest = __ballot_sync(full, rest != 0u);
-        }
-        if (lead) s_val[pos - c0] = (unsigned)v | 0x10000u;  // touched
-        __syncwarp();
-      });
-      for (int i = lane; i < cn; i += 32) {
-        const unsigned w = s_val[i];
-        if (w & 0x10000u) __stcg(map + s_cell[i], (uint16_t)(w & 0xffffu));
+        __syncwarp();  // the next batch may touch the same cells
+      }
+      for (int i = lane; i < total; i += 32) {
+        const unsigned v = s_val[i];
+        if (v & 0x10000u) __stcg(map + s_cell[i], (uint16_t)(v & 0xffffu));
       }
       __syncwarp();
     }
+    ka = kb + 1;
   }
 }
 
-// ---- fast path: at most 32 candidates (s_list, in ray order), one per lane
+// ---- fast path: at most 32 candidates (s_list, in ray order), one per lane; rings four at a time so that four map loads per
+// lane are in flight; visits of one cell inside the warp are found with match.any and applied by the lowest lane in lane order
 template <bool TILED>
 __device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const CsWTask& t, int ncand, const int* s_list, int x1, int y1,
                           int size, int pitch_tiles, int alpha) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  // this lane's ray, and its walk state at ring k0 - 1
   CsRay r;
   r.dxc = -1; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
-  if (lane < ncand) r = cs_unpack_ray(__ldcg(S.rays + s_list[lane]));
-  const int dxc = (lane < ncand) ? r.dxc : -1;
-  const int dyc = min(r.dyc, r.dxc);  // a clipped dyc > dxc walks the diagonal (m = k), like dyc = dxc
-  const int den2 = 2 * max(dxc, 1), dy2 = 2 * dyc;
-  int cs_, g;
-  cs_w_side(r.flags, cs_, g);
-  const bool steep = (r.flags & 2) != 0;
-  const int smaj = (r.flags & 4) ? -1 : 1, smin = (r.flags & 8) ? -1 : 1;
-  const int dxM = steep ? 0 : smaj, dyM = steep ? smaj : 0;  // per ring
-  const int dxN = steep ? smin : 0, dyN = steep ? 0 : smin;  // per minor step
-  int k = t.k0 - 1;
-  int q, rem;
-  {
-    const int num = dy2 * k + max(dxc, 1) - 1;  // (2 dyc k + dxc - 1) = q * 2 dxc + rem
-    q = (k == 0) ? 0 : cs_ray_minor(r, k);
-    if (dxc < 1) q = 0;
-    rem = num - q * den2;
-  }
-  int x = x1 + dxM * k + dxN * q, y = y1 + dyM * k + dyN * q;
-  int pos = cs_ * k + g * q;
-  unsigned accl = (unsigned)k * t.blo, acch = (unsigned)k * t.bhi;
-  const int c0 = max(r.a0, r.b0 + 1);
+  if (lane < ncand) r = cs_unpack_ray(S.rays[s_list[lane]]);
+  CsWWalk w;
+  w.init(r, lane < ncand, t.k0 - 1, x1, y1);
+  unsigned accl = (unsigned)(t.k0 - 1) * t.blo, acch = (unsigned)(t.k0 - 1) * t.bhi;
 
   for (int kb = t.k0; kb <= t.k1; kb += CS_W_G) {
     uint32_t cell[CS_W_G];
@@ -287,22 +400,13 @@ __device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const 
     unsigned leadbits = 0u, cfbits = 0u;
 #pragma unroll
     for (int j = 0; j < CS_W_G; j++) {
-      k = kb + j;
-      rem += dy2;
-      const bool wrap = rem >= den2;
-      if (wrap) { rem -= den2; x += dxN; y += dyN; pos += g; }
-      x += dxM; y += dyM; pos += cs_;
+      w.step();
       accl += t.blo; acch += t.bhi;
       const int lo = (int)((accl + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX), hi = (int)((acch + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX);
-      const int posn = (pos == 8 * k) ? 0 : pos;
-      const bool inw = k <= t.k1 && k <= dxc && posn >= lo && posn < hi && (unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size;
-      // pixval (closed form of :402-428, cs_ray_pixval with c0 hoisted)
-      int p;
-      if (k <= r.b0) p = CS_TS_NO_OBSTACLE + max(k - r.a0 + 1, 0) * r.incv;
-      else if (k < c0) p = CS_TS_NO_OBSTACLE;
-      else { const int jj = k - c0 + 1; p = CS_TS_NO_OBSTACLE + (r.nd_total - jj) * r.incv + min(jj, r.kc); }
-      pv[j] = p;
-      cell[j] = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
+      const int posn = w.posn();
+      const bool inw = w.k <= t.k1 && w.k <= w.dxc && posn >= lo && posn < hi && (unsigned)w.x < (unsigned)size && (unsigned)w.y < (unsigned)size;
+      pv[j] = w.pixval();
+      cell[j] = cs_cell_offset<TILED>(w.x, w.y, size, pitch_tiles);
       grp[j] = 0u;
       val[j] = 0;
       const unsigned act = __ballot_sync(full, inw);
@@ -336,20 +440,91 @@ __device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const 
   }
 }
 
+// Runs one task — rings ka .. kb of a level whose first ring is k0 (the wedge was sized for k0; the margins follow ka): while
+// the wedge holds more candidates than a warp has lanes it is cut in halves (left part first) as long as halving can help
+// (the wedge is wider than its margins); what cannot be cut takes the general path.
+template <bool TILED>
+__device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka, int kb, unsigned blo, unsigned bhi, int n, int x1,
+                         int y1, int size, int pitch_tiles, int alpha, int force_general, unsigned* s_val, uint32_t* s_cell, int* s_list,
+                         unsigned* s_bmap, long long* tl) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  int tl_pieces = 0, tl_cand = 0, tl_mode = 0;
+  const float eps = 0.5f / (float)ka + 1e-4f;
+  const unsigned min_width = (unsigned)(4.0f * eps * (float)(1 << CS_W_FIX)) + 2u;
+  unsigned lo = blo;
+  while (lo < bhi) {
+    unsigned hi = bhi;
+    CsWTask t;
+    int ncand, kmax, nw;
+    for (;;) {
+      t.k0 = ka;
+      t.k1 = kb;
+      t.blo = lo;
+      t.bhi = hi;
+      t.flo = (float)lo * (1.0f / (float)(1 << CS_W_FIX)) - eps;
+      t.fhi = (float)hi * (1.0f / (float)(1 << CS_W_FIX)) + eps;
+      t.wrap_lo = (lo == 0u) ? 8.0f - eps : 9.0f;
+      // candidates, in ray order; the largest dxc among them bounds the rings of the task
+      ncand = 0; kmax = 0;
+      nw = cs_w_batch_map(S, t, n, s_bmap);
+      int b = cs_w_next_batch(s_bmap, nw, 0);
+      int2 rk_next = make_int2(0, -1);
+      if (b >= 0 && b * 32 + lane < n) rk_next = S.w_rk[b * 32 + lane];
+      while (b >= 0) {
+        const int2 rk = rk_next;
+        const int i = b * 32 + lane;
+        b = cs_w_next_batch(s_bmap, nw, b + 1);
+        rk_next = make_int2(0, -1);
+        if (b >= 0 && b * 32 + lane < n) rk_next = S.w_rk[b * 32 + lane];
+        const bool cand = i < n && cs_w_is_candidate(t, rk);
+        const unsigned m = __ballot_sync(full, cand);
+        if (cand) {
+          const int at = ncand + __popc(m & ((1u << lane) - 1u));
+          if (at < 32) s_list[at] = i;
+        }
+        ncand += __popc(m);
+        kmax = max(kmax, __reduce_max_sync(full, cand ? rk.y : 0));
+      }
+      if (ncand <= 32 || hi - lo < min_width) break;
+      hi = lo + (hi - lo) / 2u;
+    }
+    if (tl && lane == 0 && tl_pieces == 0) tl[1] = cs_globaltimer();
+    tl_pieces++;
+    tl_cand = max(tl_cand, ncand);
+    if (ncand > 32 || force_general) tl_mode = 1;
+    if (ncand > 0) {
+      t.k1 = min(t.k1, kmax);
+      __syncwarp();
+      if (ncand <= 32 && !force_general)
+        cs_w_fast<TILED>(S, map, t, ncand, s_list, x1, y1, size, pitch_tiles, alpha);
+      else
+        cs_w_general<TILED>(S, map, t, n, x1, y1, size, pitch_tiles, alpha, s_val, s_cell, s_bmap, nw);
+      __syncwarp();
+    }
+    lo = hi;
+  }
+  if (tl && lane == 0) { tl[2] = cs_globaltimer(); tl[3] = (long long)tl_cand | ((long long)tl_mode << 16) | ((long long)tl_pieces << 20) | ((long long)ka << 32); }
+}
+
 template <bool TILED>
 __global__ void __launch_bounds__(CS_W_THREADS, 4)
 cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ int s_first[CS_W_LEVELS + 2];   // first task of each level (task 0 is ring 0); s_first[nlev] = number of tasks
-  __shared__ short s_wedges[CS_W_LEVELS];    // wedges per level
+  __shared__ int s_uniform[CS_W_LEVELS];     // > 0: the level is cut into this many equal wedges (the dense centre)
+  __shared__ int s_tot[CS_W_LEVELS];         // tasks of each level
+  __shared__ int s_T[CS_W_LEVELS];           // rays per wedge of a level cut by its sector counts
   __shared__ int s_nlev;
   __shared__ float sh_pose[5];
   __shared__ long long sh_vis[CS_W_WARPS];
   __shared__ unsigned s_val[CS_W_WARPS][CS_W_CAP];
   __shared__ uint32_t s_cell[CS_W_WARPS][CS_W_CAP];
   __shared__ int s_list[CS_W_WARPS][32];
+  __shared__ unsigned s_bmap[CS_W_WARPS][CS_W_BMAP_WORDS];
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long t_start = a.diag ? cs_globaltimer() : 0;  // diagnostics (cs_get_ring_cycles): block start, rays ready, table ready
   cs_pdl_launch_dependents();  // the next step's search may become resident once every block here has started
   // No griddepcontrol.wait in front: like the rings kernel, this one is resident before the search in front has ended; its
   // preparing blocks poll the pose words, everybody else the preparing blocks' count (see cs_rings_kernel).
@@ -363,9 +538,36 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const int alpha = S.quality;
   uint16_t* __restrict__ map = S.map;
   const int copies = S.ray_copies;
+  const int NL = S.w_levels;
   const unsigned slot = a.step_id & 1u;
   const unsigned long long ll_tag = (unsigned long long)a.step_id << 32;
-  int* alive = S.w_alive + (size_t)a.w_slot * (CS_W_LEVELS + 1);
+  const size_t top_words = (size_t)NL * (CS_W_SECTORS + 1) + 1;  // per (level, sector), per level, all valid rays
+  int* top = S.w_top + (size_t)a.w_slot * top_words;
+
+  // ---- while the pose is not out yet: pull the part of the map the scan can reach into L2.  The centre is the pose the
+  // step starts from (searchPose :728, or the given pose), the radius the ring count the host launched for plus the reach
+  // of the search; one 128-byte tile per thread.  (Harmless where the map is L2-resident already: the prefetch hits.)
+  if (TILED && a.w_prefetch) {
+    float sp[3];
+    if (a.step_mode == CS_STEP_UPDATE && a.do_search) cs_search_pose(S, hdr, a, sp);
+    else { sp[0] = hdr.odo[0]; sp[1] = hdr.odo[1]; sp[2] = hdr.odo[2]; }
+    const int cx = cs_cvt_i32(__fmul_rn(sp[0], scale)), cy = cs_cvt_i32(__fmul_rn(sp[1], scale));
+    const int R = a.max_ring_hint + 16 + (int)(4.0f * S.sigma_xy * scale);
+    if (cx > -R && cy > -R && cx < size + R && cy < size + R) {  // (NaN / far-off poses: nothing to fetch)
+      const int tx0 = max(cx - R, 0) >> 3, tx1 = min(cx + R, size - 1) >> 3;
+      const int ty0 = max(cy - R, 0) >> 3, ty1 = min(cy + R, size - 1) >> 3;
+      const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
+      const long long r2 = (long long)(R + 8) * (R + 8);
+      for (int i = (int)blockIdx.x * CS_W_THREADS + tid; i < tw * th; i += (int)gridDim.x * CS_W_THREADS) {
+        const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+        const long long dx = tx * 8 + 4 - cx, dy = ty * 8 + 4 - cy;
+        if (dx * dx + dy * dy <= r2) {
+          const uint16_t* line = map + ((size_t)ty * pitch_tiles + tx) * 64;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+        }
+      }
+    }
+  }
 
   // ---- ray preparation: the first nprep blocks take a.prep_group rays each, one ray per thread
   const int group = a.prep_group;
@@ -374,8 +576,8 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
     const int g_begin = blockIdx.x * group, g_end = min(n, g_begin + group);
     if (blockIdx.x == 0) {  // the other half of the counters is this step's to re-arm (nobody reads or counts into it now)
-      int* other = S.w_alive + (size_t)(a.w_slot ^ 1) * (CS_W_LEVELS + 1);
-      for (int i = tid; i <= CS_W_LEVELS; i += CS_W_THREADS) other[i] = 0;
+      int* other = S.w_top + (size_t)(a.w_slot ^ 1) * top_words;
+      for (int i = tid; i < (int)top_words; i += CS_W_THREADS) other[i] = 0;
     }
     if (tid < 5) {
       volatile unsigned long long* ll = S.ll_pose + tid;
@@ -393,7 +595,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       if (base + warp * 32 < g_end) {
         const bool in_range = i < g_end;
         const float2 p = in_range ? __ldg(points + i) : make_float2(1.f, 0.f);
-        cs_w_prepare(S, f, p, i, in_range, alive, vis);
+        cs_w_prepare(S, f, p, i, in_range, top, vis);
       }
     }
 #pragma unroll
@@ -417,30 +619,49 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     __threadfence();
   }
   __syncthreads();
+  const long long t_prep = a.diag ? cs_globaltimer() : 0;
+  // wedges per level.  Where the margins of ring k0 alone hold more rays than a wedge is sized for (the centre) the level is
+  // cut into equal wedges as wide as the margins; elsewhere into wedges of T rays each by the sector counts (boundaries at
+  // the T-quantiles of the level's rays, interpolated inside a sector: long rays cluster in a few directions, and equal
+  // wedges would leave some with several times the candidates a warp holds).
+  const int* tot_tab = top + (size_t)NL * CS_W_SECTORS;
+  for (int L = tid; L < NL; L += CS_W_THREADS) {
+    const int alive = __ldcg(tot_tab + L);
+    const int k0 = cs_w_level_first(L);
+    int tot = 0, uni = 0, T = 0;
+    if (alive > 0 && alive / (8 * k0) > CS_W_OWN / 2) {
+      uni = cs_w_wedges(alive, k0);
+      tot = uni;
+    } else if (alive > 0) {
+      T = CS_W_OWN - alive / (8 * k0);  // the margins of a wedge, 1 / k0 wide in all, hold alive / (8 k0) rays on average
+      tot = (alive + T - 1) / T;
+    }
+    s_tot[L] = tot; s_uniform[L] = uni; s_T[L] = T;
+  }
+  __syncthreads();
   if (warp == 0) {
     int total = 1, nlev = 0;  // task 0: ring 0
-    for (int L0 = 0; L0 < CS_W_LEVELS; L0 += 32) {
+    for (int L0 = 0; L0 < NL; L0 += 32) {
       const int L = L0 + lane;
-      const int al = L < CS_W_LEVELS ? __ldcg(alive + L) : 0;
-      const int W = al > 0 ? cs_w_wedges(al, cs_w_level_first(L)) : 0;
+      const int W = L < NL ? s_tot[L] : 0;
       int incl = W;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(full, incl, o);
         if (lane >= o) incl += u;
       }
-      if (L < CS_W_LEVELS) { s_first[L] = total + incl - W; s_wedges[L] = (short)W; }
+      if (L < NL) s_first[L] = total + incl - W;
       const unsigned has = __ballot_sync(full, W > 0);
       if (has) nlev = L0 + 32 - __clz(has);
       total += __shfl_sync(full, incl, 31);
-      if (!has) break;  // levels are reached by fewer and fewer rays: an empty chunk ends the scan
     }
     if (lane == 0) { s_first[nlev] = total; s_nlev = nlev; }
   }
   __syncthreads();
+  const long long t_sched = a.diag ? cs_globaltimer() : 0;
   const int nlev = s_nlev;
   const int n_tasks = s_first[nlev];
-  const int n_valid = __ldcg(alive + CS_W_LEVELS);
+  const int n_valid = __ldcg(tot_tab + NL);
   const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
@@ -449,12 +670,23 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // ---- tasks: static round-robin over the warps of the session's blocks, the (long) centre tasks first, starting with
   // the warps of the blocks that did not prepare rays
   if (n_valid > 0) {
-    const int total_warps = gridDim.x * CS_W_WARPS;
-    int gw = (int)blockIdx.x * CS_W_WARPS + warp - min(nprep, (int)gridDim.x - 1) * CS_W_WARPS;
-    if (gw < 0) gw += total_warps;
-    for (int task = gw; task < n_tasks; task += total_warps) {
+    // consecutive tasks go to different blocks (different SMs); the blocks that prepared rays come last.  When the table
+    // holds fewer tasks than the grid has warps, the rings of every task are split over 2, 4 or 8 warps (the kernel is a
+    // latency chain: shorter tasks, not fewer, end it sooner).
+    const int nblocks = (int)gridDim.x;
+    int sub = 1;
+    const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 8;
+    while (sub < sub_max && 1 + (n_tasks - 1) * (sub * 2) <= nblocks * CS_W_WARPS) sub *= 2;
+    const int n_sub_tasks = 1 + (n_tasks - 1) * sub;
+    int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
+    if (rb < 0) rb += nblocks;
+    for (int stask = rb + nblocks * warp; stask < n_sub_tasks; stask += nblocks * CS_W_WARPS) {
+      const int task = stask == 0 ? 0 : 1 + (stask - 1) / sub;
+      const int sub_j = stask == 0 ? 0 : (stask - 1) % sub;
       if (task == 0) {
+        if (a.diag && sj == 0 && lane == 0) { a.diag[0] = cs_globaltimer(); a.diag[4] = t_start; a.diag[5] = t_prep; a.diag[6] = t_sched; }
         cs_w_ring0<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha);
+        if (a.diag && sj == 0 && lane == 0) { a.diag[2] = cs_globaltimer(); a.diag[1] = a.diag[0]; a.diag[3] = 0; a.diag[7] = cs_smid(); }
         continue;
       }
       int L = 0;  // level of the task: last L with s_first[L] <= task
@@ -466,40 +698,52 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         }
         L = lo;
       }
-      const int W = s_wedges[L], w = task - s_first[L];
-      if (W <= 0 || w >= W) continue;  // (empty level inside the table: its range of tasks is empty)
-      CsWTask t;
-      t.k0 = cs_w_level_first(L);
-      t.k1 = cs_w_level_last(L);
-      t.blo = cs_w_beta(w, W);
-      t.bhi = cs_w_beta(w + 1, W);
-      const float eps = 0.5f / (float)t.k0 + 1e-4f;
-      t.flo = (float)t.blo * (1.0f / (float)(1 << CS_W_FIX)) - eps;
-      t.fhi = (float)t.bhi * (1.0f / (float)(1 << CS_W_FIX)) + eps;
-      t.wrap_lo = (w == 0) ? 8.0f - eps : 9.0f;
-      // candidates, in ray order; the largest dxc among them bounds the rings of the task
-      int ncand = 0, kmax = 0;
-      cs_w_for_batches(S, t, n, [&](int b) {
-        const int i = b * 32 + lane;
-        int2 rk = make_int2(0, -1);
-        if (i < n) rk = __ldcg(S.w_rk + i);
-        const bool cand = i < n && cs_w_is_candidate(t, rk);
-        const unsigned m = __ballot_sync(full, cand);
-        if (cand) {
-          const int at = ncand + __popc(m & ((1u << lane) - 1u));
-          if (at < 32) s_list[warp][at] = i;
+      const int r = task - s_first[L];
+      unsigned blo, bhi;
+      if (s_uniform[L] > 0) {
+        const int W = s_uniform[L];
+        if (r >= W) continue;
+        blo = cs_w_beta(r, W);
+        bhi = cs_w_beta(r + 1, W);
+      } else {
+        // wedge r of the level holds the rays number r T .. (r + 1) T - 1 in key order (by the sector counts)
+        const int c0 = __ldcg(top + L * CS_W_SECTORS + lane), c1 = __ldcg(top + L * CS_W_SECTORS + 32 + lane);
+        int p0 = c0, p1 = c1;  // inclusive prefix sums over the 64 sectors
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u0 = __shfl_up_sync(full, p0, o), u1 = __shfl_up_sync(full, p1, o);
+          if (lane >= o) { p0 += u0; p1 += u1; }
         }
-        ncand += __popc(m);
-        kmax = max(kmax, __reduce_max_sync(full, cand ? rk.y : 0));
-      });
-      if (ncand == 0) continue;
-      t.k1 = min(t.k1, kmax);
-      __syncwarp();
-      if (ncand <= 32 && !a.w_general)
-        cs_w_fast<TILED>(S, map, t, ncand, s_list[warp], x1, y1, size, pitch_tiles, alpha);
-      else
-        cs_w_general<TILED>(S, map, t, n, x1, y1, size, pitch_tiles, alpha, s_val[warp], s_cell[warp]);
-      __syncwarp();
+        p1 += __shfl_sync(full, p0, 31);
+        const int T = s_T[L], W = s_tot[L];
+        if (r >= W) continue;
+        unsigned bnd[2];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int x = (r + e) * T;  // key below which x rays of the level lie
+          const unsigned b0 = __ballot_sync(full, p0 >= x), b1 = __ballot_sync(full, p1 >= x);
+          unsigned v = 8u << CS_W_FIX;
+          if (x <= 0) v = 0u;
+          else if (b0 | b1) {
+            const int sec = b0 ? __ffs(b0) - 1 : 32 + __ffs(b1) - 1;
+            const int incl = sec < 32 ? __shfl_sync(full, p0, sec) : __shfl_sync(full, p1, sec - 32);
+            const int cs_ = sec < 32 ? __shfl_sync(full, c0, sec) : __shfl_sync(full, c1, sec - 32);
+            v = ((unsigned)sec << (CS_W_FIX - 3)) + (((unsigned)(x - (incl - cs_))) << (CS_W_FIX - 3)) / (unsigned)cs_;
+          }
+          bnd[e] = v;
+        }
+        blo = bnd[0];
+        bhi = (r == W - 1) ? (8u << CS_W_FIX) : bnd[1];
+      }
+      // this warp's share of the level's rings
+      const int k0 = cs_w_level_first(L), k1 = cs_w_level_last(L);
+      const int per = (k1 - k0 + sub) / sub;
+      const int ka = k0 + sub_j * per, kb = min(k1, ka + per - 1);
+      if (ka > k1) continue;
+      long long* tl = (a.diag && sj == 0 && stask < a.diag_rings) ? a.diag + (size_t)stask * 8 : nullptr;
+      if (tl && lane == 0) { tl[0] = cs_globaltimer(); tl[4] = t_start; tl[5] = t_prep; tl[6] = t_sched; tl[7] = cs_smid() | ((long long)blockIdx.x << 16); }
+      cs_w_run<TILED>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
+                      s_list[warp], s_bmap[warp], tl);
     }
   }
   cs_pdl_wait();  // the kernel in front has long finished; this only makes "this grid done" imply "that grid done"

@@ -1,0 +1,52 @@
+"""Diagnostics: per-task timeline (%globaltimer stamps) of the wedge kernel for one Update.
+usage: python tools/wedge_probe.py [cfg2|cfg3|cfg1]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import slam.net_b200 as sn
+from slam.net_b200 import synth
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+P, size, phys, iters, threads = {"cfg2": (1024, 2048, 40.0, 1024, 4), "cfg3": (8192, 4096, 40.96, 1, 1), "cfg1": (360, 1600, 40.0, 1000, 1)}[wl]
+n_scans = 12
+rp = synth.make_replay(n_scans, P, phys)
+p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P)
+if wl == "cfg3":
+    p.set_position_search_beginning(2 ** 31 - 1)
+log = sn.ScanLog(n_scans, P, n_offsets=0)
+for k in range(n_scans):
+    log.set(k, rp.points[k], rp.odometry[k])
+log.upload()
+p.ring_cycles()
+p.replay(log, 0, n_scans - 2, want_results=False)
+p.sync()
+for rep in range(2):
+    p.ring_cycles()  # (clears nothing; records are overwritten by the next step)
+    p.replay(log, n_scans - 2 + rep, 1, want_results=False)
+    p.sync()
+    rc = p.ring_cycles(size)
+    rc = rc[rc[:, 0] > 0]
+    t0 = rc[:, 4].min()
+    us = lambda a: (a - t0) / 1e3
+    print("---- step %d: %d tasks recorded on %d SMs" % (rep, len(rc), len(np.unique(rc[:, 7]))))
+    q = lambda a: "min %6.2f p50 %6.2f p90 %6.2f max %6.2f" % (a.min(), np.percentile(a, 50), np.percentile(a, 90), a.max())
+    print("block start      ", q(us(rc[:, 4])))
+    print("rays ready       ", q(us(rc[:, 5])))
+    print("table ready      ", q(us(rc[:, 6])))
+    print("task start       ", q(us(rc[:, 0])))
+    print("task filtered    ", q(us(rc[:, 1])))
+    print("task end         ", q(us(rc[:, 2])))
+    blk = (rc[:, 7] >> 16).astype(int)
+    ub, first = np.unique(blk, return_index=True)
+    sel = first[:: max(1, len(first) // 24)]
+    print("blocks (id: start / rays ready / table ready):", ", ".join("%d: %.1f/%.1f/%.1f" % (blk[i], us(rc[i, 4]), us(rc[i, 5]), us(rc[i, 6])) for i in sel))
+    k0 = (rc[:, 3] >> 32).astype(int)
+    cand = (rc[:, 3] & 0xffff).astype(int)
+    mode = ((rc[:, 3] >> 16) & 0xf).astype(int)
+    pieces = ((rc[:, 3] >> 20) & 0xfff).astype(int)
+    for k in sorted(set(k0)):
+        m = k0 == k
+        print("k0 %5d: %4d tasks  cand p50 %3d max %3d  general %3d  pieces max %d | filter us p50 %5.2f max %5.2f | body us p50 %6.2f max %6.2f | end max %6.2f" % (
+            k, m.sum(), np.percentile(cand[m], 50), cand[m].max(), mode[m].sum(), pieces[m].max(),
+            np.percentile((rc[m, 1] - rc[m, 0]) / 1e3, 50), ((rc[m, 1] - rc[m, 0]) / 1e3).max(),
+            np.percentile((rc[m, 2] - rc[m, 1]) / 1e3, 50), ((rc[m, 2] - rc[m, 1]) / 1e3).max(), us(rc[m, 2]).max()))
