@@ -435,8 +435,9 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
                 q.close()
             if oracle_check:
                 from oracle import oracle as orc
-                o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"])
-                wk = orc.Worker(pow2_threads(n_cand, os.cpu_count() or 1))
+                T = pow2_threads(n_cand, os.cpu_count() or 1)  # same flat candidate order, fewer and longer threads
+                o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, n_cand // T, T)
+                wk = orc.Worker(T)
                 for k in range(n_total):
                     off = sn.philox_offsets(args.seed, k, n_cand, SIGMA_XY, SIGMA_THETA) if k >= PRIME_SCANS else None
                     o.update(rp.points[k], rp.odometry[k], off, worker=wk)

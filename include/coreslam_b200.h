@@ -32,7 +32,7 @@ typedef enum cs_status {
   CS_ERR_OUT_OF_MEMORY = 4,
   CS_ERR_CAPACITY = 5,    /* more points / candidates than the handle was created for */
   CS_ERR_STATE = 6,
-  CS_ERR_NCCL = 7
+  CS_ERR_NCCL = 7         /* multi-GPU exchange failed (peer mapping refused, or a rank of the group never delivered its key) */
 } cs_status;
 
 /* cs_config.flags */
@@ -160,6 +160,24 @@ cs_status cs_update_segments(cs_processor* h, const float* rays, const int32_t* 
 /* ScanSegmentsToCloud alone (:187-207) for an explicit odometry pose: points_out receives n_rays * (x, y). */
 cs_status cs_segments_to_cloud(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
                                int32_t n_segments, const float odometry_pose[3], float* points_out);
+
+/* Candidate-split GROUP: the same split as cs_update_begin / cs_update_finish below, but with the 8-byte exchange done
+ * INSIDE the search kernel — the thread that owns this GPU's arg-min writes the packed key into every rank's table over
+ * peer-mapped memory (NVLink), waits until its own table holds the world's keys, takes the minimum and publishes the
+ * pose: no collective launch, no second kernel, the kernels of a scan stay chained.  After cs_group_attach every
+ * cs_update / cs_update_segments / cs_replay of the handle evaluates this rank's slice
+ * [rank*(T*I+1)/world, (rank+1)*(T*I+1)/world) and ends on the group's winner; all ranks must feed the same scans in the
+ * same order (and, in verification mode, the same full candidate table).  A rank that waits longer than 2 s for the
+ * others fails the call with CS_ERR_NCCL.  Replaces the cross-thread arg-min of ParallelMonteCarloSearch
+ * (CoreSLAMProcessor.cs:694-705) at GPU granularity.
+ *   one process per GPU:  cs_group_export on every rank, exchange the 64-byte handles by any means (MPI, a socket,
+ *                         torch.distributed.all_gather), cs_group_attach(rank, world, handles) on every rank;
+ *   one process, several handles (one per device, or several on one device): cs_group_attach_local(rank, world, peers). */
+typedef struct { unsigned char bytes[64]; } cs_ipc_handle;
+cs_status cs_group_export(cs_processor* h, cs_ipc_handle* out);
+cs_status cs_group_attach(cs_processor* h, int32_t rank, int32_t world, const cs_ipc_handle* handles /* world entries */);
+cs_status cs_group_attach_local(cs_processor* h, int32_t rank, int32_t world, cs_processor* const* peers /* world entries */);
+cs_status cs_group_detach(cs_processor* h);
 
 /* Multi-GPU candidate split (very large candidate sets, BASELINE cfg4): the map is replicated, GPU g
  * evaluates the flat candidate indices [cand_first, cand_first + cand_count) of the same scan, and ONE

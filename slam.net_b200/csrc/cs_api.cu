@@ -122,6 +122,13 @@ struct cs_processor {
   CsStepArgs pending_args{};
   int pending_points = 0, pending_rings = 0;
 
+  // candidate-split group (cs_group_*): this rank's exchange table and the (peer-mapped) tables of all ranks
+  int group_rank = 0, group_world = 0;
+  unsigned xchg_seq = 0;
+  unsigned long long* d_xchg = nullptr;
+  unsigned long long* xchg_peer[CS_GROUP_MAX] = {};
+  bool xchg_ipc[CS_GROUP_MAX] = {};  // opened with cudaIpcOpenMemHandle (to be closed on detach)
+
   uint64_t launches = 0;
   unsigned step_counter = 0;
   Timing tm;
@@ -662,6 +669,21 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   return CS_OK;
 }
 
+// A handle that belongs to a candidate-split group evaluates its slice of the flat candidate indices and exchanges the
+// arg-min inside the search kernel (cs_exchange_min); the exchange number advances with every searched scan, identically on
+// every rank.
+void apply_group(cs_processor* h, CsStepArgs& a) {
+  if (h->group_world <= 1 || !a.do_search || a.empty_cloud) return;
+  const long long n_flat = (long long)h->n_cand + 1;
+  const long long lo = (long long)h->group_rank * n_flat / h->group_world, hi = (long long)(h->group_rank + 1) * n_flat / h->group_world;
+  a.cand_first = (int)lo;
+  a.cand_count = (int)(hi - lo);
+  a.xchg_world = h->group_world;
+  a.xchg_rank = h->group_rank;
+  a.xchg_seq = ++h->xchg_seq;
+  for (int p = 0; p < h->group_world; p++) a.xchg_peer[p] = h->xchg_peer[p];
+}
+
 cs_status wait_for_pose(cs_processor* h, unsigned seq, cudaEvent_t fallback_event) {
   auto t0 = std::chrono::steady_clock::now();
   if (h->cfg.flags & CS_FLAG_NO_HOST_SPIN) {
@@ -918,6 +940,9 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_rays);
   cudaFree(h->d_batch_max);
   cudaFree(h->d_prep_words);
+  for (int p = 0; p < CS_GROUP_MAX; p++)
+    if (h->xchg_ipc[p] && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
+  cudaFree(h->d_xchg);
   cudaFree(h->d_ray_dbg);
   cudaFree(h->d_w_rk);
   cudaFree(h->d_w_bkey);
@@ -1251,7 +1276,8 @@ static double max_range_of_segments(const float* rays, const int32_t* seg_first,
 }
 
 static cs_status stage_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
-                              const float* cand_offsets, bool timing, CsStepArgs* out_args, const SegInput* seg = nullptr) {
+                              const float* cand_offsets, bool timing, CsStepArgs* out_args, const SegInput* seg = nullptr,
+                              bool split_phase = false) {
   if ((!points && !seg && n_points > 0) || !odometry_pose || n_points < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_update: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
   if (!finite3(odometry_pose)) return fail(h, CS_ERR_INVALID_ARGUMENT, "odometry pose is NaN");
@@ -1319,6 +1345,7 @@ static cs_status stage_update(cs_processor* h, const float* points, int32_t n_po
   a.cand_count = h->n_cand + 1;
   a.s2_host_points = n_points;
   a.empty_cloud = (do_search && n_points == 0) ? 1 : 0;
+  if (!split_phase) apply_group(h, a);  // (cs_update_begin / _finish: the caller exchanges the key between the phases)
   *out_args = a;
   return CS_OK;
 }
@@ -1334,6 +1361,9 @@ static cs_status complete_update(cs_processor* h, const CsStepArgs& a, bool timi
     st = collect_timing(h, true);
     if (st != CS_OK) return st;
   }
+  if (reinterpret_cast<const CsDevResult*>(h->h_slot)->searched < 0)
+    return fail(h, CS_ERR_NCCL, "candidate-split group: a rank never delivered its arg-min (exchange timed out after %.1f s)",
+                (double)CS_XCHG_TIMEOUT_NS * 1e-9);
   if (out) {
     copy_result(out, reinterpret_cast<const CsDevResult*>(h->h_slot));
     out->visits = -1;  // counted on the device while the integration runs; cs_get_visits() after cs_sync()
@@ -1408,7 +1438,7 @@ cs_status cs_update_begin(cs_processor* h, const float* points, int32_t n_points
     return fail(h, CS_ERR_INVALID_ARGUMENT, "candidate slice [%d, %d) outside [0, T*I+1 = %d)", cand_first,
                 cand_first + cand_count, h->n_cand + 1);
   CsStepArgs a{};
-  cs_status st = stage_update(h, points, n_points, odometry_pose, cand_offsets, false, &a);
+  cs_status st = stage_update(h, points, n_points, odometry_pose, cand_offsets, false, &a, nullptr, true);
   if (st != CS_OK) return st;
   a.cand_first = cand_first;
   a.cand_count = cand_count;
@@ -1437,6 +1467,115 @@ cs_status cs_update_finish(cs_processor* h, cs_result* out) {
   cs_status st = launch_step(h, a, h->pending_points, h->pending_rings, false, 2, CS_PHASE_FINISH);
   if (st != CS_OK) return st;
   return complete_update(h, a, false, out);
+}
+
+// ---- candidate-split group with the exchange inside the search kernel (SURVEY 8b "cs_group_create", 8e) ------------------
+static cs_status group_table(cs_processor* h) {
+  if (!h->d_xchg) {
+    const size_t bytes = (size_t)2 * CS_GROUP_MAX * 2 * sizeof(unsigned long long);
+    CS_CUDA(h, cudaMalloc(&h->d_xchg, bytes));
+    CS_CUDA(h, cudaMemset(h->d_xchg, 0, bytes));
+  }
+  return CS_OK;
+}
+
+cs_status cs_group_export(cs_processor* h, cs_ipc_handle* out) {
+  CS_CHECK_HANDLE(h);
+  if (!out) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_group_export: null out");
+  cs_status st = group_table(h);
+  if (st != CS_OK) return st;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(cs_ipc_handle), "cs_ipc_handle too small");
+  cudaIpcMemHandle_t mh;
+  CS_CUDA(h, cudaIpcGetMemHandle(&mh, h->d_xchg));
+  memset(out, 0, sizeof(*out));
+  memcpy(out, &mh, sizeof(mh));
+  return CS_OK;
+}
+
+cs_status cs_group_detach(cs_processor* h) {
+  CS_CHECK_HANDLE(h);
+  CS_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int p = 0; p < CS_GROUP_MAX; p++) {
+    if (h->xchg_ipc[p] && h->xchg_peer[p]) cudaIpcCloseMemHandle(h->xchg_peer[p]);
+    h->xchg_peer[p] = nullptr;
+    h->xchg_ipc[p] = false;
+  }
+  h->group_world = 0;
+  h->group_rank = 0;
+  h->xchg_seq = 0;
+  if (h->d_xchg) CS_CUDA(h, cudaMemset(h->d_xchg, 0, (size_t)2 * CS_GROUP_MAX * 2 * sizeof(unsigned long long)));
+  cudaGetLastError();
+  return CS_OK;
+}
+
+static cs_status group_check(cs_processor* h, int32_t rank, int32_t world) {
+  if (world < 1 || world > CS_GROUP_MAX || rank < 0 || rank >= world)
+    return fail(h, CS_ERR_INVALID_ARGUMENT, "group: rank %d of %d (at most %d ranks)", rank, world, CS_GROUP_MAX);
+  if ((long long)h->n_cand + 1 < world) return fail(h, CS_ERR_INVALID_ARGUMENT, "group: fewer candidates than ranks");
+  if (h->pending) return fail(h, CS_ERR_STATE, "a split-phase update is in flight");
+  return CS_OK;
+}
+
+cs_status cs_group_attach(cs_processor* h, int32_t rank, int32_t world, const cs_ipc_handle* handles) {
+  CS_CHECK_HANDLE(h);
+  cs_status st = group_check(h, rank, world);
+  if (st != CS_OK) return st;
+  if (!handles && world > 1) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_group_attach: null handles");
+  st = cs_group_detach(h);
+  if (st == CS_OK) st = group_table(h);
+  if (st != CS_OK) return st;
+  for (int p = 0; p < world; p++) {
+    if (p == rank) { h->xchg_peer[p] = h->d_xchg; continue; }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, &handles[p], sizeof(mh));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      cs_group_detach(h);
+      return fail(h, CS_ERR_NCCL, "cs_group_attach: cudaIpcOpenMemHandle(rank %d) failed: %s", p, cudaGetErrorString(e));
+    }
+    h->xchg_peer[p] = static_cast<unsigned long long*>(ptr);
+    h->xchg_ipc[p] = true;
+  }
+  h->group_rank = rank;
+  h->group_world = world;
+  return CS_OK;
+}
+
+cs_status cs_group_attach_local(cs_processor* h, int32_t rank, int32_t world, cs_processor* const* peers) {
+  CS_CHECK_HANDLE(h);
+  cs_status st = group_check(h, rank, world);
+  if (st != CS_OK) return st;
+  if (!peers && world > 1) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_group_attach_local: null peers");
+  st = cs_group_detach(h);
+  if (st == CS_OK) st = group_table(h);
+  if (st != CS_OK) return st;
+  for (int p = 0; p < world; p++) {
+    cs_processor* q = (p == rank) ? h : peers[p];
+    if (!q) { cs_group_detach(h); return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_group_attach_local: peer %d is null", p); }
+    if (q != h) {
+      if (cudaSetDevice(q->device) != cudaSuccess || group_table(q) != CS_OK) {
+        cudaSetDevice(h->device);
+        cs_group_detach(h);
+        return fail(h, CS_ERR_CUDA, "cs_group_attach_local: peer %d has no exchange table", p);
+      }
+      cudaSetDevice(h->device);
+      if (q->device != h->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          cudaGetLastError();
+          cs_group_detach(h);
+          return fail(h, CS_ERR_NCCL, "cs_group_attach_local: no peer access to device %d: %s", q->device, cudaGetErrorString(e));
+        }
+        cudaGetLastError();
+      }
+    }
+    h->xchg_peer[p] = q->d_xchg;
+  }
+  h->group_rank = rank;
+  h->group_world = world;
+  return CS_OK;
 }
 
 cs_status cs_sync(cs_processor* h) {
@@ -1919,6 +2058,7 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     a.cand_first = 0;
     a.cand_count = h->n_cand + 1;
     a.s2_host_points = log->h_hdr[sidx].n_points;
+    apply_group(h, a);
     cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, rings_hint(h, log->h_max_range[sidx]), per_kernel, 2);
     if (st != CS_OK) return st;
     h->parity ^= 1;

@@ -22,6 +22,9 @@
 #define CS_TS_NO_OBSTACLE 65500  // CoreSLAMProcessor.cs:21
 #define CS_TS_OBSTACLE 0         // CoreSLAMProcessor.cs:22
 
+#define CS_GROUP_MAX 8                      // most GPUs of a candidate-split group (one NVSwitch box)
+#define CS_XCHG_TIMEOUT_NS 2000000000ll     // a rank that waits this long for the others' keys gives up (searched = -1)
+
 enum CsCandMode { CS_CAND_PHILOX = 0, CS_CAND_OFFSETS = 1, CS_CAND_ABSOLUTE = 2 };
 enum CsStepMode { CS_STEP_UPDATE = 0, CS_STEP_SEARCH_ONLY = 1, CS_STEP_INTEGRATE_ONLY = 2 };
 
@@ -172,7 +175,15 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned long long s2_seed;
   int s2_size, s2_pitch_tiles;
   float s2_scale, s2_sigma_xy, s2_sigma_theta;
-  int w_slot;                    // which half of CsSession::w_alive this step counts into (alternates per drawn step)
+  // candidate split over a group of GPUs with the arg-min exchanged inside the search kernel (cs_group_attach): rank r's
+  // table holds, per half (exchange number & 1) and rank, two words {packed key, tag}; every rank writes its key into every
+  // table over peer-mapped memory and waits for the world's keys in its own
+  int xchg_world;                // 0 / 1: no exchange
+  int xchg_rank;
+  unsigned xchg_seq;             // exchange number, the same on every rank
+  unsigned xchg_pad;
+  unsigned long long* xchg_peer[CS_GROUP_MAX];
+  int w_slot;                    // which half of CsSession::w_top this step counts into (alternates per drawn step)
   int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
   int w_sub_max;                 // most warps the rings of one task are split over (0: 8)
   int w_prefetch;                // 1: the wedge kernel prefetches the map around the pose into L2 while it waits for the pose
@@ -204,7 +215,7 @@ __device__ __forceinline__ void cs_pdl_wait() { asm volatile("griddepcontrol.wai
 __device__ __forceinline__ void cs_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // diagnostics only (a.diag != nullptr): wall-clock stamps and the SM a block ran on
-__device__ __forceinline__ long long cs_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ long long cs_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
 __device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
 #define CS_DIAG_SEARCH_BLOCKS 8192  // search-kernel timeline records kept after the per-ring records
 
@@ -500,6 +511,35 @@ __device__ __forceinline__ void cs_prepare_rays(CsSession& S, const float2* __re
   }
 }
 
+// The one exchange step of the candidate split, run by the publishing thread: this rank's packed arg-min goes
+// into every rank's table (8-byte stores over NVLink / peer-mapped memory, key first, then the tag behind a system fence),
+// then the thread waits until its own table holds the world's keys of this exchange and takes their minimum — the same
+// value on every rank.  Two halves by exchange parity: a rank that runs ahead writes the next exchange into the other half.
+__device__ __forceinline__ unsigned long long cs_exchange_min(const CsStepArgs& a, unsigned long long key, bool& timed_out) {
+  const size_t half = (size_t)(a.xchg_seq & 1u) * CS_GROUP_MAX * 2;
+  const unsigned long long tag = 0x100000000ull | (unsigned long long)a.xchg_seq;  // never 0
+  for (int p = 0; p < a.xchg_world; p++) {
+    volatile unsigned long long* slot = a.xchg_peer[p] + half + (size_t)a.xchg_rank * 2;
+    slot[0] = key;
+  }
+  __threadfence_system();
+  for (int p = 0; p < a.xchg_world; p++) {
+    volatile unsigned long long* slot = a.xchg_peer[p] + half + (size_t)a.xchg_rank * 2;
+    slot[1] = tag;
+  }
+  volatile unsigned long long* mine = a.xchg_peer[a.xchg_rank] + half;
+  unsigned long long best = ~0ull;
+  const long long t0 = cs_globaltimer();
+  for (int r = 0; r < a.xchg_world; r++) {
+    while (mine[2 * r + 1] != tag) {
+      if (cs_globaltimer() - t0 > CS_XCHG_TIMEOUT_NS) { timed_out = true; return key; }
+    }
+    __threadfence_system();
+    best = min(best, mine[2 * r]);
+  }
+  return best;
+}
+
 // Glue + publish by one thread (the rays are prepared by the first blocks of the rings kernel).
 __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
                                            CsDevResult* result, bool have_guess = false, unsigned long long guess = 0ull) {
@@ -508,8 +548,11 @@ __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr
   const bool need_key = a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search;
   unsigned long long key = 0ull;
   if (need_key) key = a.empty_cloud ? (0x7fffffffull << 32) : atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
+  bool timed_out = false;
+  const bool exchange = need_key && a.xchg_world > 1 && !a.empty_cloud;
+  if (exchange) key = cs_exchange_min(a, key, timed_out);
   CsGlue g;
-  if (have_guess && need_key) {
+  if (have_guess && need_key && !exchange) {
     // The arg-min as this thread last saw it is almost always the final one: the glue arithmetic runs on it while
     // the read above is in flight, and is redone only if the final key differs.
     cs_glue_pose(S, hdr, a, cand, guess, g);
@@ -518,6 +561,7 @@ __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr
     cs_glue_pose(S, hdr, a, cand, key, g);
   }
   if (d) d[1] = cs_globaltimer();
+  if (timed_out) g.searched = -1;  // the host turns this into CS_ERR_NCCL: a rank of the group never delivered its key
   cs_glue_publish(S, hdr, a, result, g, d);
   if (d) d[3] = cs_globaltimer();
 }

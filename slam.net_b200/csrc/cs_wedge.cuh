@@ -113,6 +113,7 @@ __device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, 
     if (counted) same = __match_any_sync(cm, sector);
     const bool leader = counted && lane == __ffs(same) - 1;
     const int top_level = cs_w_level_of(max(bm, 1));
+#pragma unroll 4
     for (int L = 0; L <= top_level; L++) {
       const unsigned here = __ballot_sync(full, counted && r.dxc >= cs_w_level_first(L));
       if (leader && (here & same)) atomicAdd(&top[L * CS_W_SECTORS + sector], (int)__popc(here & same));
@@ -130,16 +131,22 @@ __device__ __forceinline__ int cs_w_batch_map(const CsSession& S, const CsWTask&
   const int nb = (n + 31) >> 5;
   const int nw = (nb + 31) >> 5;
   __syncwarp();  // (readers of the previous map are done)
-  for (int w = 0; w < nw; w++) {
-    const int bi = w * 32 + lane;
-    bool ov = false;
-    if (bi < nb) {
-      const int bm = S.batch_max[bi];  // (both loads in flight together)
-      const float2 kk = S.w_bkey[bi];
-      ov = bm >= t.k0 && ((kk.y >= t.flo && kk.x < t.fhi) || kk.y >= t.wrap_lo);
+  for (int w0 = 0; w0 < nw; w0 += 4) {  // four words per round trip
+    int bm[4];
+    float2 kk[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int bi = (w0 + u) * 32 + lane;
+      bm[u] = -1;
+      kk[u] = make_float2(0.f, 0.f);
+      if (bi < nb) { bm[u] = S.batch_max[bi]; kk[u] = S.w_bkey[bi]; }
     }
-    const unsigned om = __ballot_sync(full, ov);
-    if (lane == 0) s_bmap[w] = om;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const bool ov = bm[u] >= t.k0 && ((kk[u].y >= t.flo && kk[u].x < t.fhi) || kk[u].y >= t.wrap_lo);
+      const unsigned om = __ballot_sync(full, ov);
+      if (lane == 0 && w0 + u < nw) s_bmap[w0 + u] = om;
+    }
   }
   __syncwarp();
   return nw;
@@ -199,53 +206,104 @@ struct CsWWalk {
     x += dxM; y += dyM; pos += cside;
   }
   __device__ __forceinline__ int posn() const { return pos == 8 * k ? 0 : pos; }  // the corner 8k is position 0
-  __device__ __forceinline__ int pixval() const {  // closed form of :402-428 (cs_ray_pixval)
-    if (k <= b0) return CS_TS_NO_OBSTACLE + max(k - a0 + 1, 0) * incv;
-    if (k < c0) return CS_TS_NO_OBSTACLE;
-    const int j = k - c0 + 1;
-    return CS_TS_NO_OBSTACLE + (ndt - j) * incv + min(j, kc);
+  __device__ __forceinline__ int pixval() const {  // closed form of :402-428 (cs_ray_pixval), without branches
+    const int nd = max(k - a0 + 1, 0);               // descending steps taken so far (k <= b0)
+    const int j = max(k - c0 + 1, 0);                // ascending steps taken so far (k >= c0); 0 in the flat zone between
+    const int steps = (k <= b0) ? nd : ((j > 0) ? ndt - j : 0);
+    return CS_TS_NO_OBSTACLE + steps * incv + ((k <= b0) ? 0 : min(j, kc));
   }
 };
 
-// ---- ring 0: the start cell, visited by every valid ray, in ray order (one warp)
+// ---- the centre: rings 0 .. CS_W_CENTER - 1, drawn by ONE block for all rays.  Every ray crosses every one of these rings,
+// and almost every visit there carries the free-space pixval (the hole profile starts a hole width before the hit): blends
+// of one pixval commute with themselves, so a cell visited n times with that pixval alone just needs n — counted with
+// shared-memory atomics, one thread per ray — and the exact fixed-point early-out.  A cell that also sees another pixval
+// (an obstacle within a few cells of the sensor) is flagged and redone exactly, in ray order, by one warp.
+#define CS_W_CENTER 8
+#define CS_W_CENTER_CELLS (1 + 4 * CS_W_CENTER * (CS_W_CENTER - 1))  // ring 0: 1 cell, ring k: 8k cells
+__device__ __forceinline__ int cs_w_center_index(int k, int posn) { return k == 0 ? 0 : 1 + 4 * k * (k - 1) + posn; }
+
+// one cell of ring k (position p), exactly: every ray in ray order (one warp; all lanes keep the running value)
 template <bool TILED>
-__device__ void cs_w_ring0(const CsSession& S, uint16_t* __restrict__ map, int n, int x1, int y1, int size, int pitch_tiles, int alpha) {
+__device__ void cs_w_cell_exact(const CsSession& S, uint16_t* __restrict__ map, int n, int k, int p, int x1, int y1, int size,
+                                int pitch_tiles, int alpha) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const uint32_t cell = cs_cell_offset<TILED>(x1, y1, size, pitch_tiles);
+  int x, y;
+  cs_w_pos_to_xy(p, k, x1, y1, x, y);
+  if ((unsigned)x >= (unsigned)size || (unsigned)y >= (unsigned)size) return;
+  const uint32_t cell = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
   CsBlendState st;
-  st.val = 0; st.last_pv = -1; st.fixed = false;
-  bool loaded = false;
-  int4 q_next = make_int4(0, 0, 0, 0);
-  if (lane < n) q_next = S.rays[lane];
+  st.val = (int)__ldcg(map + cell); st.last_pv = -1; st.fixed = false;
   for (int base = 0; base < n; base += 32) {
     const int i = base + lane;
-    const int4 q = q_next;
-    if (i + 32 < n) q_next = S.rays[i + 32];  // the next batch's rays are in flight while this one is applied
-    int pv = 0;
-    bool valid = false;
+    int pv = 0, pos = 0;
+    uint32_t c2 = 0;
+    bool hit = false;
     if (i < n) {
-      const CsRay r = cs_unpack_ray(q);
-      valid = (r.flags & 1) != 0;
-      if (valid) pv = cs_ray_pixval(r, 0);
+      const CsRay r = cs_unpack_ray(S.rays[i]);
+      hit = cs_ring_visit<TILED>(r, k, x1, y1, size, pitch_tiles, pos, c2, pv) && pos == p;
     }
-    unsigned act = __ballot_sync(full, valid);
-    if (!act) continue;
-    if (!loaded) { st.val = (int)__ldcg(map + cell); loaded = true; }  // every lane keeps the same running value
-    const int first = __ffs(act) - 1;
-    const int pv0 = __shfl_sync(full, pv, first);
-    if (__ballot_sync(full, valid && pv != pv0) == 0u) {
-      st.apply_n(pv0, __popc(act), alpha);  // one pixval: a count, with the exact fixed-point early-out
-      st.fixed = false; st.last_pv = -1;
-    } else {
-      while (act) {
-        const int l = __ffs(act) - 1;
-        act &= act - 1;
-        st.apply(__shfl_sync(full, pv, l), alpha);
+    unsigned act = __ballot_sync(full, hit);
+    while (act) {
+      const int l = __ffs(act) - 1;
+      act &= act - 1;
+      st.apply(__shfl_sync(full, pv, l), alpha);
+    }
+  }
+  if (lane == 0) __stcg(map + cell, (uint16_t)st.val);
+}
+
+template <bool TILED>
+__device__ void cs_w_center(const CsSession& S, uint16_t* __restrict__ map, int n, int x1, int y1, int size, int pitch_tiles, int alpha,
+                            unsigned* s_cnt /* CS_W_CENTER_CELLS */, int* s_flagged /* 1 + CS_W_CENTER_CELLS */) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < CS_W_CENTER_CELLS; i += CS_W_THREADS) s_cnt[i] = 0u;
+  if (tid == 0) s_flagged[0] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += CS_W_THREADS) {
+    const CsRay r = cs_unpack_ray(S.rays[i]);
+    if (!(r.flags & 1)) continue;
+    CsWWalk w;
+    w.init(r, true, 0, x1, y1);
+#pragma unroll
+    for (int k = 0; k < CS_W_CENTER; k++) {
+      if (k > 0) w.step();
+      if (k <= w.dxc) {
+        const int idx = cs_w_center_index(k, w.posn());
+        atomicAdd(&s_cnt[idx], 1u);
+        if (w.pixval() != CS_TS_NO_OBSTACLE) atomicOr(&s_cnt[idx], 0x80000000u);
       }
     }
   }
-  if (loaded && lane == 0) __stcg(map + cell, (uint16_t)st.val);
+  __syncthreads();
+  for (int c = tid; c < CS_W_CENTER_CELLS; c += CS_W_THREADS) {
+    const unsigned wd = s_cnt[c];
+    const int cnt = (int)(wd & 0x7fffffffu);
+    if (cnt == 0) continue;
+    if (wd >> 31) { s_flagged[1 + atomicAdd(&s_flagged[0], 1)] = c; continue; }
+    int k = 0;
+#pragma unroll
+    for (int kk = 1; kk < CS_W_CENTER; kk++) if (c >= 1 + 4 * kk * (kk - 1)) k = kk;
+    const int p = k == 0 ? 0 : c - (1 + 4 * k * (k - 1));
+    int x, y;
+    cs_w_pos_to_xy(p, k, x1, y1, x, y);
+    if ((unsigned)x >= (unsigned)size || (unsigned)y >= (unsigned)size) continue;  // (cannot happen for clipped rays)
+    const uint32_t cell = cs_cell_offset<TILED>(x, y, size, pitch_tiles);
+    CsBlendState st;
+    st.val = (int)__ldcg(map + cell); st.last_pv = -1; st.fixed = false;
+    st.apply_n(CS_TS_NO_OBSTACLE, cnt, alpha);
+    __stcg(map + cell, (uint16_t)st.val);
+  }
+  __syncthreads();
+  const int nf = s_flagged[0];
+  for (int f = warp; f < nf; f += CS_W_WARPS) {
+    const int c = s_flagged[1 + f];
+    int k = 0;
+#pragma unroll
+    for (int kk = 1; kk < CS_W_CENTER; kk++) if (c >= 1 + 4 * kk * (kk - 1)) k = kk;
+    cs_w_cell_exact<TILED>(S, map, n, k, k == 0 ? 0 : c - (1 + 4 * k * (k - 1)), x1, y1, size, pitch_tiles, alpha);
+  }
 }
 
 // Folds the visits of one ring held by the lanes of a warp (inw lanes: position posn, pixval pv) into the staged cells:
@@ -261,14 +319,14 @@ __device__ __forceinline__ void cs_w_fold(bool inw, int posn, int pv, int slot, 
   int v = 0;
   if (inw) {
     const unsigned grp = __match_any_sync(act, posn);
-    lead = lane == __ffs(grp) - 1;
+    lead = (grp & ((1u << lane) - 1u)) == 0u;
     unsigned same = grp;
-    const bool multi = (grp & (grp - 1)) != 0u;  // every lane of a group sees the same grp
+    const bool multi = (grp & (grp - 1u)) != 0u;  // every lane of a group sees the same grp
     const unsigned mm = __ballot_sync(act, multi);
     if (multi) same = __match_any_sync(mm, ((unsigned long long)(unsigned)posn << 32) | (unsigned)pv);
     if (lead) {
       v = (int)(s_val[slot] & 0xffffu);
-      if (same == grp) {
+      if (same == grp) {  // one pixval: blends of one value commute with themselves — a count, exact fixed-point early-out
         CsBlendState st;
         st.val = v; st.last_pv = -1; st.fixed = false;
         st.apply_n(pv, __popc(grp), alpha);
@@ -279,12 +337,10 @@ __device__ __forceinline__ void cs_w_fold(bool inw, int posn, int pv, int slot, 
       }
     }
   }
-  unsigned any_rest = __ballot_sync(full, rest != 0u);
-  while (any_rest) {  // warp-uniform: every leader with members left fetches its next one
+  while (__any_sync(full, rest != 0u)) {  // warp-uniform: every leader with members left fetches its next one
     const int src = rest ? __ffs(rest) - 1 : lane;
     const int pvj = __shfl_sync(full, pv, src);
     if (rest) { v = cs_blend(v, pvj, alpha); rest &= rest - 1; }
-    any_rest = __ballot_sync(full, rest != 0u);
   }
   if (lead) s_val[slot] = (unsigned)v | 0x10000u;  // touched
 }
@@ -386,53 +442,64 @@ __device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const 
                           int size, int pitch_tiles, int alpha) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
   CsRay r;
   r.dxc = -1; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
   if (lane < ncand) r = cs_unpack_ray(S.rays[s_list[lane]]);
   CsWWalk w;
   w.init(r, lane < ncand, t.k0 - 1, x1, y1);
+  const int last = min(w.dxc, t.k1);  // this lane's last ring in the task (-1: none)
   unsigned accl = (unsigned)(t.k0 - 1) * t.blo, acch = (unsigned)(t.k0 - 1) * t.bhi;
 
   for (int kb = t.k0; kb <= t.k1; kb += CS_W_G) {
     uint32_t cell[CS_W_G];
     int pv[CS_W_G], val[CS_W_G];
     unsigned grp[CS_W_G];
-    unsigned leadbits = 0u, cfbits = 0u;
+    unsigned leadbits = 0u, cfbits = 0u, freebits = 0u;
 #pragma unroll
     for (int j = 0; j < CS_W_G; j++) {
+      const int k = kb + j;  // (warp-uniform)
       w.step();
       accl += t.blo; acch += t.bhi;
       const int lo = (int)((accl + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX), hi = (int)((acch + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX);
-      const int posn = w.posn();
-      const bool inw = w.k <= t.k1 && w.k <= w.dxc && posn >= lo && posn < hi && (unsigned)w.x < (unsigned)size && (unsigned)w.y < (unsigned)size;
+      const int posn = (w.pos == 8 * k) ? 0 : w.pos;
+      const bool inw = k <= last && posn >= lo && posn < hi && (unsigned)w.x < (unsigned)size && (unsigned)w.y < (unsigned)size;
       pv[j] = w.pixval();
       cell[j] = cs_cell_offset<TILED>(w.x, w.y, size, pitch_tiles);
       grp[j] = 0u;
       val[j] = 0;
       const unsigned act = __ballot_sync(full, inw);
-      if (act) {
+      if (act) {  // (match.any among the visiting lanes only: its cost grows with the number of distinct keys)
         bool lead = false;
         if (inw) {
           grp[j] = __match_any_sync(act, posn);
-          lead = lane == __ffs(grp[j]) - 1;
+          lead = (grp[j] & lt_mask) == 0u;
           if (lead) val[j] = (int)__ldcg(map + cell[j]);
         }
         if (lead) leadbits |= 1u << j;
-        if (__ballot_sync(full, inw && !lead)) cfbits |= 1u << j;  // some cell of this ring has several visitors in this warp
+        if (__any_sync(full, inw && !lead)) {  // some cell of this ring has several visitors in this warp
+          cfbits |= 1u << j;
+          if (!__any_sync(full, inw && pv[j] != CS_TS_NO_OBSTACLE)) freebits |= 1u << j;  // ... all in free space
+        }
       }
     }
 #pragma unroll
     for (int j = 0; j < CS_W_G; j++) {
       const bool lead = (leadbits >> j) & 1u;
       int v = cs_blend(val[j], pv[j], alpha);
-      if ((cfbits >> j) & 1u) {  // warp-uniform
+      if ((freebits >> j) & 1u) {  // warp-uniform: one pixval everywhere — blends of one value commute: a count per cell
+        int more = lead ? __popc(grp[j]) - 1 : 0;
+        while (more-- > 0) {
+          const int nv = cs_blend(v, CS_TS_NO_OBSTACLE, alpha);
+          if (nv == v) break;  // fixed point of this pixval (exact)
+          v = nv;
+        }
+      } else if ((cfbits >> j) & 1u) {  // warp-uniform
         unsigned rest = lead ? (grp[j] & ~(1u << lane)) : 0u;
-        unsigned any_rest = __ballot_sync(full, rest != 0u);
-        while (any_rest) {
+        while (__any_sync(full, rest != 0u)) {
           const int src = rest ? __ffs(rest) - 1 : lane;
           const int pvj = __shfl_sync(full, pv[j], src);
           if (rest) { v = cs_blend(v, pvj, alpha); rest &= rest - 1; }
-          any_rest = __ballot_sync(full, rest != 0u);
         }
       }
       if (lead) __stcg(map + cell[j], (uint16_t)v);
@@ -510,7 +577,7 @@ __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka,
 template <bool TILED>
 __global__ void __launch_bounds__(CS_W_THREADS, 4)
 cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  __shared__ int s_first[CS_W_LEVELS + 2];   // first task of each level (task 0 is ring 0); s_first[nlev] = number of tasks
+  __shared__ int s_first[CS_W_LEVELS + 2];   // first task of each level; s_first[nlev] = number of tasks
   __shared__ int s_uniform[CS_W_LEVELS];     // > 0: the level is cut into this many equal wedges (the dense centre)
   __shared__ int s_tot[CS_W_LEVELS];         // tasks of each level
   __shared__ int s_T[CS_W_LEVELS];           // rays per wedge of a level cut by its sector counts
@@ -521,6 +588,8 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ uint32_t s_cell[CS_W_WARPS][CS_W_CAP];
   __shared__ int s_list[CS_W_WARPS][32];
   __shared__ unsigned s_bmap[CS_W_WARPS][CS_W_BMAP_WORDS];
+  __shared__ unsigned s_center[CS_W_CENTER_CELLS];
+  __shared__ int s_flagged[1 + CS_W_CENTER_CELLS];
 
   const unsigned full = 0xffffffffu;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -626,8 +695,8 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // wedges would leave some with several times the candidates a warp holds).
   const int* tot_tab = top + (size_t)NL * CS_W_SECTORS;
   for (int L = tid; L < NL; L += CS_W_THREADS) {
-    const int alive = __ldcg(tot_tab + L);
     const int k0 = cs_w_level_first(L);
+    const int alive = k0 >= CS_W_CENTER ? tot_tab[L] : 0;  // (the rings of the centre are drawn by cs_w_center)
     int tot = 0, uni = 0, T = 0;
     if (alive > 0 && alive / (8 * k0) > CS_W_OWN / 2) {
       uni = cs_w_wedges(alive, k0);
@@ -640,7 +709,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   }
   __syncthreads();
   if (warp == 0) {
-    int total = 1, nlev = 0;  // task 0: ring 0
+    int total = 0, nlev = 0;
     for (int L0 = 0; L0 < NL; L0 += 32) {
       const int L = L0 + lane;
       const int W = L < NL ? s_tot[L] : 0;
@@ -661,7 +730,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const long long t_sched = a.diag ? cs_globaltimer() : 0;
   const int nlev = s_nlev;
   const int n_tasks = s_first[nlev];
-  const int n_valid = __ldcg(tot_tab + NL);
+  const int n_valid = tot_tab[NL];
   const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
@@ -676,19 +745,15 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const int nblocks = (int)gridDim.x;
     int sub = 1;
     const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 8;
-    while (sub < sub_max && 1 + (n_tasks - 1) * (sub * 2) <= nblocks * CS_W_WARPS) sub *= 2;
-    const int n_sub_tasks = 1 + (n_tasks - 1) * sub;
+    while (sub < sub_max && n_tasks * (sub * 2) <= nblocks * CS_W_WARPS) sub *= 2;
+    const int n_sub_tasks = n_tasks * sub;
     int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
     if (rb < 0) rb += nblocks;
+    // the centre goes to the block whose tasks come last in the table (block-uniform branch: cs_w_center has barriers)
+    if (rb == nblocks - 1) cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
     for (int stask = rb + nblocks * warp; stask < n_sub_tasks; stask += nblocks * CS_W_WARPS) {
-      const int task = stask == 0 ? 0 : 1 + (stask - 1) / sub;
-      const int sub_j = stask == 0 ? 0 : (stask - 1) % sub;
-      if (task == 0) {
-        if (a.diag && sj == 0 && lane == 0) { a.diag[0] = cs_globaltimer(); a.diag[4] = t_start; a.diag[5] = t_prep; a.diag[6] = t_sched; }
-        cs_w_ring0<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha);
-        if (a.diag && sj == 0 && lane == 0) { a.diag[2] = cs_globaltimer(); a.diag[1] = a.diag[0]; a.diag[3] = 0; a.diag[7] = cs_smid(); }
-        continue;
-      }
+      const int task = stask / sub;
+      const int sub_j = stask % sub;
       int L = 0;  // level of the task: last L with s_first[L] <= task
       {
         int lo = 0, hi = nlev - 1;
@@ -707,7 +772,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         bhi = cs_w_beta(r + 1, W);
       } else {
         // wedge r of the level holds the rays number r T .. (r + 1) T - 1 in key order (by the sector counts)
-        const int c0 = __ldcg(top + L * CS_W_SECTORS + lane), c1 = __ldcg(top + L * CS_W_SECTORS + 32 + lane);
+        const int c0 = top[L * CS_W_SECTORS + lane], c1 = top[L * CS_W_SECTORS + 32 + lane];
         int p0 = c0, p1 = c1;  // inclusive prefix sums over the 64 sectors
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

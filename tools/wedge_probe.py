@@ -24,9 +24,13 @@ for rep in range(2):
     p.ring_cycles()  # (clears nothing; records are overwritten by the next step)
     p.replay(log, n_scans - 2 + rep, 1, want_results=False)
     p.sync()
-    rc = p.ring_cycles(size)
+    full = p.ring_cycles(size + 8192)
+    pub = full[size + 8191]
+    rc = full[:size]
     rc = rc[rc[:, 0] > 0]
     t0 = rc[:, 4].min()
+    if pub[2] > 0:
+        print("pose published at %.2f us (publisher entry %.2f)" % ((pub[2] - t0) / 1e3, (pub[0] - t0) / 1e3))
     us = lambda a: (a - t0) / 1e3
     print("---- step %d: %d tasks recorded on %d SMs" % (rep, len(rc), len(np.unique(rc[:, 7]))))
     q = lambda a: "min %6.2f p50 %6.2f p90 %6.2f max %6.2f" % (a.min(), np.percentile(a, 50), np.percentile(a, 90), a.max())
