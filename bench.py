@@ -397,7 +397,11 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
     with torch.cuda.stream(stream):
         proc = sn.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, wl["iters"], wl["threads"],
                             device=local, max_points=P, seed=args.seed, stream=stream.cuda_stream)
-        ss = par.SplitSearch(proc, rank, world, local, torch_stream=stream)
+        if args.split == "nccl":  # search kernel -> torch.distributed all_reduce(MIN) -> set-up kernel (round 1's exchange)
+            ss = par.SplitSearch(proc, rank, world, local, torch_stream=stream)
+        else:                     # the exchange inside the search kernel over peer-mapped memory (cs_group_attach)
+            par.attach_group(proc, rank, world)
+            ss = proc
         for k in range(PRIME_SCANS + W):
             ss.update(rp.points[k], rp.odometry[k], None)
         proc.sync()
@@ -462,8 +466,11 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
                     "h2d_bytes_per_step": 64 + 8 * P, "d2h_bytes_per_step": 32,
                     "api": "cs_update_begin -> exchange -> cs_update_finish with host points (the timed loop itself)"},
             "scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3)},
-            "exchange": "torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world,
-            "nvlink_bytes_per_step": 8 * max(world - 1, 0) * 2,
+            "exchange": ("torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world) if args.split == "nccl" else
+                        ("inside the search kernel: every rank's publishing thread stores {key, tag} (16 B) into every rank's table "
+                         "over peer-mapped memory (CUDA IPC, NVLink) and waits for the world's keys in its own; %d ranks, no "
+                         "collective launch, no host step" % world),
+            "nvlink_bytes_per_step": 16 * max(world - 1, 0) * world,
             "parity": {"pose_and_map_checksum_equal_on_all_ranks": ranks_equal, "equal_to_unsplit_handle_rank0": ref_ok,
                        "equal_to_cpu_oracle": oracle_ok},
             "final_pose": [float(x) for x in pose], "map_checksum": checksum, "gpu_launches": int(launches), "clocks": clocks,
@@ -700,6 +707,9 @@ def main():
     ap.add_argument("--sessions", type=int, default=0, help="cfg5: number of sessions in the job (default: the config's 1024)")
     ap.add_argument("--sub-batches", type=int, default=0,
                     help="cfg5: independent batches (streams) a rank's sessions are run as (default 1)")
+    ap.add_argument("--split", default="group", choices=["group", "nccl"],
+                    help="cfg4: how the 8-byte arg-min is exchanged: inside the search kernel over peer-mapped memory (group), or by "
+                         "a torch.distributed all_reduce between two kernels (nccl)")
     ap.add_argument("--no-sharded", action="store_true",
                     help="default (cfg2) line: skip the `sharded` block (cfg5 session batches and the cfg4 candidate split over the ranks)")
     args = ap.parse_args()

@@ -137,6 +137,10 @@ SIGNATURES = {
     "cs_update": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.POINTER(Result)]),
     "cs_update_segments": (C.c_int, [_vp, _fp, _ip, _fp, C.c_int32, C.c_int32, _fp, C.POINTER(Result)]),
     "cs_segments_to_cloud": (C.c_int, [_vp, _fp, _ip, _fp, C.c_int32, C.c_int32, _fp, _fp]),
+    "cs_group_export": (C.c_int, [_vp, C.c_void_p]),
+    "cs_group_attach": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_void_p]),
+    "cs_group_attach_local": (C.c_int, [_vp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "cs_group_detach": (C.c_int, [_vp]),
     "cs_update_begin": (C.c_int, [_vp, _fp, C.c_int32, _fp, _fp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "cs_update_finish": (C.c_int, [_vp, C.POINTER(Result)]),
     "cs_sync": (C.c_int, [_vp]),

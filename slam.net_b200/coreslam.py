@@ -307,6 +307,29 @@ class Processor:
         self._ck(N.lib().cs_update_finish(self._h, C.byref(r)))
         return _result(r)
 
+    # -- candidate-split group with the exchange inside the search kernel (cs_group_*) ---------------
+    def group_export(self) -> bytes:
+        """64-byte handle of this rank's exchange table (cs_group_export), to be passed to every other rank."""
+        buf = (C.c_ubyte * 64)()
+        self._ck(N.lib().cs_group_export(self._h, C.addressof(buf)))
+        return bytes(buf)
+
+    def group_attach(self, rank: int, world: int, handles: Sequence[bytes]):
+        """One process per GPU: `handles[p]` = rank p's group_export() (entry `rank` is ignored)."""
+        blob = (C.c_ubyte * (64 * world))()
+        for p_, hd in enumerate(handles):
+            for i, b in enumerate(bytes(hd)[:64]):
+                blob[64 * p_ + i] = b
+        self._ck(N.lib().cs_group_attach(self._h, int(rank), int(world), C.addressof(blob)))
+
+    def group_attach_local(self, rank: int, world: int, peers: Sequence["Processor"]):
+        """One process, several handles (one per device, or several on one device)."""
+        arr = (C.c_void_p * world)(*[p_._h for p_ in peers])
+        self._ck(N.lib().cs_group_attach_local(self._h, int(rank), int(world), arr))
+
+    def group_detach(self):
+        self._ck(N.lib().cs_group_detach(self._h))
+
     def replay(self, log: ScanLog, first: int = 0, count: Optional[int] = None, want_results=True):
         count = log.n_scans - first if count is None else count
         res = (N.Result * count)() if want_results else None

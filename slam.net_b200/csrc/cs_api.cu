@@ -241,7 +241,7 @@ int wedge_levels(int size) {
   if (k < 64) { while ((2 << L) <= k) L++; } else L = 5 + (k >> 6);
   return L + 1;
 }
-size_t wedge_top_words(int size) { return (size_t)wedge_levels(size) * (CS_W_SECTORS + 1) + 1; }
+size_t wedge_top_words(int size) { return (size_t)wedge_levels(size) * (CS_W_SECTORS + 1); }
 size_t wedge_smem(int) { return 0; }
 cudaError_t wedge_allow_shared_memory() {
   const int most = (int)(CS_W_LEVELS * CS_W_SECTORS * sizeof(unsigned short));
@@ -292,7 +292,7 @@ double max_range_of(const float* points, int n) {
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
-  int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0;
+  int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -306,6 +306,7 @@ struct Tune {
     w_general = geti("CS_TUNE_W_GENERAL");      // 1: every task of the wedge kernel takes its general path (tests)
     w_blocks = geti("CS_TUNE_W_BLOCKS");        // blocks of the wedge kernel per session
     w_prefetch = geti("CS_TUNE_W_PREFETCH");    // -1: no L2 prefetch of the map around the pose
+    w_prev = geti("CS_TUNE_W_PREV");            // -1: every scan builds its task table from its own counts
     w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
@@ -557,12 +558,25 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     // tasks), a session of a batch a few blocks.
     int group = (((n_points + 63) / 64) + 31) / 32 * 32;
     if (group < 128) group = 128;
+    if (group > CS_W_THREADS) group = CS_W_THREADS;  // one ray per thread of a preparing block
     a.prep_group = group;
     const int nprep = (n_points + group - 1) / group;
     int blocks = c.n_sessions == 1 ? 4 * c.num_sms : 4;
     if (tune().w_blocks > 0) blocks = tune().w_blocks;
     if (blocks < nprep) blocks = nprep;
-    a.w_slot = (*c.w_slot ^= 1);
+    // A rank of a candidate-split group must not keep a grid of polling blocks resident while its search kernel waits for
+    // the other ranks' keys (ranks that share a device would starve each other): its draw kernel starts after the search.
+    if (a.xchg_world > 1) g_next_launch_plain = true;
+    {  // the counters rotate through three thirds: counted into now / counted into by the previous drawn step / zeroed now
+      const int d = (*c.w_slot)++;
+      a.w_slot = d % 3;
+      // The previous scan's counts size this scan's wedges (the table is then ready before the pose) where a scan is a latency
+      // chain; a big scan is throughput, its wedges are narrow (a few degrees of heading change between scans would
+      // overfill some) and it builds the table from its own counts.
+      a.w_prev = (d > 0 && tune().w_prev >= 0 && n_points <= 2048) ? (d + 2) % 3 : -1;
+      a.w_zero = (d + 1) % 3;
+      if (*c.w_slot >= 3000) *c.w_slot -= 2997;  // (keeps d > 0 and d mod 3)
+    }
     a.w_general = tune().w_general > 0 ? 1 : 0;
     a.w_sub_max = tune().w_sub;
     a.w_prefetch = (c.n_sessions == 1 && tune().w_prefetch >= 0) ? 1 : 0;  // batches hide the latency with their sessions
@@ -821,8 +835,8 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(rings_allow_shared_memory());
   CS_CREATE_CUDA(cudaMalloc(&h->d_w_rk, (size_t)h->ray_stride * sizeof(int2)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_w_bkey, (size_t)(h->ray_stride / 32 + 1) * sizeof(float2)));
-  CS_CREATE_CUDA(cudaMalloc(&h->d_w_top, (size_t)2 * wedge_top_words(h->size) * sizeof(int)));
-  CS_CREATE_CUDA(cudaMemset(h->d_w_top, 0, (size_t)2 * wedge_top_words(h->size) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMalloc(&h->d_w_top, (size_t)3 * wedge_top_words(h->size) * sizeof(int)));
+  CS_CREATE_CUDA(cudaMemset(h->d_w_top, 0, (size_t)3 * wedge_top_words(h->size) * sizeof(int)));
   CS_CREATE_CUDA(wedge_allow_shared_memory());
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
@@ -2261,8 +2275,8 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_checksum, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_w_rk, (size_t)b->max_points * sizeof(int2) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_w_bkey, ((size_t)b->max_points / 32 + 1) * sizeof(float2) * (size_t)n_sessions) == cudaSuccess;
-  ok = ok && cudaMalloc(&b->d_w_top, (size_t)n_sessions * 2 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
-  ok = ok && cudaMemset(b->d_w_top, 0, (size_t)n_sessions * 2 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMalloc(&b->d_w_top, (size_t)n_sessions * 3 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
+  ok = ok && cudaMemset(b->d_w_top, 0, (size_t)n_sessions * 3 * wedge_top_words(b->size) * sizeof(int)) == cudaSuccess;
   ok = ok && wedge_allow_shared_memory() == cudaSuccess;
   b->flags = c0.flags;
   {
@@ -2310,7 +2324,7 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
     s.prep_words = b->d_prep_words + (size_t)j * 2 * 16;
     s.w_rk = b->d_w_rk + (size_t)j * b->max_points;
     s.w_bkey = b->d_w_bkey + (size_t)j * ((size_t)b->max_points / 32 + 1);
-    s.w_top = b->d_w_top + (size_t)j * 2 * wedge_top_words(b->size);
+    s.w_top = b->d_w_top + (size_t)j * 3 * wedge_top_words(b->size);
     s.w_levels = wedge_levels(b->size);
     if (b->s2_cap > 0) {
       const size_t cap = (size_t)b->s2_cap;

@@ -125,9 +125,8 @@ struct CsSession {  // one CoreSLAMProcessor, device resident
   // ---- scratch of the wedge integration (cs_wedge.cuh)
   int2* w_rk;                   // per ray: (angular key as float bits, dxc or -1 for a ray that draws nothing)
   float2* w_bkey;               // per 32 consecutive rays: (smallest, largest) key of a valid ray
-  int* w_top;                   // [2][w_levels * (CS_W_SECTORS + 1) + 1]: valid rays that reach (level, key sector), that reach each
-                                // level, and all valid rays; slot = CsStepArgs::w_slot, the other slot is zeroed by the step that
-                                // uses this one
+  int* w_top;                   // [3][w_levels * (CS_W_SECTORS + 1)]: valid rays that reach (level, key sector) and that reach each
+                                // level; the thirds rotate: CsStepArgs::w_slot / w_prev / w_zero
   int w_levels, pad4;           // levels a ray of this map can reach (cs_w_level_of(size - 1) + 1)
 };
 
@@ -183,7 +182,9 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   unsigned xchg_seq;             // exchange number, the same on every rank
   unsigned xchg_pad;
   unsigned long long* xchg_peer[CS_GROUP_MAX];
-  int w_slot;                    // which half of CsSession::w_top this step counts into (alternates per drawn step)
+  int w_slot;                    // which third of CsSession::w_top this step counts into (rotates per drawn step)
+  int w_prev;                    // the third the previous drawn step counted into (its counts size this step's wedges); -1: none
+  int w_zero;                    // the third the next drawn step will count into (zeroed by this step)
   int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
   int w_sub_max;                 // most warps the rings of one task are split over (0: 8)
   int w_prefetch;                // 1: the wedge kernel prefetches the map around the pose into L2 while it waits for the pose

@@ -71,9 +71,14 @@ struct CsWTask {
 };
 
 // ---- ray preparation by the first blocks (UpdateHoleMap :517-530, ClipRay, the prologue of DrawLaserRayOnHoleMap), one ray
-// per lane: packed ray, (key, dxc), the warp's key range and largest dxc, and the per (level, sector) counts.
-__device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, const float2 p, int i, bool in_range, int* top,
-                                             long long& visits) {
+// per lane: packed ray, (key, dxc), the warp's key range and largest dxc.  Returns what cs_w_count needs.
+struct CsWPrepared {
+  float key;
+  int dxc;     // -1: the ray draws nothing
+  int bm;      // largest dxc of the warp's rays
+};
+__device__ __forceinline__ CsWPrepared cs_w_prepare(CsSession& S, const CsRayFrame& f, const float2 p, int i, bool in_range,
+                                                    long long& visits) {
   const unsigned full = 0xffffffffu;
   CsRay r;
   r.dxc = 0; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
@@ -100,22 +105,29 @@ __device__ __forceinline__ void cs_w_prepare(CsSession& S, const CsRayFrame& f, 
     S.batch_max[i >> 5] = bm;
     S.w_bkey[i >> 5] = make_float2(__uint_as_float(kmin), __uint_as_float(kmax));
   }
-  // counts: every valid ray; per level the rays that reach it, in all and per key sector.  The lanes of a sector add as one
-  // (the 32 consecutive rays of a warp span a sector or two of a lidar scan).
-  const unsigned nvalid = __popc(__ballot_sync(full, valid));
+  CsWPrepared out;
+  out.key = key; out.dxc = valid ? r.dxc : -1; out.bm = bm;
+  return out;
+}
+
+// Counts for sizing the wedges: per level the rays that reach it, in all and per key sector.  The lanes of a sector add as
+// one (the 32 consecutive rays of a warp span a sector or two of a lidar scan).  Only the balance of the task table depends
+// on these numbers, never a result.
+__device__ __forceinline__ void cs_w_count(const CsSession& S, const CsWPrepared& q, int* top) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   int* tot = top + (size_t)S.w_levels * CS_W_SECTORS;
-  if (lane == 0 && nvalid) atomicAdd(&tot[S.w_levels], (int)nvalid);
-  const bool counted = valid && r.dxc >= 1;
+  const bool counted = q.dxc >= 1;
   const unsigned cm = __ballot_sync(full, counted);
   if (cm) {
-    const int sector = min(CS_W_SECTORS - 1, (int)(key * (CS_W_SECTORS / 8.0f)));
+    const int sector = min(CS_W_SECTORS - 1, (int)(q.key * (CS_W_SECTORS / 8.0f)));
     unsigned same = 0u;
     if (counted) same = __match_any_sync(cm, sector);
     const bool leader = counted && lane == __ffs(same) - 1;
-    const int top_level = cs_w_level_of(max(bm, 1));
+    const int top_level = cs_w_level_of(max(q.bm, 1));
 #pragma unroll 4
     for (int L = 0; L <= top_level; L++) {
-      const unsigned here = __ballot_sync(full, counted && r.dxc >= cs_w_level_first(L));
+      const unsigned here = __ballot_sync(full, counted && q.dxc >= cs_w_level_first(L));
       if (leader && (here & same)) atomicAdd(&top[L * CS_W_SECTORS + sector], (int)__popc(here & same));
       if (lane == 0 && here) atomicAdd(&tot[L], (int)__popc(here));
     }
@@ -610,8 +622,55 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const int NL = S.w_levels;
   const unsigned slot = a.step_id & 1u;
   const unsigned long long ll_tag = (unsigned long long)a.step_id << 32;
-  const size_t top_words = (size_t)NL * (CS_W_SECTORS + 1) + 1;  // per (level, sector), per level, all valid rays
-  int* top = S.w_top + (size_t)a.w_slot * top_words;
+  const size_t top_words = (size_t)NL * (CS_W_SECTORS + 1);  // per (level, sector), then per level
+  int* top = S.w_top + (size_t)a.w_slot * top_words;           // this scan's counts (sizes the NEXT scan's wedges)
+  // The task table is built from the counts of the scan BEFORE this one when there is one (a.w_prev >= 0): scans follow each
+  // other closely, any cut of the circle into wedges is correct (only the balance depends on it), and the table is then
+  // ready before the pose is out.  The first scan of a handle builds it from its own counts, after its rays are ready.
+  const int* tab = S.w_top + (size_t)(a.w_prev >= 0 ? a.w_prev : a.w_slot) * top_words;
+
+  auto build_table = [&]() {
+    const int* tot_tab = tab + (size_t)NL * CS_W_SECTORS;
+    // wedges per level.  Where the margins of ring k0 alone hold more rays than a wedge is sized for (the centre) the level is
+    // cut into equal wedges as wide as the margins; elsewhere into wedges of T rays each by the sector counts (boundaries at
+    // the T-quantiles of the level's rays, interpolated inside a sector: long rays cluster in a few directions, and equal
+    // wedges would leave some with several times the candidates a warp holds).
+    for (int L = tid; L < NL; L += CS_W_THREADS) {
+      const int k0 = cs_w_level_first(L);
+      const int alive = k0 >= CS_W_CENTER ? tot_tab[L] : 0;  // (the rings of the centre are drawn by cs_w_center)
+      int tot = 0, uni = 0, T = 0;
+      // a level the previous scan did not reach still gets a task (one wedge, the whole circle): this scan may reach it
+      if (alive <= 0 && k0 >= CS_W_CENTER && a.w_prev >= 0) { uni = 1; tot = 1; }
+      if (alive > 0 && alive / (8 * k0) > CS_W_OWN / 2) {
+        uni = cs_w_wedges(alive, k0);
+        tot = uni;
+      } else if (alive > 0) {
+        T = CS_W_OWN - alive / (8 * k0);  // the margins of a wedge, 1 / k0 wide in all, hold alive / (8 k0) rays on average
+        tot = (alive + T - 1) / T;
+      }
+      s_tot[L] = tot; s_uniform[L] = uni; s_T[L] = T;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int total = 0, nlev = 0;
+      for (int L0 = 0; L0 < NL; L0 += 32) {
+        const int L = L0 + lane;
+        const int W = L < NL ? s_tot[L] : 0;
+        int incl = W;
+  #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int u = __shfl_up_sync(full, incl, o);
+          if (lane >= o) incl += u;
+        }
+        if (L < NL) s_first[L] = total + incl - W;
+        const unsigned has = __ballot_sync(full, W > 0);
+        if (has) nlev = L0 + 32 - __clz(has);
+        total += __shfl_sync(full, incl, 31);
+      }
+      if (lane == 0) { s_first[nlev] = total; s_nlev = nlev; }
+    }
+    __syncthreads();
+  };
 
   // ---- while the pose is not out yet: pull the part of the map the scan can reach into L2.  The centre is the pose the
   // step starts from (searchPose :728, or the given pose), the radius the ring count the host launched for plus the reach
@@ -641,11 +700,13 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // ---- ray preparation: the first nprep blocks take a.prep_group rays each, one ray per thread
   const int group = a.prep_group;
   const int nprep = (n + group - 1) / group;
-  if ((int)blockIdx.x < nprep) {
+  const bool preparing = (int)blockIdx.x < nprep;
+  if (!preparing && a.w_prev >= 0) build_table();  // (the preparing blocks build theirs after the rays: the pose comes first)
+  if (preparing) {
     const float2* __restrict__ points = a.points + (size_t)sj * a.points_stride;
     const int g_begin = blockIdx.x * group, g_end = min(n, g_begin + group);
-    if (blockIdx.x == 0) {  // the other half of the counters is this step's to re-arm (nobody reads or counts into it now)
-      int* other = S.w_top + (size_t)(a.w_slot ^ 1) * top_words;
+    if (blockIdx.x == 0) {  // the third of the counters that the NEXT scan will count into is this step's to re-arm
+      int* other = S.w_top + (size_t)a.w_zero * top_words;
       for (int i = tid; i < (int)top_words; i += CS_W_THREADS) other[i] = 0;
     }
     if (tid < 5) {
@@ -659,20 +720,24 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const float cs[2] = {sh_pose[3], sh_pose[4]};
     const CsRayFrame f = cs_ray_frame(S, pose, cs);
     long long vis = 0;
-    for (int base = g_begin; base < g_end; base += CS_W_THREADS) {  // whole warps: the warp reductions need every lane
-      const int i = base + tid;
-      if (base + warp * 32 < g_end) {
-        const bool in_range = i < g_end;
-        const float2 p = in_range ? __ldg(points + i) : make_float2(1.f, 0.f);
-        cs_w_prepare(S, f, p, i, in_range, top, vis);
-      }
+    // (at most CS_W_THREADS rays per block and pass; a.prep_group <= CS_W_THREADS is what the host launches)
+    CsWPrepared q;
+    q.key = 0.f; q.dxc = -1; q.bm = -1;
+    const bool my_warp = g_begin + warp * 32 < g_end;  // whole warps: the warp reductions need every lane
+    if (my_warp) {
+      const int i = g_begin + tid;
+      const bool in_range = i < g_end;
+      const float2 p = in_range ? __ldg(points + i) : make_float2(1.f, 0.f);
+      q = cs_w_prepare(S, f, p, i, in_range, vis);
+      if (a.w_prev < 0) cs_w_count(S, q, top);  // this scan's own table needs the counts before the rays are announced
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(full, vis, o);
     if (lane == 0) sh_vis[warp] = vis;
-    __threadfence();  // this thread's stores and counts are visible device-wide before the block's arrival is counted
+    __threadfence();  // this thread's stores (and counts) are visible device-wide before the block's arrival is counted
     __syncthreads();
     if (tid < copies) atomicAdd(S.prep_words + ((size_t)slot * copies + tid) * 16, 1ull);
+    if (my_warp && a.w_prev >= 0) cs_w_count(S, q, top);  // off the critical path: these size the next scan's wedges
     if (tid == 0) {
       for (int w = 1; w < CS_W_WARPS; w++) vis += sh_vis[w];
       if (vis) {
@@ -680,8 +745,9 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         if (a.visits_out) atomicAdd((unsigned long long*)a.visits_out, (unsigned long long)vis);
       }
     }
+    if (a.w_prev >= 0) build_table();
   }
-  // ---- everybody: wait for the preparing blocks, then build the task table of this scan
+  // ---- everybody: wait for the preparing blocks
   if (tid == 0) {
     volatile unsigned long long* pw = S.prep_words + ((size_t)slot * copies + (cs_smid() % copies)) * 16;
     while (*pw != (unsigned long long)nprep) {}
@@ -689,48 +755,11 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   }
   __syncthreads();
   const long long t_prep = a.diag ? cs_globaltimer() : 0;
-  // wedges per level.  Where the margins of ring k0 alone hold more rays than a wedge is sized for (the centre) the level is
-  // cut into equal wedges as wide as the margins; elsewhere into wedges of T rays each by the sector counts (boundaries at
-  // the T-quantiles of the level's rays, interpolated inside a sector: long rays cluster in a few directions, and equal
-  // wedges would leave some with several times the candidates a warp holds).
-  const int* tot_tab = top + (size_t)NL * CS_W_SECTORS;
-  for (int L = tid; L < NL; L += CS_W_THREADS) {
-    const int k0 = cs_w_level_first(L);
-    const int alive = k0 >= CS_W_CENTER ? tot_tab[L] : 0;  // (the rings of the centre are drawn by cs_w_center)
-    int tot = 0, uni = 0, T = 0;
-    if (alive > 0 && alive / (8 * k0) > CS_W_OWN / 2) {
-      uni = cs_w_wedges(alive, k0);
-      tot = uni;
-    } else if (alive > 0) {
-      T = CS_W_OWN - alive / (8 * k0);  // the margins of a wedge, 1 / k0 wide in all, hold alive / (8 k0) rays on average
-      tot = (alive + T - 1) / T;
-    }
-    s_tot[L] = tot; s_uniform[L] = uni; s_T[L] = T;
-  }
-  __syncthreads();
-  if (warp == 0) {
-    int total = 0, nlev = 0;
-    for (int L0 = 0; L0 < NL; L0 += 32) {
-      const int L = L0 + lane;
-      const int W = L < NL ? s_tot[L] : 0;
-      int incl = W;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(full, incl, o);
-        if (lane >= o) incl += u;
-      }
-      if (L < NL) s_first[L] = total + incl - W;
-      const unsigned has = __ballot_sync(full, W > 0);
-      if (has) nlev = L0 + 32 - __clz(has);
-      total += __shfl_sync(full, incl, 31);
-    }
-    if (lane == 0) { s_first[nlev] = total; s_nlev = nlev; }
-  }
+  if (a.w_prev < 0) build_table();
   __syncthreads();
   const long long t_sched = a.diag ? cs_globaltimer() : 0;
   const int nlev = s_nlev;
   const int n_tasks = s_first[nlev];
-  const int n_valid = tot_tab[NL];
   const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
   const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
@@ -738,7 +767,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
 
   // ---- tasks: static round-robin over the warps of the session's blocks, the (long) centre tasks first, starting with
   // the warps of the blocks that did not prepare rays
-  if (n_valid > 0) {
+  {
     // consecutive tasks go to different blocks (different SMs); the blocks that prepared rays come last.  When the table
     // holds fewer tasks than the grid has warps, the rings of every task are split over 2, 4 or 8 warps (the kernel is a
     // latency chain: shorter tasks, not fewer, end it sooner).
@@ -772,7 +801,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         bhi = cs_w_beta(r + 1, W);
       } else {
         // wedge r of the level holds the rays number r T .. (r + 1) T - 1 in key order (by the sector counts)
-        const int c0 = top[L * CS_W_SECTORS + lane], c1 = top[L * CS_W_SECTORS + 32 + lane];
+        const int c0 = tab[L * CS_W_SECTORS + lane], c1 = tab[L * CS_W_SECTORS + 32 + lane];
         int p0 = c0, p1 = c1;  // inclusive prefix sums over the 64 sectors
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {

@@ -86,6 +86,25 @@ def allreduce_min_key(t, group=None):
     return t
 
 
+def attach_group(proc, rank: int, world: int, group=None):
+    """Candidate-split group over the ranks of a torch.distributed job (one process per GPU): every rank exports the handle
+    of its exchange table, the 64-byte handles are all-gathered (this is the only use of the process group: the exchange
+    itself runs inside the search kernel over peer-mapped memory, see include/coreslam_b200.h), every rank attaches.  After
+    this, `proc.update(...)` / `proc.replay(...)` evaluate this rank's candidate slice and end on the group's winner."""
+    import torch
+    import torch.distributed as dist
+    mine = proc.group_export()
+    if world <= 1 or not (dist.is_available() and dist.is_initialized()):
+        proc.group_attach(0, 1, [mine])
+        return
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    proc.group_attach(rank, world, [bytes(x.cpu().tolist()) for x in out])
+    dist.barrier(group=group)  # nobody starts exchanging before every rank has mapped every table
+
+
 class SplitSearch:
     """Candidate-split Update over the ranks of a torch.distributed group: every rank holds a replica of
     the map (a `Processor` on its GPU, created on `torch_stream`), evaluates its slice of the candidates

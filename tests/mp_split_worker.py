@@ -24,7 +24,10 @@ def main():
     with torch.cuda.stream(stream):
         p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, device=local, max_points=P, seed=99,
                          stream=stream.cuda_stream)
-        ss = par.SplitSearch(p, rank, world, local, torch_stream=stream)
+        use_group = len(sys.argv) > 1 and sys.argv[1] == "group"  # exchange inside the search kernel (cs_group_*) instead of NCCL
+        if use_group:
+            par.attach_group(p, rank, world)
+        ss = p if use_group else par.SplitSearch(p, rank, world, local, torch_stream=stream)
         o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
         for k in range(n_scans):
             philox = k % 2 == 1

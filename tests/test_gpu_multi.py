@@ -258,3 +258,75 @@ def test_batch_nan_point_in_one_session_does_not_truncate_the_others():
     for j in range(n_sess):
         assert np.array_equal(b.map_download(j), np.array(os_[j].map.pixels)), j
     b.close()
+
+
+@pytest.mark.parametrize("philox", [False, True])
+def test_group_exchange_inside_the_search_kernel_two_handles_one_device(philox):
+    """cs_group_attach_local: two handles on one GPU play two ranks; each evaluates its half of the candidates and the 8-byte
+    arg-min is exchanged INSIDE the search kernels (peer-mapped tables, no host step between search and integration).  Both
+    must end every scan on the unsplit oracle's pose, winner and map.  The two ranks' kernels wait for each other on the
+    device, so the two Updates are issued from two host threads."""
+    import threading
+    n_scans, P, size, phys, iters, threads = 16, 300, 320, 40.0, 305, 4  # T*I + 1 = 1221: odd split, slab search
+    rp = synth.make_replay(n_scans, P, phys, seed=23)
+    seed = 0xBEEF
+    ranks = [sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=seed) for _ in range(2)]
+    for g, p in enumerate(ranks):
+        p.group_attach_local(g, 2, ranks)
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    for k in range(n_scans):
+        off = (sn.philox_offsets(seed, k, iters * threads, 0.1, 0.17) if philox
+               else synth.candidate_offsets(6, k, iters * threads, 0.1, 0.17))
+        res = [None, None]
+
+        def run(g):
+            res[g] = ranks[g].update(rp.points[k], rp.odometry[k], None if philox else off)
+
+        ts = [threading.Thread(target=run, args=(g,)) for g in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        o.update(rp.points[k], rp.odometry[k], off)
+        for r in res:
+            assert np.array_equal(r.pose, o.pose), k
+            if k >= 5:
+                assert (r.distance, r.index) == (o.last_distance, o.last_index), k
+    for p in ranks:
+        assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+    ranks[0].group_detach()          # a detached handle searches every candidate again
+    ranks[1].group_detach()
+    off = synth.candidate_offsets(6, 99, iters * threads, 0.1, 0.17)
+    r0 = ranks[0].update(rp.points[0], rp.odometry[-1], off)
+    o.update(rp.points[0], rp.odometry[-1], off)
+    assert np.array_equal(r0.pose, o.pose) and (r0.distance, r0.index) == (o.last_distance, o.last_index)
+    for p in ranks:
+        p.close()
+
+
+def test_group_exchange_times_out_instead_of_hanging():
+    """A rank whose partner never shows up must fail the call with CS_ERR_NCCL after the device-side timeout (2 s), not hang."""
+    P, size, phys = 100, 128, 20.0
+    rp = synth.make_replay(7, P, phys, seed=5)
+    ranks = [sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, 64, 1, max_points=P) for _ in range(2)]
+    for g, p in enumerate(ranks):
+        p.group_attach_local(g, 2, ranks)
+    for k in range(5):  # map-only scans: no search, no exchange
+        ranks[0].update(rp.points[k], rp.odometry[k], None)
+    with pytest.raises(sn.CoreSlamError) as e:
+        ranks[0].update(rp.points[5], rp.odometry[5], None)  # rank 1 never calls
+    assert "CS_ERR_NCCL" in str(e.value)
+    for p in ranks:
+        p.close()
+
+
+def test_group_two_processes_peer_memory():
+    """Real thing: 2 ranks, 2 GPUs, tables mapped with CUDA IPC, exchange over NVLink inside the search kernels."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29519", os.path.join(ROOT, "tests", "mp_split_worker.py"), "group"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "SPLIT_OK" in out.stdout
