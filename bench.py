@@ -171,17 +171,64 @@ def run_cpu(wl, rp, offs, n_cand, first, count, budget_s=25.0, min_s=10.0, threa
     return lookups / dt, done, T, dt, pose, complete
 
 
-def latest_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the newest committed ncu capture (profiles/*_traffic.json)."""
+def kernel_src_sha():
+    """Hash of the kernel sources (slam.net_b200/csrc), as tools/ncu_summary.py stamps its captures with."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "slam.net_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def latest_capture(kernel):
+    """The newest committed ncu capture of `kernel` (profiles/*_traffic.json, written by tools/ncu_summary.py) -> (entry,
+    file name, stale).  A capture taken from other kernel sources than the ones in the tree is reported as stale and its
+    numbers are NOT used (traffic = null): ncu counters describe the code they were measured on."""
     import glob
+    sha = None
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
         try:
             d = json.load(open(path))
             k = d[kernel]
-            return float(k["dram_bytes_read"] + k["dram_bytes_write"]), os.path.basename(path)
         except Exception:
             continue
-    return None, None
+        if sha is None:
+            sha = kernel_src_sha()
+        return k, os.path.basename(path), d.get("kernel_src_sha") != sha
+    return None, None, True
+
+
+def latest_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from its newest capture, or (None, why)."""
+    k, src, stale = latest_capture(kernel)
+    if k is None:
+        return None, None
+    if stale:
+        return None, "%s is stale (kernel sources changed since the capture)" % src
+    return float((k.get("dram_bytes_read") or 0.0) + (k.get("dram_bytes_write") or 0.0)), src
+
+
+def limiter_of(kernel, launch_ms, sm_count=148, clock_hz=1.965e9):
+    """What bounds `kernel` according to its newest capture: its stall mix, issue-slot use, and the fraction of the launch an
+    issue-bound kernel of the same instruction count would need (warp instructions / (SMs x 4 schedulers x clock))."""
+    k, src, stale = latest_capture(kernel)
+    if k is None:
+        return None
+    out = {"source": src, "stale": bool(stale)}
+    if stale:
+        return out
+    wi = k.get("warp_instructions")
+    out.update({"stall_mix": k.get("stall_mix"), "issue_slots_busy_pct": k.get("issue_slots_busy_pct"), "ipc_active": k.get("ipc_active"),
+                "achieved_occupancy_pct": k.get("achieved_occupancy_pct"), "warp_instructions_per_launch": wi,
+                "capture_duration_us": k.get("duration_us")})
+    if wi and launch_ms:
+        floor_ms = wi / (sm_count * 4 * clock_hz) * 1e3
+        out["issue_floor_ms"] = floor_ms
+        out["frac_of_issue_ceiling"] = floor_ms / launch_ms
+    return out
 
 
 def cfg5_session_params(s, seed):
@@ -654,7 +701,7 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         launch_ms = float(np.mean(i_ms))
-        traffic, traffic_src = latest_traffic("cs_rings_kernel_cfg3")
+        traffic, traffic_src = latest_traffic("cs_wedge_kernel_cfg3")
         alg_bytes = 4.0 * mean_visits + 8.0 * P
         achieved = alg_bytes / (launch_ms * 1e-3) / 1e9
         value = world * mean_visits * K / (total_ms_max * 1e-3)
@@ -669,9 +716,9 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
         line = {"metric": "HoleMap cell visits/sec", "value": value, "unit": "visits/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 ray set-up -> i32 closed-form walk -> u16 blend", "data": "synthetic",
-                "config": dict(config, candidates_per_scan=0, prime_scans=0, mode="integration only (search gated off)",
-                               l2="flushed (256 MB write) before every timed step",
-                               timing="per-step CUDA events on the launching stream, summed; max over ranks"),
+                "config": dict(config, candidates_per_scan=0, prime_scans=0, mode="integration only (search gated off)"),
+                "l2": "flushed (256 MB write) before every timed step",
+                "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                 "visits_per_step": mean_visits, "rays_per_s": value / mean_visits * P, "clocks": clocks,
                 "e2e": {"value": world * mean_visits * K / (e2e_ms_max * 1e-3), "unit": "visits/s", "h2d_bytes_per_step": 64 + 8 * P,
                         "d2h_bytes_per_step": 8, "ms_per_step": e2e_ms_max / K,
@@ -679,11 +726,13 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
                 "gpu_launches": int(launches),
                 "replay_l2_warm": {"ms_per_step": warm_ms_max, "value": world * mean_visits / (warm_ms_max * 1e-3),
                                    "note": "same replay without L2 flushes, %d scans back to back (the 32 MB map stays in L2)" % W},
-                "roofline": {"bound": "hbm", "kernel": "cs_rings_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "roofline": {"bound": "hbm", "kernel": "cs_wedge_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": launch_ms,
-                             "note": "4 B (2 B read + 2 B write) per visited cell + the scan's points; per-cell ray order is kept, so the kernel "
-                                     "is a chain of per-ring phases (latency), not a stream"},
+                             "limiter": limiter_of("cs_wedge_kernel_cfg3", launch_ms, clock_hz=(clocks.get("sm_mhz") or 1965) * 1e6),
+                             "note": "4 B (2 B read + 2 B write) per visited cell + the scan's points; per-cell ray order is kept inside "
+                                     "(ring range x wedge) tasks, one warp each; at this size the kernel is bound by instruction issue and "
+                                     "dependency latency (see limiter), not by memory"},
                 "cpu_baseline": cpu, "wall_s_timed_region": wall_region, "map_checksum": checksum_after_timed}
         print(json.dumps(line))
     proc.close()
@@ -961,21 +1010,35 @@ def main():
             gather_peak = None
         search_rate = lookups_per_step / (search_ms * 1e-3)
         kname = "cs_search2_kernel" if plan["slab"] else "cs_search_kernel"
+        draw_kernel = "cs_rings_kernel" if os.environ.get("CS_TUNE_INTEGRATE") == "1" else "cs_wedge_kernel"
         traffic, traffic_src = latest_traffic(kname) if args.workload == "cfg2" else (None, None)  # the captures are cfg2's
+        integrate_ms = float(np.mean(i_ms))
+        step_s = total_ms_max / K * 1e-3
+        sm_clock = (clocks.get("sm_mhz") or 1965) * 1e6
         roofline = {"bound": "hbm", "kernel": plan["kernel"] + " (+ the Update glue and pose hand-off in its last warp/block)",
                     "launch_shape": plan, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": search_ms,
-                    "note": "2-byte gathers out of an L2-resident map: not HBM-limited.  launch_ms covers the search stage (sort + search kernels, "
-                            "events around the stage); the random-gather rate below is the ceiling of one-line-per-lane gathers, which "
-                            "the slab search is not held to (its lanes share tiles and hit L1)",
+                    "note": "the contract's HBM fraction of the dominant stage (search: sort + search kernels, events around the stage): "
+                            "2-byte gathers out of an L2-resident map, so this number is small by construction and is NOT what limits "
+                            "the stage — `limiter` says what does, per kernel, from the newest ncu capture of the same sources",
+                    "limiter": {"search": dict(limiter_of(kname, search_ms, clock_hz=sm_clock) or {},
+                                               what="issue + latency: ~24 issue slots per lookup with L1-resident tiles; the stage "
+                                                    "also holds the candidate sort, the cold first touch of the map and the pose hand-off"),
+                                "integrate": dict(limiter_of(draw_kernel, integrate_ms, clock_hz=sm_clock) or {},
+                                                  what="latency chain pose -> rays -> wedge tasks (no block-wide barrier in the draw "
+                                                       "loop); issue-bound only for big scans (cfg3)")},
                     "gather": {"achieved_lookups_per_s": search_rate, "peak_lookups_per_s": gather_peak,
                                "frac": (search_rate / gather_peak) if gather_peak else None,
-                               "peak_source": "cs_gather_peak: random u16 loads over a table the size of the map, measured in this run"},
-                    "integrate": {"kernel": "cs_rings_kernel", "launch_ms": float(np.mean(i_ms)),
+                               "whole_update_frac": (lookups_per_step / step_s / gather_peak) if gather_peak else None,
+                               "peak_source": "cs_gather_peak: random u16 loads over a table the size of the map (one line per lane), "
+                                              "measured in this run; `frac` is the search stage alone, `whole_update_frac` the "
+                                              "lookups of a step over the whole step time"},
+                    "integrate": {"kernel": draw_kernel, "launch_ms": integrate_ms,
                                   "visits_per_launch": float(np.mean(visits)),
-                                  "achieved_GBps": 4.0 * float(np.mean(visits)) / (float(np.mean(i_ms)) * 1e-3) / 1e9,
-                                  "note": "4 B (read + write) per visited cell; ordered per cell, latency-bound"}}
+                                  "achieved_GBps": 4.0 * float(np.mean(visits)) / (integrate_ms * 1e-3) / 1e9,
+                                  "frac_of_hbm": 4.0 * float(np.mean(visits)) / (integrate_ms * 1e-3) / 1e9 / hbm_peak,
+                                  "note": "4 B (read + write) per visited cell; ordered per cell"}}
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -994,9 +1057,13 @@ def main():
         line = {"metric": metric, "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 transform -> u16 gather -> i64 sum", "data": "synthetic",
-                "config": dict(config, l2="flushed (256 MB write) before every timed step; e2e inputs arrive from host memory each step",
-                               timing="per-step CUDA events on the launching stream, summed; max over ranks"),
+                "config": config,
+                "l2": "flushed (256 MB write) before every timed step; e2e inputs arrive from host memory each step",
+                "timing": "per-step CUDA events on the launching stream, summed; max over ranks",
                 "candidate_poses_per_s": value / P,
+                "per_gpu": {"value": value / world, "e2e": e2e_value / world,
+                            "note": "whole-job numbers are N independent replays; the reference arm is ONE CPU process whatever N is, "
+                                    "so a ratio against it is meaningful per GPU"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "lookups/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,
                         "ms_per_step": e2e_ms_max / Ke, "api": "cs_update (C ABI, host buffers, pinned staging, mapped result)",

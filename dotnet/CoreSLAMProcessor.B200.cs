@@ -129,8 +129,20 @@ namespace CoreSLAM.B200
         /// CoreSLAMProcessor.Update (:717-752), whole: the raw rays and segment poses are written straight into the
         /// pinned staging block and uploaded; ScanSegmentsToCloud (:187-207), search, NormalizeAngle and both map
         /// integrations run on the device.  Returns when the pose is known; the integration overlaps the caller.
-        public void Update(List<ScanSegment> segments)
+        public void Update(List<ScanSegment> segments) => Update(segments, null);
+
+        /// Distance and flat candidate index (0 = searchPose, 1 + t*I + i = thread t's i-th candidate) of the pose the last
+        /// search chose; (int.MaxValue, 0) when the scan was integrated without a search.
+        public int LastDistance { get; private set; } = int.MaxValue;
+        public int LastIndex { get; private set; }
+
+        /// Verification mode: the same Update with the candidate offsets given (T*I x (dX, dY, dTheta), thread t iteration i at
+        /// (t*I + i)*3) instead of drawn on the device — what dotnet/reference_verification_hook.patch adds to the reference as
+        /// CoreSLAMProcessor.CandidateTable, so that both implementations search the very same poses.
+        public void Update(List<ScanSegment> segments, float[] candidateOffsets)
         {
+            if (candidateOffsets != null && candidateOffsets.Length != 3 * SearchIterationsPerThread * Math.Max(NumSearchThreads, 1))
+                throw new ArgumentException("candidateOffsets needs T*I*3 floats");
             if (segments.Count == 0) throw new InvalidOperationException("Sequence contains no elements");  // segments.Last(), :719
             float* rays = (float*)staging;                       // maxPoints * (angle, radius)
             float* poses = rays + 2 * maxPoints;                 // maxPoints * (x, y, theta)   (at most one segment per ray)
@@ -151,8 +163,12 @@ namespace CoreSLAM.B200
                 }
             }
             first[s] = n;
-            Native.Check(Native.cs_update_segments(handle, rays, first, poses, n, s, null, out CsResult res), handle);
+            CsResult res;
+            fixed (float* off = candidateOffsets)  // (null stays null: on-device Philox candidates)
+                Native.Check(Native.cs_update_segments(handle, rays, first, poses, n, s, off, out res), handle);
             Pose = new Vector3(res.Pose[0], res.Pose[1], res.Pose[2]);
+            LastDistance = res.Searched != 0 ? res.Distance : int.MaxValue;
+            LastIndex = res.Searched != 0 ? res.Index : 0;
             if (SyncMapAfterUpdate) HoleMap.SyncToHost();
             // UpdateObstacleMap (:751) ran on the device too when the handle was created with obstacle_map_size > 0
         }

@@ -1,17 +1,24 @@
-// ReplayHarness.cs — replays one CSLG scan log (include/coreslam_b200.h, "Scan-log files") through the reference
-// CoreSLAMProcessor and through the B200 drop-in, scan by scan, and reports the first divergence.
-// NOT COMPILED IN THIS REPOSITORY (no .NET SDK in the image).  A SLAM.NET maintainer adds it as a console project that
-// references CoreSLAM.csproj; it is the missing executed-reference pin of the parity claim (DESIGN.md section 7).
+// ReplayHarness.cs — the executed-reference pin of the parity claim (DESIGN.md section 7), for the day a .NET box exists.
+// NOT COMPILED IN THIS REPOSITORY (no .NET SDK in the image).  A SLAM.NET maintainer
+//   1. applies dotnet/reference_verification_hook.patch to CoreSLAM/CoreSLAMProcessor.cs (adds CandidateTable, LastDistance),
+//   2. adds this file, CoreSLAMProcessor.B200.cs and CoreSlamNative.cs as a console project referencing CoreSLAM.csproj,
+//   3. runs   ReplayHarness <log.cslg> [--golden out.golden] [--b200]
+// The harness replays one CSLG scan log (include/coreslam_b200.h, "Scan-log files"; parameters in <log.cslg>.json, written
+// by tools/make_cslg_fixture.py) through the REFERENCE CoreSLAMProcessor with the log's candidate tables, and
+//   --golden   writes one line per scan: scan index, the pose as three float bit patterns (hex), the winning distance, and
+//              the CRC-32 of the little-endian HoleMap — the golden file tests/test_golden_reference.py checks the CPU
+//              oracle and the CUDA path against (tests/golden/<name>.cslg.golden);
+//   --b200     also runs the B200 drop-in scan by scan and stops at the first divergence (pose bits, distance, map CRC).
 //
 // The log stores clouds (ScanCloud.Points) and odometry poses.  The reference only accepts List<ScanSegment>, so each scan
-// is fed as ONE segment at the odometry pose with rays (atan2(y, x), |p|): ScanSegmentsToCloud (:187-207) then rebuilds
-// the cloud from polar form in both implementations alike.  Candidate tables: the reference draws its own (unseeded)
-// deviates, so bit-exact comparison needs the verification hook — replace the two sampler calls in MonteCarloSearch
-// (:633-638) by reads from the table of the current scan (3 floats per candidate, thread t iteration i at 1 + t*I + i - 1).
+// is fed as ONE segment at the odometry pose with rays (atan2(y, x), |p|): ScanSegmentsToCloud (:187-207) then rebuilds the
+// cloud from polar form — in the reference, in the drop-in, and in the pytest that consumes the golden file alike.
 using System;
 using System.Collections.Generic;
+using System.Globalization;
 using System.IO;
 using System.Numerics;
+using System.Text.Json;
 using BaseSLAM;
 
 namespace CoreSLAM.B200
@@ -53,28 +60,67 @@ namespace CoreSLAM.B200
             return new List<ScanSegment> { seg };
         }
 
+        static uint Crc32(ushort[] pixels)   // zlib polynomial, over the little-endian bytes (KAT-B of SURVEY 8c uses the same)
+        {
+            uint crc = 0xFFFFFFFFu;
+            foreach (ushort v in pixels)
+                for (int b = 0; b < 2; b++)
+                {
+                    crc ^= (uint)((v >> (8 * b)) & 0xFF);
+                    for (int i = 0; i < 8; i++) crc = (crc >> 1) ^ (0xEDB88320u & (uint)-(int)(crc & 1));
+                }
+            return ~crc;
+        }
+
+        static string Bits(float f) => BitConverter.SingleToInt32Bits(f).ToString("x8", CultureInfo.InvariantCulture);
+
         public static int Main(string[] args)
         {
-            List<Scan> scans = ReadLog(args[0], out int maxPoints, out int nOffsets);
-            float phys = 40.0f; int holeSize = 2048, obstSize = 512, iters = 1024, threads = 4;   // cfg2 of BASELINE.json
-            using var reference = new CoreSLAM.CoreSLAMProcessor(phys, holeSize, obstSize, scans[0].Odometry, 0.1f, 0.17453292f, iters, threads);
-            using var b200 = new CoreSLAMProcessor(phys, holeSize, obstSize, scans[0].Odometry, 0.1f, 0.17453292f, iters, threads, maxPoints: maxPoints);
+            string logPath = args[0];
+            string goldenPath = null;
+            bool runB200 = false;
+            for (int i = 1; i < args.Length; i++)
+            {
+                if (args[i] == "--golden") goldenPath = args[++i];
+                else if (args[i] == "--b200") runB200 = true;
+            }
+            List<Scan> scans = ReadLog(logPath, out int maxPoints, out int nOffsets);
+            using JsonDocument cfg = JsonDocument.Parse(File.ReadAllText(logPath + ".json"));
+            JsonElement c = cfg.RootElement;
+            float phys = c.GetProperty("physical_map_size").GetSingle();
+            int holeSize = c.GetProperty("hole_map_size").GetInt32(), obstSize = c.GetProperty("obstacle_map_size").GetInt32();
+            int iters = c.GetProperty("iterations_per_thread").GetInt32(), threads = c.GetProperty("num_search_threads").GetInt32();
+            float sxy = c.GetProperty("sigma_xy").GetSingle(), sth = c.GetProperty("sigma_theta").GetSingle();
+            if (nOffsets != iters * Math.Max(threads, 1)) throw new InvalidDataException("log offsets != T*I of its .json");
+
+            using var reference = new CoreSLAM.CoreSLAMProcessor(phys, holeSize, obstSize, scans[0].Odometry, sxy, sth, iters, threads);
+            CoreSLAMProcessor b200 = runB200
+                ? new CoreSLAMProcessor(phys, holeSize, obstSize, scans[0].Odometry, sxy, sth, iters, threads, maxPoints: maxPoints) { SyncMapAfterUpdate = true }
+                : null;
+            using StreamWriter golden = goldenPath != null ? new StreamWriter(goldenPath) : null;
+            golden?.WriteLine("# scan pose_x pose_y pose_theta (float bits, hex) distance holemap_crc32   -- reference mikkleini/slam.net, CandidateTable hook");
             for (int k = 0; k < scans.Count; k++)
             {
                 List<ScanSegment> segs = AsSegments(scans[k]);
-                // reference.CandidateTable = scans[k].Offsets;   // the verification hook described above
+                reference.CandidateTable = scans[k].Offsets;   // the verification hook (reference_verification_hook.patch)
                 reference.Update(segs);
-                b200.Update(segs /* , scans[k].Offsets through cs_update_segments' cand_offsets */);
-                if (reference.Pose != b200.Pose)
+                uint crc = Crc32(reference.HoleMap.Pixels);
+                golden?.WriteLine($"{k} {Bits(reference.Pose.X)} {Bits(reference.Pose.Y)} {Bits(reference.Pose.Z)} {reference.LastDistance} {crc:x8}");
+                if (b200 == null) continue;
+                b200.Update(segs, scans[k].Offsets);
+                bool same = Bits(reference.Pose.X) == Bits(b200.Pose.X) && Bits(reference.Pose.Y) == Bits(b200.Pose.Y) &&
+                            Bits(reference.Pose.Z) == Bits(b200.Pose.Z) && reference.LastDistance == b200.LastDistance &&
+                            crc == Crc32(b200.HoleMap.Pixels);
+                if (!same)
                 {
-                    Console.WriteLine($"scan {k}: reference {reference.Pose} b200 {b200.Pose}");
+                    Console.WriteLine($"scan {k}: reference pose {reference.Pose} distance {reference.LastDistance} crc {crc:x8}; " +
+                                      $"b200 pose {b200.Pose} distance {b200.LastDistance} crc {Crc32(b200.HoleMap.Pixels):x8}");
                     return 1;
                 }
             }
-            b200.HoleMap.SyncToHost();
-            for (int i = 0; i < b200.HoleMap.Pixels.Length; i++)
-                if (b200.HoleMap.Pixels[i] != reference.HoleMap.Pixels[i]) { Console.WriteLine($"HoleMap cell {i} differs"); return 2; }
-            Console.WriteLine($"{scans.Count} scans: poses and HoleMap identical");
+            b200?.Dispose();
+            Console.WriteLine($"{scans.Count} scans replayed" + (runB200 ? ": poses, distances and HoleMap identical" : "") +
+                              (goldenPath != null ? $"; golden written to {goldenPath}" : ""));
             return 0;
         }
     }

@@ -479,6 +479,7 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   const bool fused = searching && phases == CS_PHASE_ALL;
   a.fuse_publish = fused ? 1 : 0;
   a.max_ring_hint = rings - 1;
+  a.w_prefetch = 0;  // the map around the pose goes to L2 ahead of its use (one session alone; batches hide the latency)
   a.diag = c.diag;
   a.diag_rings = c.diag_rings;
   if (phases & CS_PHASE_FINISH) {  // a call that publishes a pose takes the next step id: never 0, alternating parity
@@ -493,6 +494,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_slab = s2.threads;
     a.s2_slot = (*c.s2_toggle ^= 1);
     a.s2_batch = c.n_sessions > 1 ? 1 : 0;
+    // the candidate sort (first kernel of the step) also prefetches the map around the search pose: the search's own first
+    // touch and the integration both find it in L2
+    if (c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && draws) a.w_prefetch = 1;
     a.s2_map = c.hs->map;
     a.s2_sorted = c.hs->s2_sorted + (size_t)a.s2_slot * c.hs->s2_cap;
     a.s2_tmp = c.hs->s2_tmp;
@@ -578,8 +582,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
       if (*c.w_slot >= 3000) *c.w_slot -= 2997;  // (keeps d > 0 and d mod 3)
     }
     a.w_general = tune().w_general > 0 ? 1 : 0;
+    if (a.w_prefetch == 0 && c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0) a.w_prefetch = 2;
     a.w_sub_max = tune().w_sub;
-    a.w_prefetch = (c.n_sessions == 1 && tune().w_prefetch >= 0) ? 1 : 0;  // batches hide the latency with their sessions
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS),
                      wedge_smem(c.hs->size), c.stream, c.d_sess, a);

@@ -187,7 +187,7 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int w_zero;                    // the third the next drawn step will count into (zeroed by this step)
   int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
   int w_sub_max;                 // most warps the rings of one task are split over (0: 8)
-  int w_prefetch;                // 1: the wedge kernel prefetches the map around the pose into L2 while it waits for the pose
+  int w_prefetch;                // the map around the pose is prefetched into L2 — 1: by the candidate sort, 2: by the draw kernel
   int empty_cloud;               // 1: the scan has no points and the step searches: no search kernel ran, the arg-min is
                                  // (int.MaxValue, searchPose) by definition (:251-258, :630-648)
   int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values
@@ -239,6 +239,33 @@ __device__ __forceinline__ void cs_search_pose(const CsSession& S, const CsStepH
     for (int k = 0; k < 3; k++) sp[k] = __fadd_rn(st.pose[k], __fsub_rn(h.odo[k], st.last_odo[k]));  // :728
   } else {
     sp[0] = h.odo[0]; sp[1] = h.odo[1]; sp[2] = h.odo[2];
+  }
+}
+
+// Pulls the part of the map a scan can reach into L2: the tiles within `max_ring_hint` (+ the reach of the search) of the
+// pose the step starts from, one 128-byte tile per iteration, thread t of nt.  Called in the shadow of other work (the
+// candidate sort, the wait for the pose); where the map is L2-resident already the prefetches hit.  The state may be one step
+// old when this runs ahead of the previous step's end: good enough for a prefetch.
+__device__ __forceinline__ void cs_prefetch_disc(const CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, int t, int nt) {
+  float sp[3];
+  if (a.step_mode == CS_STEP_UPDATE && a.do_search) cs_search_pose(S, hdr, a, sp);
+  else { sp[0] = hdr.odo[0]; sp[1] = hdr.odo[1]; sp[2] = hdr.odo[2]; }
+  const int size = S.size, pitch_tiles = S.pitch_tiles;
+  const float scale = S.scale;
+  const int cx = cs_cvt_i32(__fmul_rn(sp[0], scale)), cy = cs_cvt_i32(__fmul_rn(sp[1], scale));
+  const int R = a.max_ring_hint + 16 + (int)(4.0f * S.sigma_xy * scale);
+  if (!(cx > -R && cy > -R && cx < size + R && cy < size + R)) return;  // (NaN / far-off poses: nothing to fetch)
+  const int tx0 = max(cx - R, 0) >> 3, tx1 = min(cx + R, size - 1) >> 3;
+  const int ty0 = max(cy - R, 0) >> 3, ty1 = min(cy + R, size - 1) >> 3;
+  const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
+  const long long r2 = (long long)(R + 8) * (R + 8);
+  for (int i = t; i < tw * th; i += nt) {
+    const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+    const long long dx = tx * 8 + 4 - cx, dy = ty * 8 + 4 - cy;
+    if (dx * dx + dy * dy <= r2) {
+      const uint16_t* line = S.map + ((size_t)ty * pitch_tiles + tx) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
   }
 }
 
@@ -816,6 +843,7 @@ cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // a batch of sessions: one block per session, everything per session comes from its descriptor
   const int sj = blockIdx.y;
   const CsSession& S = sessions[sj];
+  if (a.w_prefetch == 1) cs_prefetch_disc(S, a.hdr[(size_t)sj * a.hdr_stride], a, tid, CS_SORT_THREADS);
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   float4* __restrict__ out = a.s2_batch ? S.s2_sorted + (size_t)a.s2_slot * S.s2_cap : a.s2_sorted;
   float4* __restrict__ tmp = a.s2_batch ? S.s2_tmp : a.s2_tmp;
@@ -888,6 +916,7 @@ cs_sort_hist_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   cs_pdl_launch_dependents();
   const int tid = threadIdx.x;
   const int n = a.cand_count;
+  if (a.w_prefetch == 1) cs_prefetch_disc(sessions[0], a.hdr[0], a, blockIdx.x * CS_SORT_THREADS + tid, gridDim.x * CS_SORT_THREADS);
   const int base_i = blockIdx.x * (CS_SORT_MB_CHUNK);
   const int end_i = min(n, base_i + CS_SORT_MB_CHUNK);
   for (int i = tid; i < CS_SORT_BINS; i += CS_SORT_THREADS) s_hist[i] = 0u;

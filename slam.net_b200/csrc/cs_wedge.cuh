@@ -675,27 +675,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // ---- while the pose is not out yet: pull the part of the map the scan can reach into L2.  The centre is the pose the
   // step starts from (searchPose :728, or the given pose), the radius the ring count the host launched for plus the reach
   // of the search; one 128-byte tile per thread.  (Harmless where the map is L2-resident already: the prefetch hits.)
-  if (TILED && a.w_prefetch) {
-    float sp[3];
-    if (a.step_mode == CS_STEP_UPDATE && a.do_search) cs_search_pose(S, hdr, a, sp);
-    else { sp[0] = hdr.odo[0]; sp[1] = hdr.odo[1]; sp[2] = hdr.odo[2]; }
-    const int cx = cs_cvt_i32(__fmul_rn(sp[0], scale)), cy = cs_cvt_i32(__fmul_rn(sp[1], scale));
-    const int R = a.max_ring_hint + 16 + (int)(4.0f * S.sigma_xy * scale);
-    if (cx > -R && cy > -R && cx < size + R && cy < size + R) {  // (NaN / far-off poses: nothing to fetch)
-      const int tx0 = max(cx - R, 0) >> 3, tx1 = min(cx + R, size - 1) >> 3;
-      const int ty0 = max(cy - R, 0) >> 3, ty1 = min(cy + R, size - 1) >> 3;
-      const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
-      const long long r2 = (long long)(R + 8) * (R + 8);
-      for (int i = (int)blockIdx.x * CS_W_THREADS + tid; i < tw * th; i += (int)gridDim.x * CS_W_THREADS) {
-        const int ty = ty0 + i / tw, tx = tx0 + i % tw;
-        const long long dx = tx * 8 + 4 - cx, dy = ty * 8 + 4 - cy;
-        if (dx * dx + dy * dy <= r2) {
-          const uint16_t* line = map + ((size_t)ty * pitch_tiles + tx) * 64;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-        }
-      }
-    }
-  }
+  if (TILED && a.w_prefetch == 2) cs_prefetch_disc(S, hdr, a, (int)blockIdx.x * CS_W_THREADS + tid, (int)gridDim.x * CS_W_THREADS);
 
   // ---- ray preparation: the first nprep blocks take a.prep_group rays each, one ray per thread
   const int group = a.prep_group;
