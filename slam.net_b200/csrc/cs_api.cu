@@ -5,6 +5,7 @@
 // mapped result slot the finalize kernel stores the pose into.  No CPU fallback exists: every compute
 // entry point launches kernels or fails.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a pointer test unless a profiler is attached
 
 #include <chrono>
 #include <cstdarg>
@@ -33,6 +34,12 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr size_t kHdrBytes = 64;
+// NVTX range over one C-ABI call: shows up as a named span in Nsight Systems / ncu --nvtx
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 constexpr int kRayCopies = 8;  // copies of the per-ray draw parameters of a stand-alone session (see CsSession::rays)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -494,9 +501,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_slab = s2.threads;
     a.s2_slot = (*c.s2_toggle ^= 1);
     a.s2_batch = c.n_sessions > 1 ? 1 : 0;
-    // the candidate sort (first kernel of the step) also prefetches the map around the search pose: the search's own first
-    // touch and the integration both find it in L2
-    if (c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && draws) a.w_prefetch = 1;
+    // (Measured and dropped: letting the candidate sort — the first kernel of the step, one block — prefetch the map around
+    // the search pose: 65 k prefetches from one SM take 40 us.  CS_TUNE_W_PREFETCH=1 still selects it for experiments.)
+    if (c.n_sessions == 1 && c.tiled && tune().w_prefetch == 1 && draws) a.w_prefetch = 1;
     a.s2_map = c.hs->map;
     a.s2_sorted = c.hs->s2_sorted + (size_t)a.s2_slot * c.hs->s2_cap;
     a.s2_tmp = c.hs->s2_tmp;
@@ -1153,6 +1160,7 @@ cs_status cs_get_map_info(const cs_processor* h, int32_t* size, float* scale) {
 cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, const float search_pose[3],
                     const float* cand_poses, const float* cand_cs, int32_t n_cand, uint32_t scan_index,
                     cs_result* best, int32_t* distances) {
+  NvtxRange nvtx_range("cs_search");
   CS_CHECK_HANDLE(h);
   if (!points || !search_pose || !best || n_points <= 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_search: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
@@ -1211,6 +1219,7 @@ cs_status cs_search(cs_processor* h, const float* points, int32_t n_points, cons
 
 cs_status cs_integrate(cs_processor* h, const float* points, int32_t n_points, const float pose[3],
                        const float* pose_cs, int64_t* visits) {
+  NvtxRange nvtx_range("cs_integrate");
   CS_CHECK_HANDLE(h);
   if (!points || !pose || n_points < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_integrate: bad argument");
   if (n_points > h->max_points) return fail(h, CS_ERR_CAPACITY, "n_points %d > max_points %d", n_points, h->max_points);
@@ -1398,6 +1407,7 @@ static cs_status complete_update(cs_processor* h, const CsStepArgs& a, bool timi
 
 cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
                     const float* cand_offsets, cs_result* out) {
+  NvtxRange nvtx_range("cs_update");
   CS_CHECK_HANDLE(h);
   const bool timing = (h->cfg.flags & CS_FLAG_TIMING) != 0;
   CsStepArgs a{};
@@ -1411,6 +1421,7 @@ cs_status cs_update(cs_processor* h, const float* points, int32_t n_points, cons
 // CoreSLAMProcessor.Update(List<ScanSegment>) whole (:717-752): ScanSegmentsToCloud included.
 cs_status cs_update_segments(cs_processor* h, const float* rays, const int32_t* seg_first, const float* seg_poses, int32_t n_rays,
                              int32_t n_segments, const float* cand_offsets, cs_result* out) {
+  NvtxRange nvtx_range("cs_update_segments");
   CS_CHECK_HANDLE(h);
   cs_status st = check_segments(h, rays, seg_first, seg_poses, n_rays, n_segments);
   if (st != CS_OK) return st;
@@ -1451,6 +1462,7 @@ cs_status cs_segments_to_cloud(cs_processor* h, const float* rays, const int32_t
 // ---- multi-GPU candidate split (BASELINE cfg4) ---------------------------------------------
 cs_status cs_update_begin(cs_processor* h, const float* points, int32_t n_points, const float odometry_pose[3],
                           const float* cand_offsets, int32_t cand_first, int32_t cand_count, uint64_t** key_device) {
+  NvtxRange nvtx_range("cs_update_begin");
   CS_CHECK_HANDLE(h);
   if (cand_first < 0 || cand_count < 0 || (long long)cand_first + cand_count > (long long)h->n_cand + 1)
     return fail(h, CS_ERR_INVALID_ARGUMENT, "candidate slice [%d, %d) outside [0, T*I+1 = %d)", cand_first,
@@ -1478,6 +1490,7 @@ cs_status cs_update_begin(cs_processor* h, const float* points, int32_t n_points
 }
 
 cs_status cs_update_finish(cs_processor* h, cs_result* out) {
+  NvtxRange nvtx_range("cs_update_finish");
   CS_CHECK_HANDLE(h);
   if (!h->pending) return fail(h, CS_ERR_STATE, "cs_update_finish without cs_update_begin");
   h->pending = false;
@@ -1619,6 +1632,7 @@ static cs_status ensure_linear(cs_processor* h) {
 }
 
 cs_status cs_map_download(cs_processor* h, uint16_t* pixels) {
+  NvtxRange nvtx_range("cs_map_download");
   CS_CHECK_HANDLE(h);
   if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
   cs_status st = ensure_linear(h);
@@ -1633,6 +1647,7 @@ cs_status cs_map_download(cs_processor* h, uint16_t* pixels) {
 }
 
 cs_status cs_map_upload(cs_processor* h, const uint16_t* pixels) {
+  NvtxRange nvtx_range("cs_map_upload");
   CS_CHECK_HANDLE(h);
   if (!pixels) return fail(h, CS_ERR_INVALID_ARGUMENT, "null pixels");
   cs_status st = ensure_linear(h);
@@ -2045,6 +2060,7 @@ cs_status cs_scanlog_destroy(cs_scanlog* log) {
 }
 
 cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results) {
+  NvtxRange nvtx_range("cs_replay");
   CS_CHECK_HANDLE(h);
   if (!log || !log->uploaded) return fail(h, CS_ERR_STATE, "scan log not uploaded");
   if (log->device != h->device) return fail(h, CS_ERR_INVALID_ARGUMENT, "scan log lives on another device");
@@ -2477,6 +2493,7 @@ cs_status batch_stage_and_launch(cs_batch* b, uint8_t* h_stage, uint8_t* d_stage
 
 cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
                           const float* cand_offsets, cs_result* results) {
+  NvtxRange nvtx_range("cs_batch_update");
   CS_CHECK_BATCH(b);
   if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_update: null argument");
   // the pinned block may still be the source of the previous call's copy
@@ -2500,6 +2517,7 @@ cs_status cs_batch_update(cs_batch* b, const float* points, const int32_t* n_poi
 // works on step k, and consecutive steps stay chained on the stream (no host round trip between them).
 cs_status cs_batch_submit(cs_batch* b, const float* points, const int32_t* n_points, const float* odometry,
                           const float* cand_offsets) {
+  NvtxRange nvtx_range("cs_batch_submit");
   CS_CHECK_BATCH(b);
   if (!points || !n_points || !odometry) return bfail(b, CS_ERR_INVALID_ARGUMENT, "cs_batch_submit: null argument");
   if (b->pipe_submitted - b->pipe_collected >= 2u)
@@ -2539,6 +2557,7 @@ cs_status cs_batch_submit(cs_batch* b, const float* points, const int32_t* n_poi
 }
 
 cs_status cs_batch_collect(cs_batch* b, cs_result* results /* n_sessions records, or NULL to only wait */) {
+  NvtxRange nvtx_range("cs_batch_collect");
   CS_CHECK_BATCH(b);
   if (b->pipe_collected == b->pipe_submitted) return bfail(b, CS_ERR_STATE, "cs_batch_collect: nothing was submitted");
   const int slot = (int)(b->pipe_collected & 1u);
@@ -2557,6 +2576,7 @@ cs_status cs_batch_collect(cs_batch* b, cs_result* results /* n_sessions records
 // and — when the log carries no candidate tables — its own Philox stream).  results: optional, the
 // n_sessions records of the LAST scan replayed.
 cs_status cs_batch_replay(cs_batch* b, const cs_scanlog* log, int32_t first, int32_t count, cs_result* results) {
+  NvtxRange nvtx_range("cs_batch_replay");
   CS_CHECK_BATCH(b);
   if (!log || !log->uploaded) return bfail(b, CS_ERR_STATE, "scan log not uploaded");
   if (log->device != b->device) return bfail(b, CS_ERR_INVALID_ARGUMENT, "scan log lives on another device");
