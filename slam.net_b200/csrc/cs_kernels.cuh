@@ -571,7 +571,7 @@ __device__ __forceinline__ unsigned long long cs_exchange_min(const CsStepArgs& 
 // Glue + publish by one thread (the rays are prepared by the first blocks of the rings kernel).
 __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, const float* cand,
                                            CsDevResult* result, bool have_guess = false, unsigned long long guess = 0ull) {
-  long long* d = (a.diag && blockIdx.y == 0) ? a.diag + ((size_t)a.diag_rings + CS_DIAG_SEARCH_BLOCKS - 1) * 8 : nullptr;
+  long long* d = a.diag ? a.diag + ((size_t)a.diag_rings + CS_DIAG_SEARCH_BLOCKS - 1) * 8 : nullptr;  // (diagnostics: one session)
   if (d) d[0] = cs_globaltimer();
   const bool need_key = a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search;
   unsigned long long key = 0ull;
@@ -1009,8 +1009,14 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   const int pos = slab * a.s2_slab + tid;  // position in the sorted order
   const bool valid = pos < a.cand_count;
 
+  long long* tl = nullptr;  // timeline record of this block (diagnostics)
+  if (a.diag && tid == 0 && (int)(blockIdx.y * gridDim.x + blockIdx.x) < CS_DIAG_SEARCH_BLOCKS - 2) {
+    tl = a.diag + ((size_t)a.diag_rings + blockIdx.y * gridDim.x + blockIdx.x) * 8;
+    tl[0] = cs_smid(); tl[1] = cs_globaltimer(); tl[7] = 0;
+  }
   cs_pdl_wait();  // the sort of this step — and through it the previous step — is complete
   cs_pdl_launch_dependents();
+  if (tl) tl[2] = cs_globaltimer();
 
   float px = 0.f, py = 0.f, c = 0.f, s = 0.f;
   int idx = 0;
@@ -1076,6 +1082,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // last at a candidate sees every other cluster's contribution in the returned word (single-address atomics are
   // totally ordered), so it owns the candidate's complete sum: distance (:251-258), arg-min, and the word goes back to
   // zero for the next step.  No fence, no block-wide wait.
+  if (tl) tl[4] = cs_globaltimer();  // warp 0 is through its lookups
   const unsigned long long mine = (1ull << CS_S2_ARRIVAL_SHIFT) | ((unsigned long long)nb << 32) | (unsigned long long)sum;
   const unsigned long long old = atomicAdd(&acc[pos], mine);
   const bool fin = (unsigned)(old >> CS_S2_ARRIVAL_SHIFT) == n_clusters - 1u;
@@ -1088,6 +1095,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     if (distances) distances[idx] = d;
     acc[pos] = 0ull;
   }
+  if (tl) tl[5] = cs_globaltimer();  // ... and has its atomic back
   const unsigned fin_mask = __ballot_sync(act, fin);
   if (fin_mask == 0u) return;
 #pragma unroll

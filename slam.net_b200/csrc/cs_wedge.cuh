@@ -589,10 +589,11 @@ __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka,
 template <bool TILED>
 __global__ void __launch_bounds__(CS_W_THREADS, 4)
 cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
-  __shared__ int s_first[CS_W_LEVELS + 2];   // first task of each level; s_first[nlev] = number of tasks
+  __shared__ int s_first[CS_W_LEVELS + 2];   // first (sub-)task of each level; s_first[nlev] = their number
   __shared__ int s_uniform[CS_W_LEVELS];     // > 0: the level is cut into this many equal wedges (the dense centre)
   __shared__ int s_tot[CS_W_LEVELS];         // tasks of each level
   __shared__ int s_T[CS_W_LEVELS];           // rays per wedge of a level cut by its sector counts
+  __shared__ int s_split[CS_W_LEVELS];       // warps that share the rings of one task of the level
   __shared__ int s_nlev;
   __shared__ float sh_pose[5];
   __shared__ long long sh_vis[CS_W_WARPS];
@@ -652,12 +653,36 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     }
     __syncthreads();
     if (warp == 0) {
+      // How many warps share the rings of one task.  The wedges of the dense levels (equal wedges as wide as their margins:
+      // several passes of 32 rays per ring, the long tasks of a big scan) are always split ring by ring, up to 8 ways; the
+      // others by the largest power of two that still gives every warp of the grid at most one task (a small scan is a
+      // latency chain: shorter tasks end it sooner; a big one is throughput: whole levels amortise a task's set-up).
+      int dense = 0, other = 0;
+      for (int L0 = 0; L0 < NL; L0 += 32) {
+        const int L = L0 + lane;
+        const int t = L < NL ? s_tot[L] : 0;
+        const bool is_dense = L < NL && s_uniform[L] > 1;
+        dense += is_dense ? t : 0;
+        other += is_dense ? 0 : t;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { dense += __shfl_xor_sync(full, dense, o); other += __shfl_xor_sync(full, other, o); }
+      const int slots = (int)gridDim.x * CS_W_WARPS;
+      const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 8;
+      int sub = 1;
+      while (sub < sub_max && dense * 8 + other * (sub * 2) <= slots) sub *= 2;
       int total = 0, nlev = 0;
       for (int L0 = 0; L0 < NL; L0 += 32) {
         const int L = L0 + lane;
-        const int W = L < NL ? s_tot[L] : 0;
+        int split = 1;
+        if (L < NL) {
+          const int len = cs_w_level_last(L) - cs_w_level_first(L) + 1;
+          split = min(s_uniform[L] > 1 ? 8 : sub, len);
+          s_split[L] = split;
+        }
+        const int W = L < NL ? s_tot[L] * split : 0;
         int incl = W;
-  #pragma unroll
+#pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int u = __shfl_up_sync(full, incl, o);
           if (lane >= o) incl += u;
@@ -752,27 +777,24 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     // holds fewer tasks than the grid has warps, the rings of every task are split over 2, 4 or 8 warps (the kernel is a
     // latency chain: shorter tasks, not fewer, end it sooner).
     const int nblocks = (int)gridDim.x;
-    int sub = 1;
-    const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 8;
-    while (sub < sub_max && n_tasks * (sub * 2) <= nblocks * CS_W_WARPS) sub *= 2;
-    const int n_sub_tasks = n_tasks * sub;
+    const int n_sub_tasks = n_tasks;  // (the table counts sub-tasks: a task's rings split over s_split[level] warps)
     int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
     if (rb < 0) rb += nblocks;
     // the centre goes to the block whose tasks come last in the table (block-uniform branch: cs_w_center has barriers)
     if (rb == nblocks - 1) cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
     for (int stask = rb + nblocks * warp; stask < n_sub_tasks; stask += nblocks * CS_W_WARPS) {
-      const int task = stask / sub;
-      const int sub_j = stask % sub;
-      int L = 0;  // level of the task: last L with s_first[L] <= task
+      int L = 0;  // level of the task: last L with s_first[L] <= stask
       {
         int lo = 0, hi = nlev - 1;
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
-          if (s_first[mid] <= task) lo = mid; else hi = mid - 1;
+          if (s_first[mid] <= stask) lo = mid; else hi = mid - 1;
         }
         L = lo;
       }
-      const int r = task - s_first[L];
+      const int sub = s_split[L];
+      const int r = (stask - s_first[L]) / sub;
+      const int sub_j = (stask - s_first[L]) % sub;
       unsigned blo, bhi;
       if (s_uniform[L] > 0) {
         const int W = s_uniform[L];
