@@ -250,12 +250,7 @@ int wedge_levels(int size) {
 }
 size_t wedge_top_words(int size) { return (size_t)wedge_levels(size) * (CS_W_SECTORS + 1); }
 size_t wedge_smem(int) { return 0; }
-cudaError_t wedge_allow_shared_memory() {
-  const int most = (int)(CS_W_LEVELS * CS_W_SECTORS * sizeof(unsigned short));
-  cudaError_t e = cudaFuncSetAttribute(cs_wedge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-  return e;
-}
+cudaError_t wedge_allow_shared_memory();
 
 int rings_hint_of(int size, float scale, float hole_width, double max_range) {
   if (!(max_range == max_range) || max_range > 1e30) return size;
@@ -299,7 +294,7 @@ double max_range_of(const float* points, int n) {
 struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
-  int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0;
+  int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0, w_carveout = 0, s2_carveout = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -313,6 +308,8 @@ struct Tune {
     w_general = geti("CS_TUNE_W_GENERAL");      // 1: every task of the wedge kernel takes its general path (tests)
     w_blocks = geti("CS_TUNE_W_BLOCKS");        // blocks of the wedge kernel per session
     w_prefetch = geti("CS_TUNE_W_PREFETCH");    // -1: no L2 prefetch of the map around the pose
+    w_carveout = geti("CS_TUNE_W_CARVEOUT");    // shared-memory carve-out (percent) of the wedge kernel
+    s2_carveout = geti("CS_TUNE_S2_CARVEOUT");  // ... of the slab-search and sort kernels
     w_prev = geti("CS_TUNE_W_PREV");            // -1: every scan builds its task table from its own counts
     w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
     ring_span = geti("CS_TUNE_RING_SPAN");
@@ -323,6 +320,24 @@ struct Tune {
   }
 };
 const Tune& tune() { static Tune t; return t; }
+
+cudaError_t wedge_allow_shared_memory() {
+  // Experiment knobs: the shared-memory carve-out the draw and search kernels ask for (percent of the SM's 228 KB).  A
+  // kernel whose carve-out differs from its predecessor's cannot share an SM with it.
+  cudaError_t e = cudaSuccess;
+  if (tune().w_carveout > 0) {
+    e = cudaFuncSetAttribute(cs_wedge_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+  }
+  if (e == cudaSuccess && tune().s2_carveout > 0) {
+    e = cudaFuncSetAttribute(cs_search2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().s2_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_search2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().s2_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_sort_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().s2_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_sort_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().s2_carveout);
+  }
+  return e;
+}
+
 
 int device_sm_count(int device) {
   static int cache[64] = {0};

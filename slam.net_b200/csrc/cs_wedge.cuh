@@ -595,6 +595,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ int s_T[CS_W_LEVELS];           // rays per wedge of a level cut by its sector counts
   __shared__ int s_split[CS_W_LEVELS];       // warps that share the rings of one task of the level
   __shared__ int s_nlev;
+  __shared__ int s_ticket;
   __shared__ float sh_pose[5];
   __shared__ long long sh_vis[CS_W_WARPS];
   __shared__ unsigned s_val[CS_W_WARPS][CS_W_CAP];
@@ -714,6 +715,11 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       int* other = S.w_top + (size_t)a.w_zero * top_words;
       for (int i = tid; i < (int)top_words; i += CS_W_THREADS) other[i] = 0;
     }
+    // (at most CS_W_THREADS rays per block: a.prep_group <= CS_W_THREADS is what the host launches)
+    const bool my_warp = g_begin + warp * 32 < g_end;  // whole warps: the warp reductions need every lane
+    const int my_i = g_begin + tid;
+    const bool in_range = my_warp && my_i < g_end;
+    const float2 my_p = in_range ? __ldg(points + my_i) : make_float2(1.f, 0.f);  // in flight while the pose is awaited
     if (tid < 5) {
       volatile unsigned long long* ll = S.ll_pose + tid;
       unsigned long long w;
@@ -725,24 +731,21 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const float cs[2] = {sh_pose[3], sh_pose[4]};
     const CsRayFrame f = cs_ray_frame(S, pose, cs);
     long long vis = 0;
-    // (at most CS_W_THREADS rays per block and pass; a.prep_group <= CS_W_THREADS is what the host launches)
     CsWPrepared q;
     q.key = 0.f; q.dxc = -1; q.bm = -1;
-    const bool my_warp = g_begin + warp * 32 < g_end;  // whole warps: the warp reductions need every lane
     if (my_warp) {
-      const int i = g_begin + tid;
-      const bool in_range = i < g_end;
-      const float2 p = in_range ? __ldg(points + i) : make_float2(1.f, 0.f);
-      q = cs_w_prepare(S, f, p, i, in_range, vis);
+      q = cs_w_prepare(S, f, my_p, my_i, in_range, vis);
       if (a.w_prev < 0) cs_w_count(S, q, top);  // this scan's own table needs the counts before the rays are announced
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(full, vis, o);
-    if (lane == 0) sh_vis[warp] = vis;
     __threadfence();  // this thread's stores (and counts) are visible device-wide before the block's arrival is counted
     __syncthreads();
     if (tid < copies) atomicAdd(S.prep_words + ((size_t)slot * copies + tid) * 16, 1ull);
-    if (my_warp && a.w_prev >= 0) cs_w_count(S, q, top);  // off the critical path: these size the next scan's wedges
+    // off the critical path: the counts that size the next scan's wedges, and the visit count
+    if (my_warp && a.w_prev >= 0) cs_w_count(S, q, top);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vis += __shfl_xor_sync(full, vis, o);
+    if (lane == 0) sh_vis[warp] = vis;
+    __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < CS_W_WARPS; w++) vis += sh_vis[w];
       if (vis) {
@@ -752,37 +755,36 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     }
     if (a.w_prev >= 0) build_table();
   }
-  // ---- everybody: wait for the preparing blocks
-  if (tid == 0) {
-    volatile unsigned long long* pw = S.prep_words + ((size_t)slot * copies + (cs_smid() % copies)) * 16;
-    while (*pw != (unsigned long long)nprep) {}
-    __threadfence();
+  // ---- everybody: wait for the preparing blocks — as late as possible: with the table at hand (built from the previous
+  // scan's counts) a block first draws its ticket and every warp works out its wedge, and only then are this scan's rays
+  // needed.
+  bool have_rays = false;
+  int x1 = 0, y1 = 0;
+  long long t_prep = 0;
+  auto wait_rays = [&]() {  // (whole block)
+    if (tid == 0) {
+      volatile unsigned long long* pw = S.prep_words + ((size_t)slot * copies + (cs_smid() % copies)) * 16;
+      while (*pw != (unsigned long long)nprep) {}
+      __threadfence();
+    }
+    __syncthreads();
+    have_rays = true;
+    if (a.diag) t_prep = cs_globaltimer();
+    const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));  // (final: the preparing blocks saw them)
+    const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
+    x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
+    y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
+  };
+  if (a.w_prev < 0) {  // this scan's own counts: the table needs the rays first
+    wait_rays();
+    build_table();
   }
-  __syncthreads();
-  const long long t_prep = a.diag ? cs_globaltimer() : 0;
-  if (a.w_prev < 0) build_table();
-  __syncthreads();
   const long long t_sched = a.diag ? cs_globaltimer() : 0;
   const int nlev = s_nlev;
   const int n_tasks = s_first[nlev];
-  const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
-  const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
-  const int x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
-  const int y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
 
-  // ---- tasks: static round-robin over the warps of the session's blocks, the (long) centre tasks first, starting with
-  // the warps of the blocks that did not prepare rays
-  {
-    // consecutive tasks go to different blocks (different SMs); the blocks that prepared rays come last.  When the table
-    // holds fewer tasks than the grid has warps, the rings of every task are split over 2, 4 or 8 warps (the kernel is a
-    // latency chain: shorter tasks, not fewer, end it sooner).
-    const int nblocks = (int)gridDim.x;
-    const int n_sub_tasks = n_tasks;  // (the table counts sub-tasks: a task's rings split over s_split[level] warps)
-    int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
-    if (rb < 0) rb += nblocks;
-    // the centre goes to the block whose tasks come last in the table (block-uniform branch: cs_w_center has barriers)
-    if (rb == nblocks - 1) cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
-    for (int stask = rb + nblocks * warp; stask < n_sub_tasks; stask += nblocks * CS_W_WARPS) {
+  // wedge and rings of (sub-)task stask; false: nothing to do
+  auto decode = [&](int stask, int& ka, int& kb, unsigned& blo, unsigned& bhi) -> bool {
       int L = 0;  // level of the task: last L with s_first[L] <= stask
       {
         int lo = 0, hi = nlev - 1;
@@ -795,10 +797,9 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       const int sub = s_split[L];
       const int r = (stask - s_first[L]) / sub;
       const int sub_j = (stask - s_first[L]) % sub;
-      unsigned blo, bhi;
       if (s_uniform[L] > 0) {
         const int W = s_uniform[L];
-        if (r >= W) continue;
+        if (r >= W) return false;
         blo = cs_w_beta(r, W);
         bhi = cs_w_beta(r + 1, W);
       } else {
@@ -812,7 +813,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
         }
         p1 += __shfl_sync(full, p0, 31);
         const int T = s_T[L], W = s_tot[L];
-        if (r >= W) continue;
+        if (r >= W) return false;
         unsigned bnd[2];
 #pragma unroll
         for (int e = 0; e < 2; e++) {
@@ -834,8 +835,52 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       // this warp's share of the level's rings
       const int k0 = cs_w_level_first(L), k1 = cs_w_level_last(L);
       const int per = (k1 - k0 + sub) / sub;
-      const int ka = k0 + sub_j * per, kb = min(k1, ka + per - 1);
-      if (ka > k1) continue;
+      ka = k0 + sub_j * per; kb = min(k1, ka + per - 1);
+      if (ka > k1) return false;
+      return true;
+  };
+
+  // ---- tasks.  The table counts sub-tasks: a task's rings split over s_split[level] warps; inner levels come first.
+  const int n_sub_tasks = n_tasks;
+  const int n_tickets = (n_sub_tasks + CS_W_WARPS - 1) / CS_W_WARPS;
+  if (n_tickets < (int)gridDim.x) {
+    // A scan with at most a ticket per block (a latency chain).  Blocks draw tickets: ticket t is the sub-tasks t,
+    // t + n_tickets, t + 2 n_tickets ... — one per warp, from all over the table — and the ticket behind the last one is the
+    // centre.  Blocks that become resident late (an SM the search kernel left late) find the tickets gone instead of
+    // holding the scan up with tasks of their own.
+    for (;;) {
+      __syncthreads();  // (the previous ticket's readers are done; all warps are through their tasks)
+      if (tid == 0) s_ticket = (int)atomicAdd(&S.ring_ticket[slot], 1u);
+      __syncthreads();
+      const int ticket = s_ticket;
+      if (ticket > n_tickets) break;
+      int ka = 0, kb = -1;
+      unsigned blo = 0u, bhi = 0u;
+      const int stask = ticket + n_tickets * warp;
+      const bool ok = ticket < n_tickets && stask < n_sub_tasks && decode(stask, ka, kb, blo, bhi);
+      if (!have_rays) wait_rays();
+      if (ticket == n_tickets) {  // (block-uniform branch: cs_w_center has barriers)
+        cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
+        continue;
+      }
+      if (!ok) continue;
+      long long* tl = (a.diag && sj == 0 && stask < a.diag_rings) ? a.diag + (size_t)stask * 8 : nullptr;
+      if (tl && lane == 0) { tl[0] = cs_globaltimer(); tl[4] = t_start; tl[5] = t_prep; tl[6] = t_sched; tl[7] = cs_smid() | ((long long)blockIdx.x << 16); }
+      cs_w_run<TILED>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
+                      s_list[warp], s_bmap[warp], tl);
+    }
+  } else {
+    // A big scan or a session of a batch (throughput): static round-robin over the warps of the session's blocks, consecutive
+    // sub-tasks to different blocks, the blocks that prepared rays last; the centre to the block whose tasks come last.
+    if (!have_rays) wait_rays();
+    const int nblocks = (int)gridDim.x;
+    int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
+    if (rb < 0) rb += nblocks;
+    if (rb == nblocks - 1) cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
+    for (int stask = rb + nblocks * warp; stask < n_sub_tasks; stask += nblocks * CS_W_WARPS) {
+      int ka = 0, kb = -1;
+      unsigned blo = 0u, bhi = 0u;
+      if (!decode(stask, ka, kb, blo, bhi)) continue;
       long long* tl = (a.diag && sj == 0 && stask < a.diag_rings) ? a.diag + (size_t)stask * 8 : nullptr;
       if (tl && lane == 0) { tl[0] = cs_globaltimer(); tl[4] = t_start; tl[5] = t_prep; tl[6] = t_sched; tl[7] = cs_smid() | ((long long)blockIdx.x << 16); }
       cs_w_run<TILED>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],

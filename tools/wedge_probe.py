@@ -28,7 +28,8 @@ for rep in range(2):
     pub = full[size + 8191]
     rc = full[:size]
     rc = rc[rc[:, 0] > 0]
-    t0 = rc[:, 4].min()
+    t0 = rc[rc[:, 4] > 0, 4].min()
+    us = lambda a: (a - t0) / 1e3
     se = full[size:size + 8190]
     se = se[se[:, 1] > t0 - 200000]  # this step's search blocks
     if len(se):
@@ -37,7 +38,6 @@ for rep in range(2):
             np.percentile(us(se[:, 4]), 50), us(se[:, 4]).max(), np.percentile(us(se[:, 5]), 50), us(se[:, 5]).max()))
     if pub[2] > 0:
         print("pose: publisher entry %.2f, pose known %.2f, pose words out %.2f, record out %.2f" % tuple((pub[:4] - t0) / 1e3))
-    us = lambda a: (a - t0) / 1e3
     print("---- step %d: %d tasks recorded on %d SMs" % (rep, len(rc), len(np.unique(rc[:, 7]))))
     q = lambda a: "min %6.2f p50 %6.2f p90 %6.2f max %6.2f" % (a.min(), np.percentile(a, 50), np.percentile(a, 90), a.max())
     print("block start      ", q(us(rc[:, 4])))
