@@ -511,7 +511,8 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
             "lookups_per_s": lookups_per_step * K / (dev_ms_max * 1e-3), "scaling": "strong",
             "e2e": {"value": lookups_per_step * K / (wall_ms_max * 1e-3), "unit": "lookups/s", "ms_per_step": wall_ms_max / K,
                     "h2d_bytes_per_step": 64 + 8 * P, "d2h_bytes_per_step": 32,
-                    "api": "cs_update_begin -> exchange -> cs_update_finish with host points (the timed loop itself)"},
+                    "api": ("cs_update_begin -> all_reduce(MIN) -> cs_update_finish" if args.split == "nccl" else
+                            "cs_update on a handle attached to the group (cs_group_attach)") + " with host points (the timed loop itself)"},
             "scan_to_pose_latency_ms": {"p50": float(np.percentile(lat, 50) * 1e3), "p99": float(np.percentile(lat, 99) * 1e3)},
             "exchange": ("torch.distributed all_reduce(MIN) on the 8-byte in-session key, %d ranks" % world) if args.split == "nccl" else
                         ("inside the search kernel: every rank's publishing thread stores {key, tag} (16 B) into every rank's table "

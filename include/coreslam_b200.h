@@ -44,6 +44,11 @@ typedef enum cs_status {
 #define CS_FLAG_DEBUG_RAYS 0x20u   /* keep x1,y1,x2,y2,xp,yp of every ray of the last integration (cs_get_rays) */
 #define CS_FLAG_SEARCH_WARP 0x40u  /* always search with the warp-per-candidate kernel (default: by candidate count) */
 #define CS_FLAG_SEARCH_SLAB 0x80u  /* always search with the heading-sorted slab kernels, whatever the candidate count */
+#define CS_FLAG_DEBUG_BOUNDED_SPIN 0x100u /* debugging aid: every device-side poll between the kernels of a step (pose, ray
+                                             arrival, cell hand-off) gives up after 2 s (CS_TUNE_SPIN_MS) instead of spinning
+                                             for ever; the grid drains and the handle's next call returns CS_ERR_CUDA naming
+                                             the poll.  For runs under MPS / time-slicing / a debugger, where the co-residency
+                                             the polls rely on may not hold.  Costs one clock read per 1024 poll turns. */
 
 typedef struct cs_processor cs_processor; /* opaque; replaces a CoreSLAMProcessor instance */
 typedef struct cs_scanlog cs_scanlog;     /* opaque; device-resident scan log for replays */

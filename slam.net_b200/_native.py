@@ -104,6 +104,7 @@ FLAG_L2_PERSIST = 0x10
 FLAG_DEBUG_RAYS = 0x20
 FLAG_SEARCH_WARP = 0x40
 FLAG_SEARCH_SLAB = 0x80
+FLAG_DEBUG_BOUNDED_SPIN = 0x100  # device-side polls give up after 2 s (CS_TUNE_SPIN_MS) -> CS_ERR_CUDA instead of a hang
 EXPORT_GRAY16, EXPORT_PACKED4, EXPORT_OBSTACLE_I8 = 0, 1, 2
 
 STATUS_NAMES = {0: "CS_OK", 1: "CS_ERR_INVALID_ARGUMENT", 2: "CS_ERR_NO_DEVICE", 3: "CS_ERR_CUDA",

@@ -114,7 +114,7 @@ struct cs_processor {
   int stage_flip = 0, stage_cur = 0;
 
   // mapped result slot
-  uint8_t* h_slot = nullptr;  // pinned+mapped: CsDevResult at 0, seq flag at 64
+  uint8_t* h_slot = nullptr;  // pinned+mapped: CsDevResult at 0, seq flag at 64, stuck-poll word (CsSpin) at 96
   uint8_t* d_slot = nullptr;
   unsigned seq = 0;
 
@@ -131,6 +131,7 @@ struct cs_processor {
 
   // candidate-split group (cs_group_*): this rank's exchange table and the (peer-mapped) tables of all ranks
   int group_rank = 0, group_world = 0;
+  bool group_shares_device = false;  // another rank of the group runs on this handle's device (same process)
   unsigned xchg_seq = 0;
   unsigned long long* d_xchg = nullptr;
   unsigned long long* xchg_peer[CS_GROUP_MAX] = {};
@@ -181,10 +182,28 @@ cs_status fail(cs_processor* h, cs_status code, const char* fmt, ...) {
       return fail((h), CS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// CS_FLAG_DEBUG_BOUNDED_SPIN: a device-side poll of an earlier step gave up (CsSpin, cs_kernels.cuh): the handle fails
+const char* stuck_site_name(unsigned w) {
+  switch (w & 0xffu) {
+    case CS_STUCK_POSE: return "the pose of the step (search kernel / set-up kernel never published it)";
+    case CS_STUCK_RAYS: return "the rays of the step (a preparing block never arrived)";
+    case CS_STUCK_HANDOFF: return "the hand-off word of a contested cell";
+    default: return "an unknown word";
+  }
+}
+#define CS_CHECK_STUCK(h, slot, failfn)                                                                         \
+  do {                                                                                                          \
+    const unsigned _w = (slot) ? *reinterpret_cast<volatile unsigned*>(slot) : 0u;                              \
+    if (_w)                                                                                                     \
+      return failfn((h), CS_ERR_CUDA, "bounded polls: block %u of the draw kernel gave up waiting for %s", _w >> 8, \
+                    stuck_site_name(_w));                                                                       \
+  } while (0)
+
 #define CS_CHECK_HANDLE(h)                                                          \
   do {                                                                              \
     if (!(h)) return CS_ERR_INVALID_ARGUMENT;                                       \
     if ((h)->poisoned) return CS_ERR_CUDA;                                          \
+    CS_CHECK_STUCK(h, (h)->h_slot ? (h)->h_slot + 96 : nullptr, fail);              \
     cudaError_t _e = cudaSetDevice((h)->device);                                    \
     if (_e != cudaSuccess) return fail((h), CS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(_e)); \
   } while (0)
@@ -295,6 +314,7 @@ struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
   int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0, w_carveout = 0, s2_carveout = 0;
+  int spin_ms = 0, fault = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -312,6 +332,8 @@ struct Tune {
     s2_carveout = geti("CS_TUNE_S2_CARVEOUT");  // ... of the slab-search and sort kernels
     w_prev = geti("CS_TUNE_W_PREV");            // -1: every scan builds its task table from its own counts
     w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
+    spin_ms = geti("CS_TUNE_SPIN_MS");          // CS_FLAG_DEBUG_BOUNDED_SPIN: milliseconds a device-side poll lasts (default 2000)
+    fault = geti("CS_TUNE_FAULT");              // tests of the bounded polls: 1 = the draw kernel waits for a pose tag nobody publishes
     ring_span = geti("CS_TUNE_RING_SPAN");
     ring_threads = geti("CS_TUNE_RING_THREADS");
     ring_slot_bits = geti("CS_TUNE_RING_SLOT_BITS");
@@ -453,6 +475,7 @@ struct LaunchCtx {
   int* w_slot = nullptr;   // which half of CsSession::w_top the next drawn step counts into
   long long* diag;
   int diag_rings;
+  volatile unsigned* stuck_dev = nullptr;  // CS_FLAG_DEBUG_BOUNDED_SPIN: device address of the mapped-host word (CsSpin)
   cudaEvent_t ev_pose;   // optional: recorded once the pose is out
   cudaEvent_t ev_done;   // optional: recorded after the rings kernel
 };
@@ -504,6 +527,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   a.w_prefetch = 0;  // the map around the pose goes to L2 ahead of its use (one session alone; batches hide the latency)
   a.diag = c.diag;
   a.diag_rings = c.diag_rings;
+  a.stuck_flag = c.stuck_dev;
+  a.spin_ns = c.stuck_dev ? (long long)(tune().spin_ms > 0 ? tune().spin_ms : 2000) * 1000000ll : 0;
   if (phases & CS_PHASE_FINISH) {  // a call that publishes a pose takes the next step id: never 0, alternating parity
     if (++(*c.step_counter) == 0) *c.step_counter = 2;
     a.step_id = *c.step_counter;
@@ -590,9 +615,10 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     int blocks = c.n_sessions == 1 ? 4 * c.num_sms : 4;
     if (tune().w_blocks > 0) blocks = tune().w_blocks;
     if (blocks < nprep) blocks = nprep;
-    // A rank of a candidate-split group must not keep a grid of polling blocks resident while its search kernel waits for
-    // the other ranks' keys (ranks that share a device would starve each other): its draw kernel starts after the search.
-    if (a.xchg_world > 1) g_next_launch_plain = true;
+    // A rank of a candidate-split group that shares its device with another rank (several handles of one process on one GPU)
+    // must not keep a grid of polling blocks resident while its search kernel waits for the other ranks' keys — the ranks
+    // would starve each other: its draw kernel starts after the search.  Ranks on devices of their own overlap as usual.
+    if (a.xchg_world > 1 && a.xchg_serial_draw) g_next_launch_plain = true;
     {  // the counters rotate through three thirds: counted into now / counted into by the previous drawn step / zeroed now
       const int d = (*c.w_slot)++;
       a.w_slot = d % 3;
@@ -606,9 +632,11 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.w_general = tune().w_general > 0 ? 1 : 0;
     if (a.w_prefetch == 0 && c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0) a.w_prefetch = 2;
     a.w_sub_max = tune().w_sub;
+    CsStepArgs draw_args = a;
+    if (tune().fault == 1 && c.stuck_dev) draw_args.step_id ^= 0x40000000u;  // (fault injection: a pose tag nobody publishes)
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS),
-                     wedge_smem(c.hs->size), c.stream, c.d_sess, a);
+                     wedge_smem(c.hs->size), c.stream, c.d_sess, draw_args);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -695,6 +723,7 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.s2_min_cand = cs_s2_min_cand(h->cfg.flags);
   c.s2_toggle = &h->s2_toggle;
   c.hs = &h->hs;
+  if (h->cfg.flags & CS_FLAG_DEBUG_BOUNDED_SPIN) c.stuck_dev = reinterpret_cast<volatile unsigned*>(h->d_slot + 96);
   a.hdr_stride = 1;
   const bool want_pose_event = timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN));
   c.ev_pose = (want_pose_event && (phases & CS_PHASE_FINISH)) ? h->tm.ev[ev_base + 0] : nullptr;
@@ -719,6 +748,7 @@ void apply_group(cs_processor* h, CsStepArgs& a) {
   a.cand_first = (int)lo;
   a.cand_count = (int)(hi - lo);
   a.xchg_world = h->group_world;
+  a.xchg_serial_draw = h->group_shares_device ? 1 : 0;
   a.xchg_rank = h->group_rank;
   a.xchg_seq = ++h->xchg_seq;
   for (int p = 0; p < h->group_world; p++) a.xchg_peer[p] = h->xchg_peer[p];
@@ -1403,6 +1433,7 @@ static cs_status complete_update(cs_processor* h, const CsStepArgs& a, bool timi
     st = collect_timing(h, true);
     if (st != CS_OK) return st;
   }
+  CS_CHECK_STUCK(h, h->h_slot + 96, fail);
   if (reinterpret_cast<const CsDevResult*>(h->h_slot)->searched < 0)
     return fail(h, CS_ERR_NCCL, "candidate-split group: a rank never delivered its arg-min (exchange timed out after %.1f s)",
                 (double)CS_XCHG_TIMEOUT_NS * 1e-9);
@@ -1548,6 +1579,7 @@ cs_status cs_group_detach(cs_processor* h) {
   }
   h->group_world = 0;
   h->group_rank = 0;
+  h->group_shares_device = false;
   h->xchg_seq = 0;
   if (h->d_xchg) CS_CUDA(h, cudaMemset(h->d_xchg, 0, (size_t)2 * CS_GROUP_MAX * 2 * sizeof(unsigned long long)));
   cudaGetLastError();
@@ -1607,6 +1639,7 @@ cs_status cs_group_attach_local(cs_processor* h, int32_t rank, int32_t world, cs
         return fail(h, CS_ERR_CUDA, "cs_group_attach_local: peer %d has no exchange table", p);
       }
       cudaSetDevice(h->device);
+      if (q->device == h->device) h->group_shares_device = true;
       if (q->device != h->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(q->device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
@@ -2173,6 +2206,8 @@ struct cs_batch {
   uint8_t* d_stage = nullptr;
   CsDevResult* d_results = nullptr;
   CsDevResult* h_results = nullptr;  // pinned
+  uint8_t* h_stuck = nullptr;        // CS_FLAG_DEBUG_BOUNDED_SPIN: pinned+mapped stuck-poll word (CsSpin), and its device address
+  uint8_t* d_stuck = nullptr;
   int parity = 0, scan_count = 0, search_begin = 5;
   unsigned update_count = 0;
   uint64_t launches = 0;
@@ -2212,6 +2247,7 @@ cs_status bfail(cs_batch* b, cs_status code, const char* fmt, ...) {
   do {                                                                              \
     if (!(b)) return CS_ERR_INVALID_ARGUMENT;                                       \
     if ((b)->poisoned) return CS_ERR_CUDA;                                          \
+    CS_CHECK_STUCK(b, (b)->h_stuck, bfail);                                         \
     if (cudaSetDevice((b)->device) != cudaSuccess) return bfail((b), CS_ERR_CUDA, "cudaSetDevice failed"); \
   } while (0)
 
@@ -2229,6 +2265,7 @@ LaunchCtx batch_ctx(cs_batch* b) {
   c.s2_min_cand = cs_s2_min_cand(b->flags, b->n);
   c.s2_toggle = &b->s2_toggle;
   c.hs = &b->hs[0];
+  c.stuck_dev = reinterpret_cast<volatile unsigned*>(b->d_stuck);
   return c;
 }
 
@@ -2328,6 +2365,11 @@ cs_status cs_batch_create(const cs_config* cfgs, int32_t n_sessions, cs_batch** 
   ok = ok && cudaMalloc(&b->d_stage, b->stage_bytes) == cudaSuccess;
   ok = ok && cudaMalloc(&b->d_results, sizeof(CsDevResult) * (size_t)n_sessions) == cudaSuccess;
   ok = ok && cudaHostAlloc(&b->h_results, sizeof(CsDevResult) * (size_t)n_sessions, cudaHostAllocDefault) == cudaSuccess;
+  if (b->flags & CS_FLAG_DEBUG_BOUNDED_SPIN) {
+    ok = ok && cudaHostAlloc(&b->h_stuck, 64, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer((void**)&b->d_stuck, b->h_stuck, 0) == cudaSuccess;
+    if (ok) memset(b->h_stuck, 0, 64);
+  }
   ok = ok && rings_allow_shared_memory() == cudaSuccess;
   if (!ok) {
     cudaError_t e = cudaGetLastError();
@@ -2404,6 +2446,7 @@ cs_status cs_batch_destroy(cs_batch* b) {
   cudaFree(b->d_results);
   if (b->h_stage) cudaFreeHost(b->h_stage);
   if (b->h_results) cudaFreeHost(b->h_results);
+  if (b->h_stuck) cudaFreeHost(b->h_stuck);
   for (int i = 0; i < 2; i++) {
     cudaFree(b->pipe_d_stage[i]);
     cudaFree(b->pipe_d_results[i]);

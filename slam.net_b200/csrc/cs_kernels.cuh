@@ -155,6 +155,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int search_chunk;  // points staged in shared memory per pass of the search kernel (<= CS_SEARCH_CHUNK)
   unsigned step_id;  // nonzero, different for consecutive steps on the same session(s): tags ll_pose, selects the counter slots
   long long* visits_out;  // optional device slot that receives the visit count
+  volatile unsigned* stuck_flag;  // CS_FLAG_DEBUG_BOUNDED_SPIN: mapped-host word that receives the CsStuckSite of a poll
+  long long spin_ns;              // that gave up after spin_ns nanoseconds (0: polls are unbounded, the normal build of a step)
   long long* diag;        // optional diagnostics buffer (8 values per block of the rings kernel, then 8 per block of
                           // the search kernel), see cs_get_ring_cycles
   int diag_rings;         // records reserved for the rings kernel in diag
@@ -180,7 +182,7 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int xchg_world;                // 0 / 1: no exchange
   int xchg_rank;
   unsigned xchg_seq;             // exchange number, the same on every rank
-  unsigned xchg_pad;
+  int xchg_serial_draw;          // 1: another rank shares this device: the draw kernel must not be resident during the exchange
   unsigned long long* xchg_peer[CS_GROUP_MAX];
   int w_slot;                    // which third of CsSession::w_top this step counts into (rotates per drawn step)
   int w_prev;                    // the third the previous drawn step counted into (its counts size this step's wedges); -1: none
@@ -218,6 +220,26 @@ __device__ __forceinline__ void cs_pdl_launch_dependents() { asm volatile("gridd
 // diagnostics only (a.diag != nullptr): wall-clock stamps and the SM a block ran on
 __device__ __forceinline__ long long cs_globaltimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t) :: "memory"); return t; }
 __device__ __forceinline__ int cs_smid() { int v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+
+// Bounded polls (CS_FLAG_DEBUG_BOUNDED_SPIN).  The kernels of a step talk to each other through words they poll (the pose
+// out of the search kernel, the arrival count of the preparing blocks, the hand-off word of a contested cell); the polls
+// rely on co-residency arguments and normally have no way out.  With CsStepArgs::spin_ns set every
+// poll looks at the clock once in 1024 turns, gives up after spin_ns, and reports where through the mapped-host word: the
+// block leaves the kernel (its partners' polls then run out too, so the grid drains), and the host turns the word into
+// CS_ERR_CUDA on the handle's next call instead of a hang.
+enum CsStuckSite { CS_STUCK_NONE = 0, CS_STUCK_POSE = 1, CS_STUCK_RAYS = 2, CS_STUCK_HANDOFF = 3 };
+struct CsSpin {
+  long long t0 = 0;
+  unsigned turns = 0;
+  __device__ __forceinline__ bool expired(const CsStepArgs& a, unsigned site) {
+    if (a.spin_ns == 0 || (++turns & 1023u) != 0u) return false;
+    const long long t = cs_globaltimer();
+    if (t0 == 0) { t0 = t; return false; }
+    if (t - t0 < a.spin_ns) return false;
+    if (a.stuck_flag) { *a.stuck_flag = site | ((unsigned)blockIdx.x << 8); __threadfence_system(); }
+    return true;
+  }
+};
 #define CS_DIAG_SEARCH_BLOCKS 8192  // search-kernel timeline records kept after the per-ring records
 
 // wrapping int32 arithmetic (C# unchecked)
@@ -1287,14 +1309,17 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const int g_begin = blockIdx.x * group, g_end = min(n, g_begin + group);
     const int i0 = g_begin + tid;
     const float2 p0 = (i0 < g_end) ? __ldg(points + i0) : make_float2(1.f, 0.f);  // in flight while the pose is awaited
+    bool stuck = false;
     if (tid < 5) {
       volatile unsigned long long* ll = S.ll_pose + tid;
       unsigned long long w;
-      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag) {}
+      CsSpin spin;
+      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag)
+        if (spin.expired(a, CS_STUCK_POSE)) { stuck = true; break; }
       sh_pose[tid] = __uint_as_float((unsigned)w);
       if (tl) tl[3] = cs_globaltimer();
     }
-    __syncthreads();
+    if (__syncthreads_or(stuck)) return;  // (bounded polls only: the pose never came)
     const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
     const float cs[2] = {sh_pose[3], sh_pose[4]};
     long long vis = 0;
@@ -1321,14 +1346,17 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ int sh_max_ring;
   __shared__ int sh_round_max[CS_RING_MAX_ROUNDS];  // largest dxc of the rays of round r: later rings skip the round
   if (MULTI && tid < CS_RING_MAX_ROUNDS) sh_round_max[tid] = -1;
+  bool rays_stuck = false;
   if (tid == 0) {
     sh_max_ring = -1;
     volatile unsigned long long* pw = prep_words + (size_t)copy * 16;
-    while (*pw != (unsigned long long)nprep) {}
+    CsSpin spin;
+    while (*pw != (unsigned long long)nprep)
+      if (spin.expired(a, CS_STUCK_RAYS)) { rays_stuck = true; break; }
     __threadfence();
     if (tl) tl[4] = cs_globaltimer();
   }
-  __syncthreads();
+  if (__syncthreads_or(rays_stuck)) return;  // (bounded polls only: the rays never came)
   // the pose words are final: the preparing blocks saw them before they counted themselves
   const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));
   const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
@@ -1600,7 +1628,8 @@ cs_rings_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
             st.last_pv = -1; st.fixed = false;
             if (pred[j] >= 0) {
               unsigned w;
-              do { w = *hand; } while ((w >> 16) != (unsigned)(pred[j] + 1));
+              CsSpin spin;  // (a give-up leaves the cell wrong; the handle is failed by the host, see CsSpin)
+              do { w = *hand; } while ((w >> 16) != (unsigned)(pred[j] + 1) && !spin.expired(a, CS_STUCK_HANDOFF));
               st.val = (int)(w & 0xffffu);
             } else {
               st.val = v[j];

@@ -720,13 +720,16 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     const int my_i = g_begin + tid;
     const bool in_range = my_warp && my_i < g_end;
     const float2 my_p = in_range ? __ldg(points + my_i) : make_float2(1.f, 0.f);  // in flight while the pose is awaited
+    bool stuck = false;
     if (tid < 5) {
       volatile unsigned long long* ll = S.ll_pose + tid;
       unsigned long long w;
-      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag) {}
+      CsSpin spin;
+      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag)
+        if (spin.expired(a, CS_STUCK_POSE)) { stuck = true; break; }
       sh_pose[tid] = __uint_as_float((unsigned)w);
     }
-    __syncthreads();
+    if (__syncthreads_or(stuck)) return;  // (bounded polls only: the pose never came)
     const float pose[3] = {sh_pose[0], sh_pose[1], sh_pose[2]};
     const float cs[2] = {sh_pose[3], sh_pose[4]};
     const CsRayFrame f = cs_ray_frame(S, pose, cs);
@@ -761,22 +764,26 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   bool have_rays = false;
   int x1 = 0, y1 = 0;
   long long t_prep = 0;
-  auto wait_rays = [&]() {  // (whole block)
+  auto wait_rays = [&]() -> bool {  // (whole block); false: the rays never came (bounded polls only)
+    bool stuck = false;
     if (tid == 0) {
       volatile unsigned long long* pw = S.prep_words + ((size_t)slot * copies + (cs_smid() % copies)) * 16;
-      while (*pw != (unsigned long long)nprep) {}
+      CsSpin spin;
+      while (*pw != (unsigned long long)nprep)
+        if (spin.expired(a, CS_STUCK_RAYS)) { stuck = true; break; }
       __threadfence();
     }
-    __syncthreads();
+    if (__syncthreads_or(stuck)) return false;
     have_rays = true;
     if (a.diag) t_prep = cs_globaltimer();
     const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));  // (final: the preparing blocks saw them)
     const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
     x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
     y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
+    return true;
   };
   if (a.w_prev < 0) {  // this scan's own counts: the table needs the rays first
-    wait_rays();
+    if (!wait_rays()) return;
     build_table();
   }
   const long long t_sched = a.diag ? cs_globaltimer() : 0;
@@ -858,7 +865,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       unsigned blo = 0u, bhi = 0u;
       const int stask = ticket + n_tickets * warp;
       const bool ok = ticket < n_tickets && stask < n_sub_tasks && decode(stask, ka, kb, blo, bhi);
-      if (!have_rays) wait_rays();
+      if (!have_rays && !wait_rays()) return;
       if (ticket == n_tickets) {  // (block-uniform branch: cs_w_center has barriers)
         cs_w_center<TILED>(S, map, n, x1, y1, size, pitch_tiles, alpha, s_center, s_flagged);
         continue;
@@ -872,7 +879,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   } else {
     // A big scan or a session of a batch (throughput): static round-robin over the warps of the session's blocks, consecutive
     // sub-tasks to different blocks, the blocks that prepared rays last; the centre to the block whose tasks come last.
-    if (!have_rays) wait_rays();
+    if (!have_rays && !wait_rays()) return;
     const int nblocks = (int)gridDim.x;
     int rb = (int)blockIdx.x - min(nprep, nblocks - 1);
     if (rb < 0) rb += nblocks;

@@ -330,3 +330,50 @@ def test_group_two_processes_peer_memory():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "SPLIT_OK" in out.stdout
+
+
+_BOUNDED_SPIN_CHILD = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import slam.net_b200 as sn
+from slam.net_b200 import _native as N, synth
+P, size, phys = 200, 256, 20.0
+rp = synth.make_replay(4, P, phys, seed=5)
+p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, 64, 1, max_points=P, flags=N.FLAG_DEBUG_BOUNDED_SPIN)
+try:
+    for k in range(4):
+        p.update(rp.points[k], rp.odometry[k], None)
+    p.sync()
+    p.map_download()
+    print("NO_ERROR")
+except sn.CoreSlamError as e:
+    print("ERROR:", e)
+"""
+
+
+def test_bounded_spin_turns_a_stuck_poll_into_an_error():
+    """CS_FLAG_DEBUG_BOUNDED_SPIN: with the fault knob the draw kernel waits for a pose tag nobody publishes; its polls must
+    give up (50 ms here), the grid must drain, and a later call on the handle must fail with CS_ERR_CUDA naming the poll —
+    not hang.  Child process: the library reads its knobs once."""
+    env = dict(os.environ, CS_TUNE_FAULT="1", CS_TUNE_SPIN_MS="50")
+    out = subprocess.run([sys.executable, "-c", _BOUNDED_SPIN_CHILD % {"root": ROOT}], capture_output=True, text=True, timeout=300,
+                         cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "ERROR:" in out.stdout and "CS_ERR_CUDA" in out.stdout and "bounded polls" in out.stdout, out.stdout
+
+
+def test_bounded_spin_flag_changes_no_result():
+    """The same replay with and without CS_FLAG_DEBUG_BOUNDED_SPIN: identical poses, distances and maps."""
+    from slam.net_b200 import _native as N
+    n_scans, P, size, phys, iters, threads = 12, 700, 512, 40.0, 256, 4
+    rp = synth.make_replay(n_scans, P, phys, seed=31)
+    a = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=4)
+    b = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=4, flags=N.FLAG_DEBUG_BOUNDED_SPIN)
+    for k in range(n_scans):
+        ra = a.update(rp.points[k], rp.odometry[k], None)
+        rb = b.update(rp.points[k], rp.odometry[k], None)
+        assert np.array_equal(ra.pose, rb.pose) and (ra.distance, ra.index) == (rb.distance, rb.index)
+    assert np.array_equal(a.map_download(), b.map_download())
+    a.close()
+    b.close()

@@ -1,5 +1,5 @@
 """Diagnostics: per-task timeline (%globaltimer stamps) of the wedge kernel for one Update.
-usage: python tools/wedge_probe.py [cfg2|cfg3|cfg1]"""
+usage: python tools/wedge_probe.py [cfg2|cfg3|cfg1|cfg4]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -7,7 +7,8 @@ import slam.net_b200 as sn
 from slam.net_b200 import synth
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-P, size, phys, iters, threads = {"cfg2": (1024, 2048, 40.0, 1024, 4), "cfg3": (8192, 4096, 40.96, 1, 1), "cfg1": (360, 1600, 40.0, 1000, 1)}[wl]
+P, size, phys, iters, threads = {"cfg2": (1024, 2048, 40.0, 1024, 4), "cfg3": (8192, 4096, 40.96, 1, 1), "cfg1": (360, 1600, 40.0, 1000, 1),
+                                   "cfg4": (1024, 8192, 81.92, 1024, 64)}[wl]
 n_scans = 12
 rp = synth.make_replay(n_scans, P, phys)
 p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P)
