@@ -37,7 +37,13 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """nvcc-compile the library in-tree for sm_100a (cross-compiles without a GPU)."""
+    """nvcc-compile the library in-tree for sm_100a (cross-compiles without a GPU).  CS_B200_LIB=<path> selects a library
+    built elsewhere (A/B runs of kernel variants on the GPU box) instead."""
+    override = os.environ.get("CS_B200_LIB")
+    if override and not force:
+        if not os.path.exists(override):
+            raise RuntimeError("CS_B200_LIB=%s does not exist" % override)
+        return override
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

@@ -76,6 +76,7 @@ struct cs_processor {
   int2* d_w_rk = nullptr;
   float2* d_w_bkey = nullptr;
   int* d_w_top = nullptr;
+  unsigned long long* d_spec = nullptr;  // glue table (CsStepArgs::spec): 8 words per flat candidate
   int w_slot = 0;
   long long* d_ring_cycles = nullptr;
   unsigned long long* d_checksum = nullptr;
@@ -314,7 +315,7 @@ struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
   int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0, w_carveout = 0, s2_carveout = 0;
-  int spin_ms = 0, fault = 0;
+  int spin_ms = 0, fault = 0, w_resident = 0, spec = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -331,6 +332,8 @@ struct Tune {
     w_carveout = geti("CS_TUNE_W_CARVEOUT");    // shared-memory carve-out (percent) of the wedge kernel
     s2_carveout = geti("CS_TUNE_S2_CARVEOUT");  // ... of the slab-search and sort kernels
     w_prev = geti("CS_TUNE_W_PREV");            // -1: every scan builds its task table from its own counts
+    w_resident = geti("CS_TUNE_W_RESIDENT");    // 4: one small scan alone also runs the four-blocks-per-SM instance of the wedge kernel
+    spec = geti("CS_TUNE_SPEC");                // -1: no glue table (the publishing thread always computes the glue itself)
     w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
     spin_ms = geti("CS_TUNE_SPIN_MS");          // CS_FLAG_DEBUG_BOUNDED_SPIN: milliseconds a device-side poll lasts (default 2000)
     fault = geti("CS_TUNE_FAULT");              // tests of the bounded polls: 1 = the draw kernel waits for a pose tag nobody publishes
@@ -348,8 +351,10 @@ cudaError_t wedge_allow_shared_memory() {
   // kernel whose carve-out differs from its predecessor's cannot share an SM with it.
   cudaError_t e = cudaSuccess;
   if (tune().w_carveout > 0) {
-    e = cudaFuncSetAttribute(cs_wedge_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+    e = cudaFuncSetAttribute(cs_wedge_kernel<true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<true, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(cs_wedge_kernel<false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().w_carveout);
   }
   if (e == cudaSuccess && tune().s2_carveout > 0) {
     e = cudaFuncSetAttribute(cs_search2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, tune().s2_carveout);
@@ -407,18 +412,19 @@ int cs_s2_min_cand(uint32_t flags, int n_sessions = 1) {  // fewest candidates (
   // a batch fills the machine with its sessions; what the slabs need is enough candidates to amortise a block's set-up
   return n_sessions > 1 ? kS2MinCandBatch : kS2MinCand;
 }
-bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_count, int n_points, int num_sms, S2Plan* p) {
+bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_count, int n_points, int num_sms, S2Plan* p,
+                     int max_threads = CS_S2_MAX_THREADS) {
   if (min_cand <= 0 || n_sessions < 1 || s2_cap <= 0 || cand_count > s2_cap || n_points < 1) return false;
   if (cand_count < min_cand) return false;
   if (n_sessions > 1 && (cand_count > CS_SORT_THREADS * CS_SORT_REG || n_sessions > 65535)) return false;  // batches: one sort block per session
   // the plan depends on (candidates, points, SMs) only: remember the last one (a replay asks for the same every scan)
-  struct Memo { long long cand = -1; int points = -1, sms = -1, sessions = -1; bool ok = false; S2Plan plan; };
+  struct Memo { long long cand = -1; int points = -1, sms = -1, sessions = -1, max_threads = -1; bool ok = false; S2Plan plan; };
   static thread_local Memo memo;
-  if (memo.cand == cand_count && memo.points == n_points && memo.sms == num_sms && memo.sessions == n_sessions) {
+  if (memo.cand == cand_count && memo.points == n_points && memo.sms == num_sms && memo.sessions == n_sessions && memo.max_threads == max_threads) {
     *p = memo.plan;
     return memo.ok;
   }
-  memo.cand = cand_count; memo.points = n_points; memo.sms = num_sms; memo.sessions = n_sessions; memo.ok = false;
+  memo.cand = cand_count; memo.points = n_points; memo.sms = num_sms; memo.sessions = n_sessions; memo.max_threads = max_threads; memo.ok = false;
   // Launch shape: the kernel is one resident wave of blocks (clusters x slabs) and ends when the busiest SM ends.  A lane
   // pays a fixed set-up (candidate pose, cos/sin: ~kSetup instruction slots) plus ~kLookup per point of its cluster, in
   // whole batches of CS_S2_BATCH; a block's cost is that times its warps, and an SM issues about kIpcPerWarp
@@ -429,7 +435,7 @@ bool cs_plan_search2(int n_sessions, int s2_cap, int min_cand, long long cand_co
   const int p_lo = tune().s2_points > 0 ? tune().s2_points : CS_S2_BATCH;
   const int p_hi = tune().s2_points > 0 ? tune().s2_points : CS_S2_MAX_POINTS;
   const int t_lo = tune().s2_threads > 0 ? (tune().s2_threads + 31) / 32 * 32 : 64;
-  const int t_hi = tune().s2_threads > 0 ? (t_lo < CS_S2_MAX_THREADS ? t_lo : CS_S2_MAX_THREADS) : CS_S2_MAX_THREADS;
+  const int t_hi = tune().s2_threads > 0 ? (t_lo < max_threads ? t_lo : max_threads) : max_threads;
   for (int points = p_lo; points <= p_hi && points <= CS_S2_MAX_POINTS; points += 4) {
     const long long clusters = (n_points + points - 1) / points;
     if (clusters > CS_S2_MAX_CLUSTERS) continue;
@@ -476,6 +482,7 @@ struct LaunchCtx {
   long long* diag;
   int diag_rings;
   volatile unsigned* stuck_dev = nullptr;  // CS_FLAG_DEBUG_BOUNDED_SPIN: device address of the mapped-host word (CsSpin)
+  unsigned long long* spec = nullptr;      // glue table of the handle (one session alone)
   cudaEvent_t ev_pose;   // optional: recorded once the pose is out
   cudaEvent_t ev_done;   // optional: recorded after the rings kernel
 };
@@ -527,6 +534,7 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   a.w_prefetch = 0;  // the map around the pose goes to L2 ahead of its use (one session alone; batches hide the latency)
   a.diag = c.diag;
   a.diag_rings = c.diag_rings;
+  a.spec = (tune().spec >= 0 && fused && draws && a.step_mode == CS_STEP_UPDATE) ? c.spec : nullptr;
   a.stuck_flag = c.stuck_dev;
   a.spin_ns = c.stuck_dev ? (long long)(tune().spin_ms > 0 ? tune().spin_ms : 2000) * 1000000ll : 0;
   if (phases & CS_PHASE_FINISH) {  // a call that publishes a pose takes the next step id: never 0, alternating parity
@@ -536,7 +544,8 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   cudaError_t e = cudaSuccess;
   S2Plan s2;
   if ((phases & CS_PHASE_SEARCH) && searching &&
-      cs_plan_search2(c.n_sessions, c.s2_cap, c.s2_min_cand, a.cand_count, a.s2_host_points, c.num_sms, &s2)) {
+      cs_plan_search2(c.n_sessions, c.s2_cap, c.s2_min_cand, a.cand_count, a.s2_host_points, c.num_sms, &s2,
+                      a.spec ? CS_S2_MAX_THREADS - 32 : CS_S2_MAX_THREADS)) {  // (the glue table's service warp rides along)
     a.s2_points = s2.points;
     a.s2_slab = s2.threads;
     a.s2_slot = (*c.s2_toggle ^= 1);
@@ -576,11 +585,12 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     }
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_search2_kernel<decltype(T)::value>, dim3((unsigned)s2.clusters, (unsigned)s2.slabs, (unsigned)c.n_sessions),
-                     dim3(s2.threads), 0, c.stream, c.d_sess, a);
+                     dim3(s2.threads + (a.spec ? 32 : 0)), 0, c.stream, c.d_sess, a);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
   } else if ((phases & CS_PHASE_SEARCH) && searching) {
+    a.spec = nullptr;  // (the glue table is filled by the slab search's service warps)
     const int warps = cs_search_warps(a.cand_count, c.n_sessions, c.num_sms);
     dim3 grid((unsigned)((a.cand_count + warps - 1) / warps), (unsigned)c.n_sessions);
     int chunk = (n_points + 1) & ~1;  // even: the staging loop moves two points per 16-byte load
@@ -612,7 +622,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (group > CS_W_THREADS) group = CS_W_THREADS;  // one ray per thread of a preparing block
     a.prep_group = group;
     const int nprep = (n_points + group - 1) / group;
-    int blocks = c.n_sessions == 1 ? 4 * c.num_sms : 4;
+    // (one small scan alone: the 80-register instance, three blocks per SM; see cs_wedge_kernel)
+    const bool latency = c.n_sessions == 1 && n_points <= 2048 && tune().w_resident != 4;
+    int blocks = c.n_sessions == 1 ? (latency ? 3 : 4) * c.num_sms : 4;
     if (tune().w_blocks > 0) blocks = tune().w_blocks;
     if (blocks < nprep) blocks = nprep;
     // A rank of a candidate-split group that shares its device with another rank (several handles of one process on one GPU)
@@ -631,12 +643,15 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     }
     a.w_general = tune().w_general > 0 ? 1 : 0;
     if (a.w_prefetch == 0 && c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0) a.w_prefetch = 2;
+    // (Measured and left as an experiment knob, CS_TUNE_W_PREFETCH=3: in batches, the preparing thread of a ray prefetching the
+    // tiles along it — cfg5 2.01 -> 2.08 ms per step: the draw tasks of a batch already keep the memory system busy.)
+    if (c.n_sessions > 1 && c.tiled && tune().w_prefetch == 3) a.w_prefetch = 3;
     a.w_sub_max = tune().w_sub;
     CsStepArgs draw_args = a;
     if (tune().fault == 1 && c.stuck_dev) draw_args.step_id ^= 0x40000000u;  // (fault injection: a pose tag nobody publishes)
     dispatch_layout(c.tiled, [&](auto T) {
-      e = launch_pdl(cs_wedge_kernel<decltype(T)::value>, dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS),
-                     wedge_smem(c.hs->size), c.stream, c.d_sess, draw_args);
+      e = launch_pdl(latency ? cs_wedge_kernel<decltype(T)::value, 3> : cs_wedge_kernel<decltype(T)::value, 4>,
+                     dim3((unsigned)blocks, (unsigned)c.n_sessions), dim3(CS_W_THREADS), wedge_smem(c.hs->size), c.stream, c.d_sess, draw_args);
     });
     if (e != cudaSuccess) return e;
     (*c.launches)++;
@@ -723,6 +738,7 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.s2_min_cand = cs_s2_min_cand(h->cfg.flags);
   c.s2_toggle = &h->s2_toggle;
   c.hs = &h->hs;
+  c.spec = h->d_spec;
   if (h->cfg.flags & CS_FLAG_DEBUG_BOUNDED_SPIN) c.stuck_dev = reinterpret_cast<volatile unsigned*>(h->d_slot + 96);
   a.hdr_stride = 1;
   const bool want_pose_event = timing || (a.seq_flag && (h->cfg.flags & CS_FLAG_NO_HOST_SPIN));
@@ -894,6 +910,8 @@ cs_status cs_create(const cs_config* cfg, cs_processor** out) {
   CS_CREATE_CUDA(cudaMalloc(&h->d_w_top, (size_t)3 * wedge_top_words(h->size) * sizeof(int)));
   CS_CREATE_CUDA(cudaMemset(h->d_w_top, 0, (size_t)3 * wedge_top_words(h->size) * sizeof(int)));
   CS_CREATE_CUDA(wedge_allow_shared_memory());
+  CS_CREATE_CUDA(cudaMalloc(&h->d_spec, ((size_t)n_cand + 1) * 8 * sizeof(unsigned long long)));
+  CS_CREATE_CUDA(cudaMemset(h->d_spec, 0, ((size_t)n_cand + 1) * 8 * sizeof(unsigned long long)));  // (tag 0 is never a step's)
   CS_CREATE_CUDA(cudaMalloc(&h->d_distances, ((size_t)n_cand + 1) * sizeof(int)));
   CS_CREATE_CUDA(cudaMalloc(&h->d_checksum, sizeof(unsigned long long)));
   if (cs_s2_min_cand(cfg->flags) > 0 && n_cand + 1 >= cs_s2_min_cand(cfg->flags)) {
@@ -1017,6 +1035,7 @@ cs_status cs_destroy(cs_processor* h) {
   cudaFree(h->d_w_rk);
   cudaFree(h->d_w_bkey);
   cudaFree(h->d_w_top);
+  cudaFree(h->d_spec);
   cudaFree(h->d_distances);
   cudaFree(h->d_ring_cycles);
   cudaFree(h->d_checksum);

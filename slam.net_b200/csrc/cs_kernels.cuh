@@ -179,6 +179,14 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   // candidate split over a group of GPUs with the arg-min exchanged inside the search kernel (cs_group_attach): rank r's
   // table holds, per half (exchange number & 1) and rank, two words {packed key, tag}; every rank writes its key into every
   // table over peer-mapped memory and waits for the world's keys in its own
+  // glue table (one session alone, slab search): entry idx = the pose and (cos, sin) an UPDATE step ends on if flat candidate
+  // idx wins, as five words {step tag << 32 | float bits} (the format of CsSession::ll_pose) in a 64-byte slot.  Every block
+  // of the slab search carries one extra warp that looks nothing up: at the start of the kernel it writes the entries of its
+  // share of the slab's candidates.  The publishing thread then copies the winner's entry instead of running the glue
+  // arithmetic (candidate pose, NormalizeAngle, cos, sin: ~1000 dependent instructions of cold code) at the very end of the
+  // step's critical path.  An entry whose tags are not this step's is ignored and the glue computed as before (the winner
+  // of a candidate-split group may be another rank's candidate): nothing depends on timing.
+  unsigned long long* spec;      // nullptr: no table
   int xchg_world;                // 0 / 1: no exchange
   int xchg_rank;
   unsigned xchg_seq;             // exchange number, the same on every rank
@@ -450,17 +458,8 @@ __device__ __forceinline__ void cs_glue_pose(CsSession& S, const CsStepHeader& h
 // side effects: processor state, arg-min re-arm, result record + flag, session scratch for the integration
 __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a,
                                                 CsDevResult* result, const CsGlue& g, long long* d = nullptr) {
-  if (a.step_mode == CS_STEP_UPDATE) {
-    const CsState& st0 = S.state[a.parity];
-    CsState& st1 = S.state[a.parity ^ 1];
-    st1.pose[0] = g.pose[0]; st1.pose[1] = g.pose[1]; st1.pose[2] = g.pose[2];                   // :747
-    st1.last_odo[0] = hdr.odo[0]; st1.last_odo[1] = hdr.odo[1]; st1.last_odo[2] = hdr.odo[2];   // :745
-    st1.scan_count = st0.scan_count + (a.do_search ? 0 : 1);                                     // :741
-    S.key[a.parity ^ 1] = ~0ull;  // arm the next step's arg-min
-  } else if (a.step_mode == CS_STEP_SEARCH_ONLY) {
-    S.key[a.parity] = ~0ull;  // re-arm in place
-  }
-  // device-side consumers first: the rings kernel of this step is already resident and polls these words
+  // device-side consumers first: the draw kernel of this step is already resident and polls these words (nothing it reads
+  // besides them is written below; the state is for the next step, which a kernel boundary orders behind this one)
   {
     const unsigned long long tag = (unsigned long long)a.step_id << 32;
     volatile unsigned long long* ll = S.ll_pose;
@@ -471,6 +470,16 @@ __device__ __forceinline__ void cs_glue_publish(CsSession& S, const CsStepHeader
     ll[4] = tag | __float_as_uint(g.cs[1]);
   }
   if (d) d[2] = cs_globaltimer();
+  if (a.step_mode == CS_STEP_UPDATE) {
+    const CsState& st0 = S.state[a.parity];
+    CsState& st1 = S.state[a.parity ^ 1];
+    st1.pose[0] = g.pose[0]; st1.pose[1] = g.pose[1]; st1.pose[2] = g.pose[2];                   // :747
+    st1.last_odo[0] = hdr.odo[0]; st1.last_odo[1] = hdr.odo[1]; st1.last_odo[2] = hdr.odo[2];   // :745
+    st1.scan_count = st0.scan_count + (a.do_search ? 0 : 1);                                     // :741
+    S.key[a.parity ^ 1] = ~0ull;  // arm the next step's arg-min
+  } else if (a.step_mode == CS_STEP_SEARCH_ONLY) {
+    S.key[a.parity] = ~0ull;  // re-arm in place
+  }
   S.cur_pose[0] = g.pose[0]; S.cur_pose[1] = g.pose[1]; S.cur_pose[2] = g.pose[2];
   S.cur_cs[0] = g.cs[0]; S.cur_cs[1] = g.cs[1];
   // re-arm the NEXT step's counters (kernel boundaries order this before that step's rings kernel; this step's
@@ -596,13 +605,42 @@ __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr
   long long* d = a.diag ? a.diag + ((size_t)a.diag_rings + CS_DIAG_SEARCH_BLOCKS - 1) * 8 : nullptr;  // (diagnostics: one session)
   if (d) d[0] = cs_globaltimer();
   const bool need_key = a.step_mode != CS_STEP_INTEGRATE_ONLY && a.do_search;
+  // the winner's entry of the glue table (see CsStepArgs::spec): fetched for the arg-min as this thread last saw it — almost
+  // always the final one — together with the read of the final key, and again only if the two differ
+  const bool use_table = a.spec && need_key && a.step_mode == CS_STEP_UPDATE;
+  unsigned long long w[5] = {0ull, 0ull, 0ull, 0ull, 0ull};
+  unsigned widx = 0xffffffffu;
+  if (use_table && have_guess) {
+    widx = (unsigned)(guess & 0xffffffffull);
+    const unsigned long long* e = a.spec + (size_t)widx * 8;
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = __ldcg(e + i);
+  }
   unsigned long long key = 0ull;
   if (need_key) key = a.empty_cloud ? (0x7fffffffull << 32) : atomicAdd(&S.key[a.parity], 0ull);  // L2 read: sees every block's atomicMin
   bool timed_out = false;
   const bool exchange = need_key && a.xchg_world > 1 && !a.empty_cloud;
   if (exchange) key = cs_exchange_min(a, key, timed_out);
   CsGlue g;
-  if (have_guess && need_key && !exchange) {
+  bool from_table = false;
+  if (use_table) {
+    if ((unsigned)(key & 0xffffffffull) != widx) {
+      const unsigned long long* e = a.spec + (size_t)(unsigned)(key & 0xffffffffull) * 8;
+#pragma unroll
+      for (int i = 0; i < 5; i++) w[i] = __ldcg(e + i);
+    }
+    const unsigned long long tag = (unsigned long long)a.step_id << 32;
+    from_table = true;
+#pragma unroll
+    for (int i = 0; i < 5; i++) from_table = from_table && (w[i] & 0xffffffff00000000ull) == tag;
+    if (from_table) {
+      g.pose[0] = __uint_as_float((unsigned)w[0]); g.pose[1] = __uint_as_float((unsigned)w[1]); g.pose[2] = __uint_as_float((unsigned)w[2]);
+      g.cs[0] = __uint_as_float((unsigned)w[3]); g.cs[1] = __uint_as_float((unsigned)w[4]);
+      g.dist = (int)(unsigned)(key >> 32); g.index = (int)(unsigned)(key & 0xffffffffu); g.searched = 1;
+    }
+  }
+  if (from_table) {
+  } else if (have_guess && need_key && !exchange) {
     // The arg-min as this thread last saw it is almost always the final one: the glue arithmetic runs on it while
     // the read above is in flight, and is redone only if the final key differs.
     cs_glue_pose(S, hdr, a, cand, guess, g);
@@ -610,7 +648,7 @@ __device__ __forceinline__ void cs_publish(CsSession& S, const CsStepHeader& hdr
   } else {
     cs_glue_pose(S, hdr, a, cand, key, g);
   }
-  if (d) d[1] = cs_globaltimer();
+  if (d) { d[1] = cs_globaltimer(); d[4] = from_table ? 1 : 0; }
   if (timed_out) g.searched = -1;  // the host turns this into CS_ERR_NCCL: a rank of the group never delivered its key
   cs_glue_publish(S, hdr, a, result, g, d);
   if (d) d[3] = cs_globaltimer();
@@ -1029,7 +1067,7 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   unsigned long long* __restrict__ acc = a.s2_batch ? S.s2_acc : a.s2_acc;
   int* const distances = S.distances;
   const int pos = slab * a.s2_slab + tid;  // position in the sorted order
-  const bool valid = pos < a.cand_count;
+  const bool valid = tid < a.s2_slab && pos < a.cand_count;  // (threads beyond the slab: the service warp, see below)
 
   long long* tl = nullptr;  // timeline record of this block (diagnostics)
   if (a.diag && tid == 0 && (int)(blockIdx.y * gridDim.x + blockIdx.x) < CS_DIAG_SEARCH_BLOCKS - 2) {
@@ -1070,6 +1108,31 @@ cs_search2_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     s = __fmul_rn(st, scale);                         // :235
   }
   __syncthreads();  // s_pts
+  if (a.spec && tid >= a.s2_slab) {
+    // ---- the service warp: glue-table entries (CsStepArgs::spec) of this block's share of the slab's candidates — one in
+    // n_clusters, the blocks of a slab between them cover it — while the other warps look up
+    const unsigned long long tag = (unsigned long long)a.step_id << 32;
+    float sp[3];
+    cs_search_pose(S, hdr, a, sp);
+    for (int q = cluster + lane * (int)n_clusters; q < a.s2_slab; q += 32 * (int)n_clusters) {
+      const int p = slab * a.s2_slab + q;
+      if (p >= a.cand_count) break;
+      const float4 e = __ldcg(sorted + p);
+      const int ei = __float_as_int(e.w);
+      float pz[3];
+      if (ei == 0) { pz[0] = sp[0]; pz[1] = sp[1]; pz[2] = sp[2]; }
+      else if (a.cand_mode == CS_CAND_ABSOLUTE) { pz[0] = e.x; pz[1] = e.y; pz[2] = e.z; }
+      else { pz[0] = __fadd_rn(sp[0], e.x); pz[1] = __fadd_rn(sp[1], e.y); pz[2] = __fadd_rn(sp[2], e.z); }  // :635-637
+      pz[2] = cs_normalize_angle(pz[2]);  // :746 (the table is only used by UPDATE steps)
+      unsigned long long* w = a.spec + (size_t)ei * 8;
+      __stcg(w + 0, tag | __float_as_uint(pz[0]));
+      __stcg(w + 1, tag | __float_as_uint(pz[1]));
+      __stcg(w + 2, tag | __float_as_uint(pz[2]));
+      __stcg(w + 3, tag | __float_as_uint(cs_cosf(pz[2])));
+      __stcg(w + 4, tag | __float_as_uint(cs_sinf(pz[2])));
+    }
+    return;
+  }
   const unsigned act = __ballot_sync(0xffffffffu, valid);  // lanes of this warp that own a candidate
   if (!valid) return;
 

@@ -31,7 +31,8 @@
 #define CS_W_LEVELS 264   // rings [1,1] [2,3] [4,7] [8,15] [16,31] [32,63], then 64 rings each: ring 16383 is level 260
 #define CS_W_FIX 14       // wedge boundaries are multiples of 2^-14 (keys span [0, 8])
 #define CS_W_CAP 256      // cells of a wedge staged per pass of the general path
-#define CS_W_G 4          // rings in flight per lane on the fast path
+#define CS_W_G 4            // rings in flight per lane on the fast path
+#define CS_W_H 4            // ... handled in parts of this many (cs_w_fast_group)
 #define CS_W_MAX_WEDGES 8192
 #define CS_W_SECTORS 64   // key sectors of width 1/8: the rays that reach a level are counted per sector, and each sector is
                           // cut into wedges of its own (long rays cluster in a few directions: a uniform cut would leave some
@@ -76,6 +77,7 @@ struct CsWPrepared {
   float key;
   int dxc;     // -1: the ray draws nothing
   int bm;      // largest dxc of the warp's rays
+  int dyc, flags;  // (of the ray, for cs_w_prefetch_ray)
 };
 __device__ __forceinline__ CsWPrepared cs_w_prepare(CsSession& S, const CsRayFrame& f, const float2 p, int i, bool in_range,
                                                     long long& visits) {
@@ -107,7 +109,27 @@ __device__ __forceinline__ CsWPrepared cs_w_prepare(CsSession& S, const CsRayFra
   }
   CsWPrepared out;
   out.key = key; out.dxc = valid ? r.dxc : -1; out.bm = bm;
+  out.dyc = r.dyc; out.flags = r.flags;
   return out;
+}
+
+// The tiles a ray crosses, to L2 (tiled maps): one prefetch per 8 major steps.  Run by the ray's preparing thread right after the
+// rays are announced, in batches of sessions — there every session's map comes from HBM (the maps of a batch are many times
+// the L2), and the draw tasks, which start a few microseconds later, otherwise pay the DRAM latency once per group of rings.
+__device__ __forceinline__ void cs_w_prefetch_ray(const uint16_t* __restrict__ map, const CsWPrepared& q, int x1, int y1, int size,
+                                                  int pitch_tiles) {
+  if (q.dxc < 1) return;
+  const bool steep = (q.flags & 2) != 0;
+  const int smaj = (q.flags & 4) ? -1 : 1, smin = (q.flags & 8) ? -1 : 1;
+  const float slope = (float)min(q.dyc, q.dxc) / (float)q.dxc;
+  for (int t = 4; t <= q.dxc; t += 8) {
+    const int m = (int)(slope * (float)t + 0.5f);
+    const int x = x1 + (steep ? smin * m : smaj * t), y = y1 + (steep ? smaj * t : smin * m);
+    if ((unsigned)x < (unsigned)size && (unsigned)y < (unsigned)size) {
+      const uint16_t* line = map + ((size_t)(y >> 3) * pitch_tiles + (x >> 3)) * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+  }
 }
 
 // Counts for sizing the wedges: per level the rays that reach it, in all and per key sector.  The lanes of a sector add as
@@ -447,82 +469,117 @@ __device__ void cs_w_general(const CsSession& S, uint16_t* __restrict__ map, con
   }
 }
 
+// match.any among the lanes of `mask` (exactly the lanes with `on`); 0 for the others.  Predicated instead of branched: the
+// intrinsic inside an `if` compiles to a branch around every match with the result copied right behind it, which serialises
+// the matches of consecutive rings on their ~40-cycle latency.
+__device__ __forceinline__ unsigned cs_match_any_if(bool on, unsigned mask, unsigned key) {
+  unsigned r = 0u;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p match.any.sync.b32 %0, %1, %2;\n\t}" : "+r"(r) : "r"(key), "r"(mask), "r"((unsigned)on));
+  return r;
+}
+
 // ---- fast path: at most 32 candidates (s_list, in ray order), one per lane; rings four at a time so that four map loads per
-// lane are in flight; visits of one cell inside the warp are found with match.any and applied by the lowest lane in lane order
-template <bool TILED>
-__device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const CsWTask& t, int ncand, const int* s_list, int x1, int y1,
-                          int size, int pitch_tiles, int alpha) {
+// lane are in flight; visits of one cell inside the warp are found with match.any and applied by the lowest lane in lane order.
+// One group of CS_W_G rings.  FREE: no lane is inside its hole profile on these rings (k < a0 for every ray, decided by the
+// caller with one vote): every visit carries the free-space pixval, which is then a constant — no pixval evaluation, and
+// same-cell visits are a count.
+template <bool TILED, bool FREE>
+__device__ __forceinline__ void cs_w_fast_group(uint16_t* __restrict__ map, CsWWalk& w, const CsWTask& t, int kb, int last, unsigned& accl,
+                                                unsigned& acch, int size, int pitch_tiles, int alpha) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  CsRay r;
-  r.dxc = -1; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
-  if (lane < ncand) r = cs_unpack_ray(S.rays[s_list[lane]]);
-  CsWWalk w;
-  w.init(r, lane < ncand, t.k0 - 1, x1, y1);
-  const int last = min(w.dxc, t.k1);  // this lane's last ring in the task (-1: none)
-  unsigned accl = (unsigned)(t.k0 - 1) * t.blo, acch = (unsigned)(t.k0 - 1) * t.bhi;
-
-  for (int kb = t.k0; kb <= t.k1; kb += CS_W_G) {
-    uint32_t cell[CS_W_G];
-    int pv[CS_W_G], val[CS_W_G];
-    unsigned grp[CS_W_G];
-    unsigned leadbits = 0u, cfbits = 0u, freebits = 0u;
+  uint32_t cell[CS_W_G];
+  int pv[CS_W_G], val[CS_W_G];
+  unsigned grp[CS_W_G], act[CS_W_G];
+  unsigned inwbits = 0u, leadbits = 0u, cfbits = 0u, freebits = 0u;
+  // (In halves of CS_W_H rings, three passes each: the walk and the ownership test, then the match.any of the half back to
+  // back — ~40 cycles each, and the intrinsic inside a branch would be serialised by the copy the compiler puts behind it:
+  // hence all lanes take part, the lanes that do not visit with a key no cell has — then the leaders' map loads.  The second
+  // half's arithmetic runs under the first half's loads.)
 #pragma unroll
-    for (int j = 0; j < CS_W_G; j++) {
+  for (int h = 0; h < CS_W_G; h += CS_W_H) {
+#pragma unroll
+    for (int j = h; j < h + CS_W_H; j++) {
       const int k = kb + j;  // (warp-uniform)
       w.step();
       accl += t.blo; acch += t.bhi;
       const int lo = (int)((accl + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX), hi = (int)((acch + ((1u << CS_W_FIX) - 1u)) >> CS_W_FIX);
       const int posn = (w.pos == 8 * k) ? 0 : w.pos;
       const bool inw = k <= last && posn >= lo && posn < hi && (unsigned)w.x < (unsigned)size && (unsigned)w.y < (unsigned)size;
-      pv[j] = w.pixval();
-      cell[j] = cs_cell_offset<TILED>(w.x, w.y, size, pitch_tiles);
-      grp[j] = 0u;
-      val[j] = 0;
-      const unsigned act = __ballot_sync(full, inw);
-      if (act) {  // (match.any among the visiting lanes only: its cost grows with the number of distinct keys)
-        bool lead = false;
-        if (inw) {
-          grp[j] = __match_any_sync(act, posn);
-          lead = (grp[j] & lt_mask) == 0u;
-          if (lead) val[j] = (int)__ldcg(map + cell[j]);
-        }
-        if (lead) leadbits |= 1u << j;
-        if (__any_sync(full, inw && !lead)) {  // some cell of this ring has several visitors in this warp
-          cfbits |= 1u << j;
-          if (!__any_sync(full, inw && pv[j] != CS_TS_NO_OBSTACLE)) freebits |= 1u << j;  // ... all in free space
-        }
-      }
+      pv[j] = FREE ? CS_TS_NO_OBSTACLE : w.pixval();
+      cell[j] = cs_cell_offset<TILED>(w.x, w.y, size, pitch_tiles);  // (one value per cell of the map: the key of the match)
+      if (inw) inwbits |= 1u << j;
+      act[j] = __ballot_sync(full, inw);
     }
 #pragma unroll
-    for (int j = 0; j < CS_W_G; j++) {
-      const bool lead = (leadbits >> j) & 1u;
-      int v = cs_blend(val[j], pv[j], alpha);
-      if ((freebits >> j) & 1u) {  // warp-uniform: one pixval everywhere — blends of one value commute: a count per cell
-        int more = lead ? __popc(grp[j]) - 1 : 0;
-        while (more-- > 0) {
-          const int nv = cs_blend(v, CS_TS_NO_OBSTACLE, alpha);
-          if (nv == v) break;  // fixed point of this pixval (exact)
-          v = nv;
-        }
-      } else if ((cfbits >> j) & 1u) {  // warp-uniform
-        unsigned rest = lead ? (grp[j] & ~(1u << lane)) : 0u;
-        while (__any_sync(full, rest != 0u)) {
-          const int src = rest ? __ffs(rest) - 1 : lane;
-          const int pvj = __shfl_sync(full, pv[j], src);
-          if (rest) { v = cs_blend(v, pvj, alpha); rest &= rest - 1; }
-        }
+    for (int j = h; j < h + CS_W_H; j++)
+      grp[j] = __match_any_sync(full, ((inwbits >> j) & 1u) ? cell[j] : 0xffffffffu);
+#pragma unroll
+    for (int j = h; j < h + CS_W_H; j++) {
+      const bool inw = (inwbits >> j) & 1u;
+      const bool lead = inw && (grp[j] & lt_mask) == 0u;
+      val[j] = 0;
+      if (lead) { val[j] = (int)__ldcg(map + cell[j]); leadbits |= 1u << j; }
+      if (act[j] != 0u && __any_sync(full, inw && !lead)) {  // some cell of this ring has several visitors in this warp
+        cfbits |= 1u << j;
+        if (FREE || !__any_sync(full, inw && pv[j] != CS_TS_NO_OBSTACLE)) freebits |= 1u << j;  // ... all in free space
       }
-      if (lead) __stcg(map + cell[j], (uint16_t)v);
     }
+  }
+#pragma unroll
+  for (int j = 0; j < CS_W_G; j++) {
+    const bool lead = (leadbits >> j) & 1u;
+    int v = cs_blend(val[j], pv[j], alpha);
+    if ((freebits >> j) & 1u) {  // warp-uniform: one pixval everywhere — blends of one value commute: a count per cell
+      int more = lead ? __popc(grp[j]) - 1 : 0;
+      while (more-- > 0) {
+        const int nv = cs_blend(v, CS_TS_NO_OBSTACLE, alpha);
+        if (nv == v) break;  // fixed point of this pixval (exact)
+        v = nv;
+      }
+    } else if (!FREE && ((cfbits >> j) & 1u)) {  // warp-uniform: every leader fetches its members' pixvals in lane (= ray) order
+      unsigned rest = lead ? (grp[j] & ~(1u << lane)) : 0u;
+      const int apv = alpha * pv[j];  // (the member's half of the blend :431, so that the leader's chain is one multiply-add)
+      for (int turns = __reduce_max_sync(full, __popc(rest)); turns > 0; turns--) {
+        const int apvj = __shfl_sync(full, apv, __ffs(rest) - 1);  // (rest == 0: lane 31's, unused)
+        if (rest) { v = (int)(uint16_t)(((256 - alpha) * v + apvj) >> 8); rest &= rest - 1; }
+      }
+    }
+    if (lead) __stcg(map + cell[j], (uint16_t)v);
+  }
+}
+
+template <bool TILED>
+__device__ void cs_w_fast(const CsSession& S, uint16_t* __restrict__ map, const CsWTask& t, int ncand, const int* s_list,
+                          const int4* s_rays /* the candidates' rays, already fetched by the filter; or nullptr */, int x1, int y1,
+                          int size, int pitch_tiles, int alpha) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  CsRay r;
+  r.dxc = -1; r.dyc = 0; r.a0 = 0; r.b0 = -1; r.incv = 0; r.kc = 0; r.nd_total = 0; r.flags = 0;
+  if (lane < ncand) r = cs_unpack_ray(s_rays ? s_rays[lane] : S.rays[s_list[lane]]);
+  CsWWalk w;
+  w.init(r, lane < ncand, t.k0 - 1, x1, y1);
+  const int last = min(w.dxc, t.k1);  // this lane's last ring in the task (-1: none)
+  unsigned accl = (unsigned)(t.k0 - 1) * t.blo, acch = (unsigned)(t.k0 - 1) * t.bhi;
+
+  for (int kb = t.k0; kb <= t.k1; kb += CS_W_G) {
+    const bool hot = kb <= last && kb + CS_W_G - 1 >= w.a0;  // this lane's hole profile (:402-428) starts at ring a0
+    if (!__any_sync(full, hot))
+      cs_w_fast_group<TILED, true>(map, w, t, kb, last, accl, acch, size, pitch_tiles, alpha);
+    else
+      cs_w_fast_group<TILED, false>(map, w, t, kb, last, accl, acch, size, pitch_tiles, alpha);
   }
 }
 
 // Runs one task — rings ka .. kb of a level whose first ring is k0 (the wedge was sized for k0; the margins follow ka): while
 // the wedge holds more candidates than a warp has lanes it is cut in halves (left part first) as long as halving can help
 // (the wedge is wider than its margins); what cannot be cut takes the general path.
-template <bool TILED>
+// PRELOAD: the filter fetches every ray it looks at together with its (key, dxc) and parks the candidates' rays in shared
+// memory (the general path's cell staging, idle on the fast path): one trip to L2 less in front of the first ring, for the
+// price of fetching the rays of the non-candidates of the batches looked at — the latency instance of the kernel does it.
+template <bool TILED, bool PRELOAD>
 __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka, int kb, unsigned blo, unsigned bhi, int n, int x1,
                          int y1, int size, int pitch_tiles, int alpha, int force_general, unsigned* s_val, uint32_t* s_cell, int* s_list,
                          unsigned* s_bmap, long long* tl) {
@@ -549,18 +606,29 @@ __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka,
       nw = cs_w_batch_map(S, t, n, s_bmap);
       int b = cs_w_next_batch(s_bmap, nw, 0);
       int2 rk_next = make_int2(0, -1);
-      if (b >= 0 && b * 32 + lane < n) rk_next = S.w_rk[b * 32 + lane];
+      int4 ray_next = make_int4(0, 0, 0, 0);
+      if (b >= 0 && b * 32 + lane < n) {
+        rk_next = S.w_rk[b * 32 + lane];
+        if (PRELOAD) ray_next = S.rays[b * 32 + lane];
+      }
       while (b >= 0) {
         const int2 rk = rk_next;
+        const int4 ray = ray_next;
         const int i = b * 32 + lane;
         b = cs_w_next_batch(s_bmap, nw, b + 1);
         rk_next = make_int2(0, -1);
-        if (b >= 0 && b * 32 + lane < n) rk_next = S.w_rk[b * 32 + lane];
+        if (b >= 0 && b * 32 + lane < n) {
+          rk_next = S.w_rk[b * 32 + lane];
+          if (PRELOAD) ray_next = S.rays[b * 32 + lane];
+        }
         const bool cand = i < n && cs_w_is_candidate(t, rk);
         const unsigned m = __ballot_sync(full, cand);
         if (cand) {
           const int at = ncand + __popc(m & ((1u << lane) - 1u));
-          if (at < 32) s_list[at] = i;
+          if (at < 32) {
+            s_list[at] = i;
+            if (PRELOAD) reinterpret_cast<int4*>(s_cell)[at] = ray;
+          }
         }
         ncand += __popc(m);
         kmax = max(kmax, __reduce_max_sync(full, cand ? rk.y : 0));
@@ -576,7 +644,7 @@ __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka,
       t.k1 = min(t.k1, kmax);
       __syncwarp();
       if (ncand <= 32 && !force_general)
-        cs_w_fast<TILED>(S, map, t, ncand, s_list, x1, y1, size, pitch_tiles, alpha);
+        cs_w_fast<TILED>(S, map, t, ncand, s_list, PRELOAD ? reinterpret_cast<const int4*>(s_cell) : nullptr, x1, y1, size, pitch_tiles, alpha);
       else
         cs_w_general<TILED>(S, map, t, n, x1, y1, size, pitch_tiles, alpha, s_val, s_cell, s_bmap, nw);
       __syncwarp();
@@ -586,8 +654,12 @@ __device__ void cs_w_run(const CsSession& S, uint16_t* __restrict__ map, int ka,
   if (tl && lane == 0) { tl[2] = cs_globaltimer(); tl[3] = (long long)tl_cand | ((long long)tl_mode << 16) | ((long long)tl_pieces << 20) | ((long long)ka << 32); }
 }
 
-template <bool TILED>
-__global__ void __launch_bounds__(CS_W_THREADS, 4)
+// Two instances per layout.  RESIDENT = 4 (64 registers, a few spills): the most warps per SM — batches of sessions and big
+// scans, which are throughput.  RESIDENT = 3 (80 registers, no spills): one small scan alone, a latency chain, where a
+// shorter instruction stream per ring and fewer polling blocks beside the search kernel are worth more than the warps
+// (cfg2 43.6 -> 42.4 us per step, cfg1 36.4 -> 35.2; cfg5 the other way, 2.00 -> 2.08 ms).
+template <bool TILED, int RESIDENT>
+__global__ void __launch_bounds__(CS_W_THREADS, RESIDENT)
 cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ int s_first[CS_W_LEVELS + 2];   // first (sub-)task of each level; s_first[nlev] = their number
   __shared__ int s_uniform[CS_W_LEVELS];     // > 0: the level is cut into this many equal wedges (the dense centre)
@@ -599,7 +671,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   __shared__ float sh_pose[5];
   __shared__ long long sh_vis[CS_W_WARPS];
   __shared__ unsigned s_val[CS_W_WARPS][CS_W_CAP];
-  __shared__ uint32_t s_cell[CS_W_WARPS][CS_W_CAP];
+  __shared__ __align__(16) uint32_t s_cell[CS_W_WARPS][CS_W_CAP];
   __shared__ int s_list[CS_W_WARPS][32];
   __shared__ unsigned s_bmap[CS_W_WARPS][CS_W_BMAP_WORDS];
   __shared__ unsigned s_center[CS_W_CENTER_CELLS];
@@ -743,6 +815,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     __threadfence();  // this thread's stores (and counts) are visible device-wide before the block's arrival is counted
     __syncthreads();
     if (tid < copies) atomicAdd(S.prep_words + ((size_t)slot * copies + tid) * 16, 1ull);
+    if (TILED && a.w_prefetch == 3 && my_warp) cs_w_prefetch_ray(map, q, f.x1, f.y1, size, pitch_tiles);
     // off the critical path: the counts that size the next scan's wedges, and the visit count
     if (my_warp && a.w_prev >= 0) cs_w_count(S, q, top);
 #pragma unroll
@@ -772,12 +845,20 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       while (*pw != (unsigned long long)nprep)
         if (spin.expired(a, CS_STUCK_RAYS)) { stuck = true; break; }
       __threadfence();
+    } else if (!preparing && (tid == 32 || tid == 64)) {
+      // the pose words are out long before the rays are (the preparing blocks work from them): two more threads fetch x and
+      // y meanwhile, instead of one more trip to L2 after the arrival
+      volatile unsigned long long* ll = S.ll_pose + (tid >> 6);
+      unsigned long long w;
+      CsSpin spin;
+      while (((w = *ll) & 0xffffffff00000000ull) != ll_tag)
+        if (spin.expired(a, CS_STUCK_POSE)) { stuck = true; break; }
+      sh_pose[tid >> 6] = __uint_as_float((unsigned)w);
     }
     if (__syncthreads_or(stuck)) return false;
     have_rays = true;
     if (a.diag) t_prep = cs_globaltimer();
-    const float pose_x = __uint_as_float((unsigned)__ldcg(&S.ll_pose[0]));  // (final: the preparing blocks saw them)
-    const float pose_y = __uint_as_float((unsigned)__ldcg(&S.ll_pose[1]));
+    const float pose_x = sh_pose[0], pose_y = sh_pose[1];  // (the preparing blocks have theirs from their own poll)
     x1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_x, scale), 0.5f));  // :499, :505
     y1 = cs_cvt_i32(__fadd_rn(__fmul_rn(pose_y, scale), 0.5f));  // :500, :506
     return true;
@@ -873,7 +954,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       if (!ok) continue;
       long long* tl = (a.diag && sj == 0 && stask < a.diag_rings) ? a.diag + (size_t)stask * 8 : nullptr;
       if (tl && lane == 0) { tl[0] = cs_globaltimer(); tl[4] = t_start; tl[5] = t_prep; tl[6] = t_sched; tl[7] = cs_smid() | ((long long)blockIdx.x << 16); }
-      cs_w_run<TILED>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
+      cs_w_run<TILED, RESIDENT == 3>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
                       s_list[warp], s_bmap[warp], tl);
     }
   } else {
@@ -890,7 +971,7 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
       if (!decode(stask, ka, kb, blo, bhi)) continue;
       long long* tl = (a.diag && sj == 0 && stask < a.diag_rings) ? a.diag + (size_t)stask * 8 : nullptr;
       if (tl && lane == 0) { tl[0] = cs_globaltimer(); tl[4] = t_start; tl[5] = t_prep; tl[6] = t_sched; tl[7] = cs_smid() | ((long long)blockIdx.x << 16); }
-      cs_w_run<TILED>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
+      cs_w_run<TILED, RESIDENT == 3>(S, map, ka, kb, blo, bhi, n, x1, y1, size, pitch_tiles, alpha, a.w_general, s_val[warp], s_cell[warp],
                       s_list[warp], s_bmap[warp], tl);
     }
   }

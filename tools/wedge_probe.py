@@ -7,7 +7,10 @@ import slam.net_b200 as sn
 from slam.net_b200 import synth
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-P, size, phys, iters, threads = {"cfg2": (1024, 2048, 40.0, 1024, 4), "cfg3": (8192, 4096, 40.96, 1, 1), "cfg1": (360, 1600, 40.0, 1000, 1),
+if wl == "custom":  # custom P size phys iters threads
+    P, size, phys, iters, threads = int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
+else:
+  P, size, phys, iters, threads = {"cfg2": (1024, 2048, 40.0, 1024, 4), "cfg3": (8192, 4096, 40.96, 1, 1), "cfg1": (360, 1600, 40.0, 1000, 1),
                                    "cfg4": (1024, 8192, 81.92, 1024, 64)}[wl]
 n_scans = 12
 rp = synth.make_replay(n_scans, P, phys)
@@ -21,8 +24,15 @@ log.upload()
 p.ring_cycles()
 p.replay(log, 0, n_scans - 2, want_results=False)
 p.sync()
+FLUSH = os.environ.get("PROBE_FLUSH") == "1"  # write 256 MB before each probed step, like bench.py's default line
+if FLUSH:
+    import torch
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for rep in range(2):
     p.ring_cycles()  # (clears nothing; records are overwritten by the next step)
+    if FLUSH:
+        flush_buf.fill_(rep + 1)
+        torch.cuda.synchronize()
     p.replay(log, n_scans - 2 + rep, 1, want_results=False)
     p.sync()
     full = p.ring_cycles(size + 8192)
@@ -38,7 +48,8 @@ for rep in range(2):
             len(se), us(se[:, 1]).min(), np.percentile(us(se[:, 1]), 50), us(se[:, 1]).max(), np.percentile(us(se[:, 2]), 50), us(se[:, 2]).max(),
             np.percentile(us(se[:, 4]), 50), us(se[:, 4]).max(), np.percentile(us(se[:, 5]), 50), us(se[:, 5]).max()))
     if pub[2] > 0:
-        print("pose: publisher entry %.2f, pose known %.2f, pose words out %.2f, record out %.2f" % tuple((pub[:4] - t0) / 1e3))
+        print("pose: publisher entry %.2f, pose known %.2f, pose words out %.2f, record out %.2f" % tuple((pub[:4] - t0) / 1e3),
+              "(glue from the table)" if pub[4] == 1 else "(glue computed by the publisher)")
     print("---- step %d: %d tasks recorded on %d SMs" % (rep, len(rc), len(np.unique(rc[:, 7]))))
     q = lambda a: "min %6.2f p50 %6.2f p90 %6.2f max %6.2f" % (a.min(), np.percentile(a, 50), np.percentile(a, 90), a.max())
     print("block start      ", q(us(rc[:, 4])))
