@@ -57,6 +57,23 @@ PRIME_SCANS = 5  # PositionSearchBeginning: the first 5 scans only build the map
 SIGMA_XY, SIGMA_THETA = 0.1, 0.17453292  # 0.1 m, 10 degrees (Simulation/MainWindow.xaml.cs:69)
 
 
+ALL_CORES = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None  # before any per-rank pinning
+
+
+class all_cores:
+    """Context: lift this rank's core pinning (parallel.pin_rank_to_cores) while the multi-threaded CPU oracle checks a result."""
+
+    def __enter__(self):
+        self.saved = os.sched_getaffinity(0) if ALL_CORES is not None else None
+        if ALL_CORES is not None:
+            os.sched_setaffinity(0, ALL_CORES)
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+        return False
+
+
 def cpu_min_seconds(default=10.0):
     """Shortest CPU sample of the reference arm / cpu_baseline (CS_BENCH_CPU_MIN_S shortens it for the CPU test-suite)."""
     try:
@@ -488,11 +505,12 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
                 from oracle import oracle as orc
                 T = pow2_threads(n_cand, os.cpu_count() or 1)  # same flat candidate order, fewer and longer threads
                 o = orc.Processor(wl["phys"], wl["size"], rp.odometry[0], SIGMA_XY, SIGMA_THETA, n_cand // T, T)
-                wk = orc.Worker(T)
-                for k in range(n_total):
-                    off = sn.philox_offsets(args.seed, k, n_cand, SIGMA_XY, SIGMA_THETA) if k >= PRIME_SCANS else None
-                    o.update(rp.points[k], rp.odometry[k], off, worker=wk)
-                wk.close()
+                with all_cores():
+                    wk = orc.Worker(T)
+                    for k in range(n_total):
+                        off = sn.philox_offsets(args.seed, k, n_cand, SIGMA_XY, SIGMA_THETA) if k >= PRIME_SCANS else None
+                        o.update(rp.points[k], rp.odometry[k], off, worker=wk)
+                    wk.close()
                 oracle_ok = bool(np.array_equal(o.pose, pose) and int(sn.host_map_checksum(np.array(o.map.pixels), wl["size"])) == checksum)
     # all ranks: same pose, same map
     sig = torch.tensor([float(pose[0]), float(pose[1]), float(pose[2]), float(checksum & 0xFFFFFF), float((checksum >> 24) & 0xFFFFFF),
@@ -536,6 +554,8 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from slam.net_b200 import parallel as _par
+        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
     P = wl["points"]
     if args.workload == "cfg4":
         m = measure_cfg4(args, rank, world, local, K, W)
@@ -608,6 +628,8 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from slam.net_b200 import parallel as _par
+        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
 
     def barrier():
         if world > 1:
@@ -830,6 +852,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from slam.net_b200 import parallel as _par
+        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
 
     def barrier():
         if world > 1:

@@ -1890,7 +1890,9 @@ cs_status cs_get_search_plan(cs_processor* h, int32_t n_points, int32_t n_cand, 
   if (!plan || n_points < 1 || n_cand < 0) return fail(h, CS_ERR_INVALID_ARGUMENT, "cs_get_search_plan: bad argument");
   const int sms = device_sm_count(h->device);
   S2Plan s2;
-  if (cs_plan_search2(1, h->s2_cap, cs_s2_min_cand(h->cfg.flags), (long long)n_cand + 1, n_points, sms, &s2)) {
+  // (as cs_update launches it: a block carries the glue table's service warp beside the slab's threads)
+  const int cap = (tune().spec >= 0 && h->d_spec) ? CS_S2_MAX_THREADS - 32 : CS_S2_MAX_THREADS;
+  if (cs_plan_search2(1, h->s2_cap, cs_s2_min_cand(h->cfg.flags), (long long)n_cand + 1, n_points, sms, &s2, cap)) {
     plan[0] = 1; plan[1] = s2.clusters; plan[2] = s2.slabs; plan[3] = s2.threads; plan[4] = s2.points;
   } else {
     const int warps = cs_search_warps((long long)n_cand + 1, 1, sms);

@@ -64,6 +64,25 @@ def key_from_i64(v: int) -> int:
     return KEY_EMPTY if v == (1 << 63) - 1 else v
 
 
+def pin_rank_to_cores(local_rank: int, local_world: int) -> List[int]:
+    """One process per GPU on one node: give rank `local_rank` its own contiguous share of the cores this process may run on
+    (os.sched_setaffinity), so that the ranks' pose-polling threads and staging copies do not migrate onto each other's
+    cores.  Returns the cores kept (everything, untouched, when there are fewer cores than ranks or no affinity API)."""
+    import os
+    if not hasattr(os, "sched_getaffinity") or local_world <= 1:
+        return sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else []
+    cores = sorted(os.sched_getaffinity(0))
+    per = len(cores) // local_world
+    if per < 1:
+        return cores
+    mine = cores[local_rank * per:(local_rank + 1) * per]
+    try:
+        os.sched_setaffinity(0, mine)
+    except OSError:
+        return cores
+    return mine
+
+
 class _DevicePtr:
     """Zero-copy view of `count` int64 at a raw CUDA address for torch.as_tensor (CUDA array interface)."""
 

@@ -317,3 +317,30 @@ def test_slab_cfg2_back_to_back_equals_scan_by_scan():
     assert ca == cb and np.array_equal(pa, pb)
     assert all(np.array_equal(x.pose, y.pose) and (x.distance, x.index) == (y.distance, y.index) for x, y in zip(ra, rb))
     log.close()
+
+
+def test_glue_table_is_used_and_changes_nothing():
+    """One session alone with the slab search: the publishing thread takes the winner's pose and (cos, sin) from the glue table
+    the service warps filled (diagnostics record: word 4 of the publisher's record = 1) — for uploaded tables and for on-device
+    Philox candidates — and every pose, distance, index and the final map equal the oracle's, as without the table."""
+    n_scans, P, size, phys, iters, threads = 16, 500, 512, 40.0, 300, 4  # 1201 candidates: slab search
+    rp = synth.make_replay(n_scans, P, phys, seed=77)
+    p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=13)
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    assert p.search_plan(P)["slab"]
+    p.ring_cycles()  # enables the diagnostics records
+    from_table = 0
+    for k in range(n_scans):
+        philox = k % 2 == 1
+        off = sn.philox_offsets(13, k, iters * threads, 0.1, 0.17) if philox else synth.candidate_offsets(3, k, iters * threads, 0.1, 0.17)
+        r = p.update(rp.points[k], rp.odometry[k], None if philox else off)
+        o.update(rp.points[k], rp.odometry[k], off)
+        assert np.array_equal(r.pose, o.pose), k
+        if k >= 5:
+            assert (r.distance, r.index) == (o.last_distance, o.last_index), k
+            p.sync()
+            rec = p.ring_cycles(size + 8192)[size + 8191]
+            from_table += int(rec[4] == 1)
+    assert from_table == n_scans - 5, from_table
+    assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+    p.close()

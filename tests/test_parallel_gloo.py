@@ -163,3 +163,24 @@ def _session_rank_single(n_sessions, n_scans):
             o.update(rp.points[k], rp.odometry[k], synth.candidate_offsets(100 + s, k, 32, 0.05 + 0.01 * s, 0.1))
         out.append(o.map.crc32())
     return out
+
+
+def test_pin_rank_to_cores_partitions_the_allowed_cores():
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    """parallel.pin_rank_to_cores: the ranks of a node get disjoint contiguous shares of the cores the process may use (run in
+    child processes: the affinity of the test runner itself must not change)."""
+    import subprocess
+    import sys
+    allowed = sorted(os.sched_getaffinity(0))
+    world = 2 if len(allowed) >= 2 else 1
+    got = []
+    for r in range(world):
+        code = ("import sys, os; sys.path.insert(0, %r); from slam.net_b200 import parallel as p; "
+                "m = p.pin_rank_to_cores(%d, %d); assert sorted(os.sched_getaffinity(0)) == sorted(m); print(','.join(map(str, m)))" % (ROOT, r, world))
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        got.append([int(x) for x in out.stdout.strip().split(",")])
+    flat = [c for g in got for c in g]
+    assert len(set(flat)) == len(flat) and set(flat) <= set(allowed)
+    if world == 2:
+        assert len(got[0]) == len(got[1]) == len(allowed) // 2
