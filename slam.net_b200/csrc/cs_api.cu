@@ -552,7 +552,6 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_batch = c.n_sessions > 1 ? 1 : 0;
     // (Measured and dropped: letting the candidate sort — the first kernel of the step, one block — prefetch the map around
     // the search pose: 65 k prefetches from one SM take 40 us.  CS_TUNE_W_PREFETCH=1 still selects it for experiments.)
-    if (c.n_sessions == 1 && c.tiled && tune().w_prefetch == 1 && draws) a.w_prefetch = 1;
     a.s2_map = c.hs->map;
     a.s2_sorted = c.hs->s2_sorted + (size_t)a.s2_slot * c.hs->s2_cap;
     a.s2_tmp = c.hs->s2_tmp;
@@ -567,14 +566,20 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_sigma_theta = c.hs->sigma_theta;
     // one block sorts a table of up to 8192 candidates out of its registers; generated (Philox) candidates are spread over
     // the SMs, one per thread, as soon as there are more than one block's threads of them (batches: one block per session)
+    // (Measured and dropped: a warm-up kernel in front of the sort, one block per SM loading the map within reach of the step while
+    // the one-block sort runs: one more link in the dependency chain costs more than the cold lookups — cfg2 41.8 -> 42.6 us.)
     const bool one_block = a.cand_count <= CS_SORT_THREADS * CS_SORT_REG &&
                            (a.cand_mode != CS_CAND_PHILOX || a.cand_count <= CS_SORT_THREADS || c.n_sessions > 1 || tune().s2_sort_one_block > 0);
     if (one_block) {
-      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>, dim3(1, (unsigned)c.n_sessions),
-                     dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+      // (one session alone, tiled map: the grid's other blocks pull the map within reach of the step into L2 beside the sort)
+      const bool warm = c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && tune().w_prefetch != 2;
+      if (warm) a.w_prefetch = 1;
+      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>,
+                     dim3(warm ? 1u + (unsigned)c.num_sms : 1u, (unsigned)c.n_sessions), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
       if (e != cudaSuccess) return e;
       (*c.launches)++;
     } else {
+      if (c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && tune().w_prefetch != 2) a.w_prefetch = 1;  // (by the threads of the histogram kernel)
       const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_MB_CHUNK - 1) / CS_SORT_MB_CHUNK);
       e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_hist_kernel<true> : cs_sort_hist_kernel<false>, dim3(sort_blocks),
                      dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);

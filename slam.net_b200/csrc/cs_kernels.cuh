@@ -197,7 +197,8 @@ struct CsStepArgs {  // by-value kernel argument; session j uses element j of ev
   int w_zero;                    // the third the next drawn step will count into (zeroed by this step)
   int w_general;                 // diagnostics: 1 = every task of the wedge integration takes the general path
   int w_sub_max;                 // most warps the rings of one task are split over (0: 8)
-  int w_prefetch;                // the map around the pose is prefetched into L2 — 1: by the candidate sort, 2: by the draw kernel
+  int w_prefetch;                // the map around the pose is pulled into L2 — 1: by the candidate sort, 2: by the draw kernel's
+                                 // blocks while they wait, 3: (batches) along every ray
   int empty_cloud;               // 1: the scan has no points and the step searches: no search kernel ran, the arg-min is
                                  // (int.MaxValue, searchPose) by definition (:251-258, :630-648)
   int s2_batch;                  // 1: a batch of sessions (session = blockIdx.z of the search, blockIdx.y of the sort): the values
@@ -273,7 +274,7 @@ __device__ __forceinline__ void cs_search_pose(const CsSession& S, const CsStepH
 }
 
 // Pulls the part of the map a scan can reach into L2: the tiles within `max_ring_hint` (+ the reach of the search) of the
-// pose the step starts from, one 128-byte tile per iteration, thread t of nt.  Called in the shadow of other work (the
+// pose the step starts from, one 32-byte sector per iteration, thread t of nt.  Called in the shadow of other work (the
 // candidate sort, the wait for the pose); where the map is L2-resident already the prefetches hit.  The state may be one step
 // old when this runs ahead of the previous step's end: good enough for a prefetch.
 __device__ __forceinline__ void cs_prefetch_disc(const CsSession& S, const CsStepHeader& hdr, const CsStepArgs& a, int t, int nt) {
@@ -289,12 +290,15 @@ __device__ __forceinline__ void cs_prefetch_disc(const CsSession& S, const CsSte
   const int ty0 = max(cy - R, 0) >> 3, ty1 = min(cy + R, size - 1) >> 3;
   const int tw = tx1 - tx0 + 1, th = ty1 - ty0 + 1;
   const long long r2 = (long long)(R + 8) * (R + 8);
-  for (int i = t; i < tw * th; i += nt) {
-    const int ty = ty0 + i / tw, tx = tx0 + i % tw;
+  // (Plain loads whose results nobody uses, one per 32-byte sector: `prefetch.global.L2` changed nothing measurable —
+  // cfg2 flushed 42.6 us per step with it, 42.5 without — while loads from the same idle threads take the step to 41.7.)
+  for (int i = t; i < tw * th * 4; i += nt) {
+    const int tile = i >> 2, ty = ty0 + tile / tw, tx = tx0 + tile % tw;
     const long long dx = tx * 8 + 4 - cx, dy = ty * 8 + 4 - cy;
     if (dx * dx + dy * dy <= r2) {
-      const uint16_t* line = S.map + ((size_t)ty * pitch_tiles + tx) * 64;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+      const uint16_t* sector = S.map + ((size_t)ty * pitch_tiles + tx) * 64 + (i & 3) * 16;
+      unsigned unused;
+      asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(unused) : "l"(sector));
     }
   }
 }
@@ -903,7 +907,15 @@ cs_sort_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
   // a batch of sessions: one block per session, everything per session comes from its descriptor
   const int sj = blockIdx.y;
   const CsSession& S = sessions[sj];
-  if (a.w_prefetch == 1) cs_prefetch_disc(S, a.hdr[(size_t)sj * a.hdr_stride], a, tid, CS_SORT_THREADS);
+  if (blockIdx.x > 0) {
+    // One session alone: the sort is this grid's block 0, on one SM, for ~5 us.  The other blocks meanwhile load the sectors of
+    // the map within reach of the step — what the search is about to gather from and the draw kernel to blend into — so that a
+    // step whose map is not in L2 (the first scan after a pause, bench.py's flushed default line, maps beyond the L2) pays the
+    // HBM latency here, beside the sort, and not in the lookups.  Where the map is L2-resident the loads hit.
+    cs_prefetch_disc(S, a.hdr[(size_t)sj * a.hdr_stride], a, (int)(blockIdx.x - 1) * CS_SORT_THREADS + tid, (int)(gridDim.x - 1) * CS_SORT_THREADS);
+    cs_pdl_wait();
+    return;
+  }
   const float* cand = a.cand ? a.cand + (size_t)sj * a.cand_stride : nullptr;
   float4* __restrict__ out = a.s2_batch ? S.s2_sorted + (size_t)a.s2_slot * S.s2_cap : a.s2_sorted;
   float4* __restrict__ tmp = a.s2_batch ? S.s2_tmp : a.s2_tmp;
