@@ -253,7 +253,7 @@ struct CsWWalk {
 // of one pixval commute with themselves, so a cell visited n times with that pixval alone just needs n — counted with
 // shared-memory atomics, one thread per ray — and the exact fixed-point early-out.  A cell that also sees another pixval
 // (an obstacle within a few cells of the sensor) is flagged and redone exactly, in ray order, by one warp.
-#define CS_W_CENTER 8
+#define CS_W_CENTER 16
 #define CS_W_CENTER_CELLS (1 + 4 * CS_W_CENTER * (CS_W_CENTER - 1))  // ring 0: 1 cell, ring k: 8k cells
 __device__ __forceinline__ int cs_w_center_index(int k, int posn) { return k == 0 ? 0 : 1 + 4 * k * (k - 1) + posn; }
 
@@ -728,29 +728,32 @@ cs_wedge_kernel(CsSession* __restrict__ sessions, CsStepArgs a) {
     if (warp == 0) {
       // How many warps share the rings of one task.  The wedges of the dense levels (equal wedges as wide as their margins:
       // several passes of 32 rays per ring, the long tasks of a big scan) are always split ring by ring, up to 8 ways; the
-      // others by the largest power of two that still gives every warp of the grid at most one task (a small scan is a
-      // latency chain: shorter tasks end it sooner; a big one is throughput: whole levels amortise a task's set-up).
-      int dense = 0, other = 0;
-      for (int L0 = 0; L0 < NL; L0 += 32) {
-        const int L = L0 + lane;
-        const int t = L < NL ? s_tot[L] : 0;
-        const bool is_dense = L < NL && s_uniform[L] > 1;
-        dense += is_dense ? t : 0;
-        other += is_dense ? 0 : t;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { dense += __shfl_xor_sync(full, dense, o); other += __shfl_xor_sync(full, other, o); }
+      // others into sub-tasks of r rings, r the shortest of 4, 8, 16, 32, 64 (= whole levels) at which the table still holds at
+      // most one sub-task per warp of the grid — a small scan is a latency chain: shorter tasks end it sooner, and equal lengths
+      // keep the 64-ring outer levels from ending it; a big scan is throughput: whole levels amortise a task's set-up.
       const int slots = (int)gridDim.x * CS_W_WARPS;
-      const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 8;
-      int sub = 1;
-      while (sub < sub_max && dense * 8 + other * (sub * 2) <= slots) sub *= 2;
+      const int sub_max = a.w_sub_max > 0 ? a.w_sub_max : 16;
+      int rlen = 64;
+      for (int r = 64 / sub_max; r < 64; r *= 2) {
+        int cnt = 0;
+        for (int L0 = 0; L0 < NL; L0 += 32) {
+          const int L = L0 + lane;
+          if (L < NL) {
+            const int len = cs_w_level_last(L) - cs_w_level_first(L) + 1;
+            cnt += s_tot[L] * (s_uniform[L] > 1 ? min(8, len) : (len + r - 1) / r);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(full, cnt, o);
+        if (cnt <= slots) { rlen = r; break; }
+      }
       int total = 0, nlev = 0;
       for (int L0 = 0; L0 < NL; L0 += 32) {
         const int L = L0 + lane;
         int split = 1;
         if (L < NL) {
           const int len = cs_w_level_last(L) - cs_w_level_first(L) + 1;
-          split = min(s_uniform[L] > 1 ? 8 : sub, len);
+          split = s_uniform[L] > 1 ? min(8, len) : (len + rlen - 1) / rlen;
           s_split[L] = split;
         }
         const int W = L < NL ? s_tot[L] * split : 0;
