@@ -373,8 +373,9 @@ def measure_cfg5(args, rank, world, local, K, W, n_sessions=None, sub_batches=0,
                     st = L.cs_batch_update(b._h, pts.ctypes.data_as(fp), npts.ctypes.data_as(ip), odo.ctypes.data_as(fp), None, res)
                     if st != 0:
                         raise RuntimeError("cs_batch_update failed: %d" % st)
+            torch.cuda.synchronize()
+            e2e_blocking_wall = time.perf_counter() - t0e  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
             barrier()
-            e2e_blocking_wall = time.perf_counter() - t0e
 
             def submit(i):
                 for b, (per_step, res) in zip(batches, packed):
@@ -400,8 +401,9 @@ def measure_cfg5(args, rank, world, local, K, W, n_sessions=None, sub_batches=0,
                 submit(i)
                 collect()
             collect()
+            torch.cuda.synchronize()
+            e2e_wall = time.perf_counter() - t0e  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
             barrier()
-            e2e_wall = time.perf_counter() - t0e
         elif e2e:
             barrier(); barrier(); barrier(); barrier()
         log.close()
@@ -483,8 +485,8 @@ def measure_cfg4(args, rank, world, local, K, W, oracle_check=True):
             lat[i] = time.perf_counter() - ta
         e1.record(stream)
         proc.sync()
+        wall = time.perf_counter() - t0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        wall = time.perf_counter() - t0
         clocks = sampler.stop()
         dev_ms = e0.elapsed_time(e1)
         launches = proc.launch_count() - launches0
@@ -555,7 +557,8 @@ def run_sharded(args, wl, metric, config, rank, world, local, K, W):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from slam.net_b200 import parallel as _par
-        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
+        if os.environ.get("CS_BENCH_NO_PIN") != "1":
+            _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
     P = wl["points"]
     if args.workload == "cfg4":
         m = measure_cfg4(args, rank, world, local, K, W)
@@ -629,7 +632,8 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from slam.net_b200 import parallel as _par
-        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
+        if os.environ.get("CS_BENCH_NO_PIN") != "1":
+            _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
 
     def barrier():
         if world > 1:
@@ -666,8 +670,9 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
             ev0[i].record(stream)
             proc.replay(log, cur + i, 1, want_results=False)
             ev1[i].record(stream)
+        torch.cuda.synchronize()
+        wall_region = time.perf_counter() - wall0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        wall_region = time.perf_counter() - wall0
         clocks = sampler.stop()
         launches = proc.launch_count() - launches0
         total_ms = float(sum(ev0[i].elapsed_time(ev1[i]) for i in range(K)))
@@ -707,8 +712,8 @@ def run_cfg3(args, wl, config, rank, world, local, K, W):
             if st != 0:
                 N.check(st, proc._h)
         proc.sync()
+        e2e_s = time.perf_counter() - t0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        e2e_s = time.perf_counter() - t0
 
     mean_visits = float(np.mean(visits))
     t_all = torch.tensor([total_ms, e2e_s * 1e3, warm_ms], dtype=torch.float64, device="cuda")
@@ -853,7 +858,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         from slam.net_b200 import parallel as _par
-        _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
+        if os.environ.get("CS_BENCH_NO_PIN") != "1":
+            _par.pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))  # each rank on its own cores (e2e at N > 1)
 
     def barrier():
         if world > 1:
@@ -936,8 +942,9 @@ def main():
             ev0[i].record(stream)
             proc.replay(log, cur + i, 1, want_results=False)
             ev1[i].record(stream)
+        torch.cuda.synchronize()
+        wall_region = time.perf_counter() - wall0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        wall_region = time.perf_counter() - wall0
         clocks = sampler.stop()
         launches = proc.launch_count() - launches0
         step_ms = np.array([ev0[i].elapsed_time(ev1[i]) for i in range(K)])
@@ -989,8 +996,8 @@ def main():
             if st != 0:
                 N.check(st, proc._h)
         proc.sync()
+        e2e_s = time.perf_counter() - t0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        e2e_s = time.perf_counter() - t0
         final_pose = proc.get_pose()
 
         # ---- the same call in production mode: no candidate table, the deviates are generated on the device (Philox);
@@ -1006,14 +1013,21 @@ def main():
             if st != 0:
                 N.check(st, proc._h)
         proc.sync()
+        prod_s = time.perf_counter() - t0  # this rank's own end (max over ranks below): the closing barrier is not part of the steps
         barrier()
-        prod_s = time.perf_counter() - t0
 
     # ---- reduce over ranks: max time, summed work
     t_all = torch.tensor([total_ms, e2e_s * 1e3, warm_ms_per_step], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     total_ms_max, e2e_ms_max, warm_ms_max = (float(x) for x in t_all.tolist())
+    per_rank = None  # every rank's own step time (device-timed, and end to end): where the max over ranks comes from
+    step_trace = [round(float(x) * 1e3, 1) for x in step_ms] if os.environ.get("CS_BENCH_STEP_TRACE") == "1" else None
+    if world > 1:
+        mine_t = torch.tensor([total_ms / K, e2e_s * 1e3 / max(Ke, 1)], dtype=torch.float64, device="cuda")
+        all_t = [torch.empty_like(mine_t) for _ in range(world)]
+        dist.all_gather(all_t, mine_t)
+        per_rank = {"ms_per_step": [float(x[0]) for x in all_t], "e2e_ms_per_step": [float(x[1]) for x in all_t]}
 
     value = world * lookups_per_step * K / (total_ms_max * 1e-3)
     e2e_value = world * lookups_per_step * Ke / (e2e_ms_max * 1e-3)
@@ -1080,7 +1094,7 @@ def main():
                                         "sample": "%d Updates of the same replay, %.1f s, %d search threads as in the reference's simulator" % (done4, dt4, T4)}
 
         line = {"metric": metric, "value": value, "unit": "lookups/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": total_ms_max / K, "per_rank": per_rank, "step_trace_us_rank0": step_trace, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 transform -> u16 gather -> i64 sum", "data": "synthetic",
                 "config": config,
                 "l2": "flushed (256 MB write) before every timed step; e2e inputs arrive from host memory each step",
