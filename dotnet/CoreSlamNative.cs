@@ -15,7 +15,8 @@ namespace CoreSLAM.B200
     public enum CsFlags : uint
     {
         None = 0, RowMajorMap = 0x1, Timing = 0x2, KeepDistances = 0x4, NoHostSpin = 0x8, L2Persist = 0x10, DebugRays = 0x20,
-        SearchWarp = 0x40, SearchSlab = 0x80
+        SearchWarp = 0x40, SearchSlab = 0x80,
+        DebugBoundedSpin = 0x100   // device-side polls give up after 2 s: CS_ERR_CUDA instead of a hang (MPS, time-slicing, debuggers)
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -98,6 +99,16 @@ namespace CoreSLAM.B200
         [DllImport(Lib)] public static extern CsStatus cs_batch_sync(IntPtr batch);
         [DllImport(Lib)] public static extern CsStatus cs_batch_get_poses(IntPtr batch, float* poses3);
         [DllImport(Lib)] public static extern CsStatus cs_batch_map_download(IntPtr batch, int session, ushort* pixels);
+
+        // Candidate split over the GPUs of a node (BASELINE cfg4): one process per GPU exports the 64-byte handle of its exchange
+        // table, the handles travel between the processes by any means (a pipe, a file, MPI), every process attaches all of them;
+        // from then on Update on this handle evaluates this rank's slice of the candidates and the 8-byte arg-min is exchanged
+        // inside the search kernels over NVLink peer memory.  cs_group_attach_local: the handles of one process (one per GPU).
+        [StructLayout(LayoutKind.Sequential)] public unsafe struct CsIpcHandle { public fixed byte Bytes[64]; }
+        [DllImport(Lib)] public static extern CsStatus cs_group_export(IntPtr h, out CsIpcHandle handle);
+        [DllImport(Lib)] public static extern CsStatus cs_group_attach(IntPtr h, int rank, int world, CsIpcHandle* handles);
+        [DllImport(Lib)] public static extern CsStatus cs_group_attach_local(IntPtr h, int rank, int world, IntPtr* peers);
+        [DllImport(Lib)] public static extern CsStatus cs_group_detach(IntPtr h);
 
         public static void Check(CsStatus st, IntPtr h)
         {

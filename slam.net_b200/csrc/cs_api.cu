@@ -619,9 +619,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   if (c.ev_pose) cudaEventRecord(c.ev_pose, c.stream);
   if (draws && tune().integrate != 1 && c.w_slot) {
     // The wedge kernel: (ring range x angular wedge) tasks, one warp each (cs_wedge.cuh).  The first blocks prepare the rays,
-    // 128 each (big scans: bigger groups, so that at most 64 blocks prepare); every warp of the grid then takes tasks
-    // round-robin.  One session alone gets four blocks per SM (all resident: the kernel is a latency chain pose -> rays ->
-    // tasks), a session of a batch a few blocks.
+    // 128 each (big scans: bigger groups, so that at most 64 blocks prepare); every warp of the grid then takes tasks (small
+    // scans: by block tickets; otherwise round-robin).  One session alone gets a resident wave — three blocks per SM of the
+    // 80-register instance for a small scan, four of the 64-register one for a big scan — a session of a batch four blocks.
     int group = (((n_points + 63) / 64) + 31) / 32 * 32;
     if (group < 128) group = 128;
     if (group > CS_W_THREADS) group = CS_W_THREADS;  // one ray per thread of a preparing block

@@ -16,13 +16,16 @@
 // Two paths per task, chosen by the candidate count:
 //   fast     <= 32 candidates: one ray per lane, Bresenham state carried in registers from ring to ring (no per-ring
 //            division), visits of one cell inside the warp found with match.any and applied by the lowest lane in lane
-//            (= ray) order; rings are processed four at a time so four map loads per lane are in flight.
-//   general  any number of candidates (the dense centre, where every ray crosses every wedge; clustered or multi-turn
-//            scans): per ring the wedge's cells are staged in shared memory, the candidate rays are evaluated in closed
-//            form 32 at a time in ray order, same-cell groups fold into the staged value (uniform groups as a count
-//            with the exact fixed-point early-out), then the touched cells go back.
+//            (= ray) order; rings go four at a time in three passes (walk + ownership, the four match.any back to back, the
+//            leaders' four map loads), with an instance for groups of rings on which no lane is inside its hole profile.
+//   general  any number of candidates (dense levels, where the margins alone exceed a warp; clustered or multi-turn
+//            scans): the wedge's cells of up to 8 rings are staged in shared memory, the batches of 32 rays that can hold
+//            candidates are walked in ray order with the next batch's rays in flight, same-cell groups fold into the
+//            staged values (uniform groups as a count with the exact fixed-point early-out), then the touched cells go back.
+// Rings 0 .. CS_W_CENTER - 1, which every ray crosses, are drawn by one block as shared-memory counts (cs_w_center).
 // The first blocks prepare the rays exactly as the rings kernel's do (cs_ray_from_point), plus each ray's key, the key
-// range of every 32 rays, and per level the number of rays that reach it (which sizes the wedges: ~26 candidates each).
+// range of every 32 rays, and per level and key sector the number of rays that reach it (which sizes the wedges: ~26
+// candidates each, cut at the quantiles of the level's rays).  DESIGN.md section 4 has the scheduling and the measurements.
 #pragma once
 #include "cs_kernels.cuh"
 
@@ -469,15 +472,6 @@ __device__ void cs_w_general(const CsSession& S, uint16_t* __restrict__ map, con
   }
 }
 
-// match.any among the lanes of `mask` (exactly the lanes with `on`); 0 for the others.  Predicated instead of branched: the
-// intrinsic inside an `if` compiles to a branch around every match with the result copied right behind it, which serialises
-// the matches of consecutive rings on their ~40-cycle latency.
-__device__ __forceinline__ unsigned cs_match_any_if(bool on, unsigned mask, unsigned key) {
-  unsigned r = 0u;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p match.any.sync.b32 %0, %1, %2;\n\t}" : "+r"(r) : "r"(key), "r"(mask), "r"((unsigned)on));
-  return r;
-}
-
 // ---- fast path: at most 32 candidates (s_list, in ray order), one per lane; rings four at a time so that four map loads per
 // lane are in flight; visits of one cell inside the warp are found with match.any and applied by the lowest lane in lane order.
 // One group of CS_W_G rings.  FREE: no lane is inside its hole profile on these rings (k < a0 for every ray, decided by the
@@ -493,10 +487,10 @@ __device__ __forceinline__ void cs_w_fast_group(uint16_t* __restrict__ map, CsWW
   int pv[CS_W_G], val[CS_W_G];
   unsigned grp[CS_W_G], act[CS_W_G];
   unsigned inwbits = 0u, leadbits = 0u, cfbits = 0u, freebits = 0u;
-  // (In halves of CS_W_H rings, three passes each: the walk and the ownership test, then the match.any of the half back to
-  // back — ~40 cycles each, and the intrinsic inside a branch would be serialised by the copy the compiler puts behind it:
-  // hence all lanes take part, the lanes that do not visit with a key no cell has — then the leaders' map loads.  The second
-  // half's arithmetic runs under the first half's loads.)
+  // (In parts of CS_W_H rings — all CS_W_G of them: halves measured slower — three passes each: the walk and the ownership
+  // test, then the match.any of the part back to back — ~40 cycles each, and the intrinsic inside a branch would be
+  // serialised by the copy the compiler puts behind it: hence all lanes take part, the lanes that do not visit with ONE
+  // shared key no cell has (the cost of a match grows with its distinct keys) — then the leaders' map loads.)
 #pragma unroll
   for (int h = 0; h < CS_W_G; h += CS_W_H) {
 #pragma unroll

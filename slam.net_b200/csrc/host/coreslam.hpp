@@ -146,6 +146,19 @@ class CoreSLAMProcessor {  // CoreSLAM/CoreSLAMProcessor.cs
 
   cs_processor* Handle() const { return h_; }
 
+  // Candidate split over several GPUs (the cross-thread arg-min of ParallelMonteCarloSearch :694-705 at GPU granularity):
+  // after attaching, Update() evaluates this rank's slice of the candidates and the arg-min is exchanged inside the search
+  // kernels over peer memory.  One process driving several GPUs: AttachGroup(rank, {all processors of the group}); one
+  // process per GPU: ExportGroupHandle() everywhere, exchange the 64-byte handles, AttachGroup(rank, handles).
+  cs_ipc_handle ExportGroupHandle() { cs_ipc_handle out; check(cs_group_export(h_, &out)); return out; }
+  void AttachGroup(int rank, const std::vector<cs_ipc_handle>& handles) { check(cs_group_attach(h_, rank, (int)handles.size(), handles.data())); }
+  void AttachGroup(int rank, const std::vector<CoreSLAMProcessor*>& group) {
+    std::vector<cs_processor*> hs;
+    for (CoreSLAMProcessor* p : group) hs.push_back(p ? p->h_ : nullptr);
+    check(cs_group_attach_local(h_, rank, (int)hs.size(), hs.data()));
+  }
+  void DetachGroup() { check(cs_group_detach(h_)); }
+
  private:
   void check(cs_status st) const {
     if (st != CS_OK) throw std::runtime_error(cs_last_error(h_));
