@@ -51,6 +51,16 @@ struct Timing {
 
 }  // namespace
 
+// Production mode (on-device Philox candidates): the candidates of scan k+1 are a function of (seed, k+1) alone, so their sort
+// is queued right behind the draw kernel of scan k and runs in its shadow; the search of scan k+1 then starts without a sort
+// in front.  The descriptor says what was sorted into which half of CsSession::s2_sorted; a step that asks for anything else
+// (another candidate mode, slice or scan number) sorts as usual and overwrites it.
+struct Presort {
+  bool valid = false;
+  unsigned scan_index = 0;
+  int cand_first = 0, cand_count = 0, slot = 0;
+};
+
 struct cs_processor {
   cs_config cfg{};
   int device = 0;
@@ -88,6 +98,7 @@ struct cs_processor {
   unsigned long long* d_s2_acc = nullptr;
   unsigned* d_s2_ghist = nullptr;
   int s2_cap = 0, s2_toggle = 0;
+  Presort presort;
 
   // ObstacleMap (cfg.obstacle_map_size > 0): CoreSLAM/ObstacleMap.cs, CoreSLAMProcessor.cs:53, :132-133
   CsObstacle ho{};               // host mirror of the descriptor
@@ -315,7 +326,7 @@ struct Tune {
   int search_warps = 0, ring_span = 0, ring_threads = 0, ring_slot_bits = 0, ring_blocks_per_sm = 0, ring_small = 0;
   int search2 = 0, s2_points = 0, s2_threads = 0, s2_min_cand = 0, s2_sort_one_block = 0, copy_stream = 0;
   int integrate = 0, w_general = 0, w_blocks = 0, w_prefetch = 0, w_sub = 0, w_prev = 0, w_carveout = 0, s2_carveout = 0;
-  int spin_ms = 0, fault = 0, w_resident = 0, spec = 0;
+  int spin_ms = 0, fault = 0, w_resident = 0, spec = 0, presort = 0;
   Tune() {
     auto geti = [](const char* name) { const char* v = getenv(name); return v ? atoi(v) : 0; };
     search_warps = geti("CS_TUNE_SEARCH_WARPS");
@@ -333,6 +344,7 @@ struct Tune {
     s2_carveout = geti("CS_TUNE_S2_CARVEOUT");  // ... of the slab-search and sort kernels
     w_prev = geti("CS_TUNE_W_PREV");            // -1: every scan builds its task table from its own counts
     w_resident = geti("CS_TUNE_W_RESIDENT");    // 4: one small scan alone also runs the four-blocks-per-SM instance of the wedge kernel
+    presort = geti("CS_TUNE_PRESORT");          // -1: production mode sorts a scan's candidates in front of its search, never ahead
     spec = geti("CS_TUNE_SPEC");                // -1: no glue table (the publishing thread always computes the glue itself)
     w_sub = geti("CS_TUNE_W_SUB");              // most warps a task's rings are split over (1, 2, 4, 8)
     spin_ms = geti("CS_TUNE_SPIN_MS");          // CS_FLAG_DEBUG_BOUNDED_SPIN: milliseconds a device-side poll lasts (default 2000)
@@ -470,6 +482,7 @@ struct LaunchCtx {
   int s2_cap = 0;            // capacity of the slab-search scratch (0: none)
   int s2_min_cand = 0;       // cs_s2_min_cand of the handle
   int* s2_toggle = nullptr;  // which half of CsSession::s2_sorted the next sort writes
+  Presort* presort = nullptr;  // one session alone: the sort queued ahead for the next scan, if any
   const CsSession* hs = nullptr;  // host mirror of the session (host-owned constants for the slab kernels)
   int num_sms;
   cudaStream_t stream;
@@ -522,6 +535,33 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// The candidate sort of a step (a.s2_* set): one block sorts a table of up to 8192 candidates out of its registers; generated
+// (Philox) candidates are spread over the SMs, one per thread, as soon as there are more than one block's threads of them
+// (batches: one block per session).  warm: one session alone with a tiled map — the sort grid's other blocks (or the
+// histogram kernel's threads) pull the map within reach of the step into L2 beside the sort.
+cudaError_t launch_sort(const LaunchCtx& c, CsStepArgs& a, bool warm) {
+  cudaError_t e = cudaSuccess;
+  warm = warm && c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && tune().w_prefetch != 2;
+  const bool one_block = a.cand_count <= CS_SORT_THREADS * CS_SORT_REG &&
+                         (a.cand_mode != CS_CAND_PHILOX || a.cand_count <= CS_SORT_THREADS || c.n_sessions > 1 || tune().s2_sort_one_block > 0);
+  if (warm) a.w_prefetch = 1;
+  if (one_block) {
+    e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>,
+                   dim3(warm ? 1u + (unsigned)c.num_sms : 1u, (unsigned)c.n_sessions), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+    if (e != cudaSuccess) return e;
+    (*c.launches)++;
+  } else {
+    const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_MB_CHUNK - 1) / CS_SORT_MB_CHUNK);
+    e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_hist_kernel<true> : cs_sort_hist_kernel<false>, dim3(sort_blocks),
+                   dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+    if (e != cudaSuccess) return e;
+    e = launch_pdl(cs_sort_scatter_kernel, dim3(sort_blocks), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+    if (e != cudaSuccess) return e;
+    (*c.launches) += 2;
+  }
+  return e;
+}
+
 cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int rings, int phases) {
   // An empty cloud (Update with segments that carry no rays): CalculateDistance returns int.MaxValue for every pose (:251-258),
   // so searchPose wins (:630-648, strict <) without a single lookup: no search kernel, the glue decodes (MaxValue, index 0).
@@ -543,9 +583,11 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   }
   cudaError_t e = cudaSuccess;
   S2Plan s2;
+  bool used_s2 = false;
   if ((phases & CS_PHASE_SEARCH) && searching &&
       cs_plan_search2(c.n_sessions, c.s2_cap, c.s2_min_cand, a.cand_count, a.s2_host_points, c.num_sms, &s2,
                       a.spec ? CS_S2_MAX_THREADS - 32 : CS_S2_MAX_THREADS)) {  // (the glue table's service warp rides along)
+    used_s2 = true;
     a.s2_points = s2.points;
     a.s2_slab = s2.threads;
     a.s2_slot = (*c.s2_toggle ^= 1);
@@ -564,29 +606,14 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_scale = c.hs->scale;
     a.s2_sigma_xy = c.hs->sigma_xy;
     a.s2_sigma_theta = c.hs->sigma_theta;
-    // one block sorts a table of up to 8192 candidates out of its registers; generated (Philox) candidates are spread over
-    // the SMs, one per thread, as soon as there are more than one block's threads of them (batches: one block per session)
     // (Measured and dropped: a warm-up kernel in front of the sort, one block per SM loading the map within reach of the step while
     // the one-block sort runs: one more link in the dependency chain costs more than the cold lookups — cfg2 41.8 -> 42.6 us.)
-    const bool one_block = a.cand_count <= CS_SORT_THREADS * CS_SORT_REG &&
-                           (a.cand_mode != CS_CAND_PHILOX || a.cand_count <= CS_SORT_THREADS || c.n_sessions > 1 || tune().s2_sort_one_block > 0);
-    if (one_block) {
-      // (one session alone, tiled map: the grid's other blocks pull the map within reach of the step into L2 beside the sort)
-      const bool warm = c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && tune().w_prefetch != 2;
-      if (warm) a.w_prefetch = 1;
-      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_kernel<true> : cs_sort_kernel<false>,
-                     dim3(warm ? 1u + (unsigned)c.num_sms : 1u, (unsigned)c.n_sessions), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
+    const bool presorted = c.presort && c.presort->valid && a.cand_mode == CS_CAND_PHILOX && c.presort->scan_index == a.scan_index &&
+                           c.presort->cand_first == a.cand_first && c.presort->cand_count == a.cand_count && c.presort->slot == a.s2_slot;
+    if (c.presort) c.presort->valid = false;
+    if (!presorted) {
+      e = launch_sort(c, a, /*warm=*/true);
       if (e != cudaSuccess) return e;
-      (*c.launches)++;
-    } else {
-      if (c.n_sessions == 1 && c.tiled && tune().w_prefetch >= 0 && tune().w_prefetch != 2) a.w_prefetch = 1;  // (by the threads of the histogram kernel)
-      const unsigned sort_blocks = (unsigned)((a.cand_count + CS_SORT_MB_CHUNK - 1) / CS_SORT_MB_CHUNK);
-      e = launch_pdl(a.cand_mode == CS_CAND_PHILOX ? cs_sort_hist_kernel<true> : cs_sort_hist_kernel<false>, dim3(sort_blocks),
-                     dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
-      if (e != cudaSuccess) return e;
-      e = launch_pdl(cs_sort_scatter_kernel, dim3(sort_blocks), dim3(CS_SORT_THREADS), 0, c.stream, c.d_sess, a);
-      if (e != cudaSuccess) return e;
-      (*c.launches) += 2;
     }
     dispatch_layout(c.tiled, [&](auto T) {
       e = launch_pdl(cs_search2_kernel<decltype(T)::value>, dim3((unsigned)s2.clusters, (unsigned)s2.slabs, (unsigned)c.n_sessions),
@@ -705,6 +732,22 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     if (e != cudaSuccess) return e;
     (*c.launches)++;
   }
+  // ---- production mode: the next scan's candidate sort, queued in the shadow of this scan's draw kernel (see Presort).  Not
+  // under CS_FLAG_TIMING (the events around the stages would count it to the wrong one).
+  if (c.presort && tune().presort >= 0 && used_s2 && fused && draws && a.cand_mode == CS_CAND_PHILOX && c.n_sessions == 1 && !c.ev_done) {
+    CsStepArgs b = a;
+    b.scan_index = a.scan_index + 1;
+    b.s2_slot = a.s2_slot ^ 1;
+    b.s2_sorted = c.hs->s2_sorted + (size_t)b.s2_slot * c.hs->s2_cap;
+    b.w_prefetch = 0;  // (the next scan's header is not known yet: its draw kernel's blocks warm the map themselves)
+    e = launch_sort(c, b, /*warm=*/false);
+    if (e != cudaSuccess) return e;
+    c.presort->valid = true;
+    c.presort->scan_index = b.scan_index;
+    c.presort->cand_first = a.cand_first;
+    c.presort->cand_count = a.cand_count;
+    c.presort->slot = b.s2_slot;
+  }
   if (c.ev_done) cudaEventRecord(c.ev_done, c.stream);
   return cudaGetLastError();
 }
@@ -742,6 +785,7 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.s2_cap = h->s2_cap;
   c.s2_min_cand = cs_s2_min_cand(h->cfg.flags);
   c.s2_toggle = &h->s2_toggle;
+  c.presort = &h->presort;
   c.hs = &h->hs;
   c.spec = h->d_spec;
   if (h->cfg.flags & CS_FLAG_DEBUG_BOUNDED_SPIN) c.stuck_dev = reinterpret_cast<volatile unsigned*>(h->d_slot + 96);
