@@ -53,12 +53,17 @@ struct Timing {
 
 // Production mode (on-device Philox candidates): the candidates of scan k+1 are a function of (seed, k+1) alone, so their sort
 // is queued right behind the draw kernel of scan k and runs in its shadow; the search of scan k+1 then starts without a sort
-// in front.  The descriptor says what was sorted into which half of CsSession::s2_sorted; a step that asks for anything else
-// (another candidate mode, slice or scan number) sorts as usual and overwrites it.
+// in front.  The same holds for the replay of a device-resident scan log with candidate tables (cs_replay): the next scan's
+// table is already in HBM.  (Not for cs_update with a host table: it arrives with the scan.)  The descriptor says what was
+// sorted into which half of CsSession::s2_sorted; a step that asks for anything else (another candidate mode, table, slice or
+// scan number, another upload of the log) sorts as usual and overwrites it.
 struct Presort {
   bool valid = false;
   unsigned scan_index = 0;
   int cand_first = 0, cand_count = 0, slot = 0;
+  int cand_mode = 0;
+  const float* cand = nullptr;  // replay of a device-resident log with candidate tables: the table that was sorted ...
+  uint64_t tag = 0;             // ... and the upload of the log it belongs to
 };
 
 struct cs_processor {
@@ -168,6 +173,7 @@ struct cs_scanlog {
   float* d_offsets = nullptr;
   CsDevResult* d_results = nullptr;
   bool uploaded = false;
+  uint64_t generation = 0;  // counts the uploads: what a handle sorted ahead from this log is only good for the same upload
 };
 
 namespace {
@@ -483,6 +489,8 @@ struct LaunchCtx {
   int s2_min_cand = 0;       // cs_s2_min_cand of the handle
   int* s2_toggle = nullptr;  // which half of CsSession::s2_sorted the next sort writes
   Presort* presort = nullptr;  // one session alone: the sort queued ahead for the next scan, if any
+  const float* next_cand = nullptr;  // cs_replay with tables: the next scan's table (nullptr: none) and the log's upload number
+  uint64_t log_tag = 0;
   const CsSession* hs = nullptr;  // host mirror of the session (host-owned constants for the slab kernels)
   int num_sms;
   cudaStream_t stream;
@@ -608,8 +616,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     a.s2_sigma_theta = c.hs->sigma_theta;
     // (Measured and dropped: a warm-up kernel in front of the sort, one block per SM loading the map within reach of the step while
     // the one-block sort runs: one more link in the dependency chain costs more than the cold lookups — cfg2 41.8 -> 42.6 us.)
-    const bool presorted = c.presort && c.presort->valid && a.cand_mode == CS_CAND_PHILOX && c.presort->scan_index == a.scan_index &&
-                           c.presort->cand_first == a.cand_first && c.presort->cand_count == a.cand_count && c.presort->slot == a.s2_slot;
+    const bool presorted = c.presort && c.presort->valid && !c.ev_done /* (CS_FLAG_TIMING measures the whole stage) */ && c.presort->cand_mode == a.cand_mode && c.presort->scan_index == a.scan_index &&
+                           c.presort->cand_first == a.cand_first && c.presort->cand_count == a.cand_count && c.presort->slot == a.s2_slot &&
+                           (a.cand_mode == CS_CAND_PHILOX || (a.cand_mode == CS_CAND_OFFSETS && c.presort->cand == a.cand && c.presort->tag == c.log_tag && c.log_tag != 0));
     if (c.presort) c.presort->valid = false;
     if (!presorted) {
       e = launch_sort(c, a, /*warm=*/true);
@@ -734,8 +743,11 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
   }
   // ---- production mode: the next scan's candidate sort, queued in the shadow of this scan's draw kernel (see Presort).  Not
   // under CS_FLAG_TIMING (the events around the stages would count it to the wrong one).
-  if (c.presort && tune().presort >= 0 && used_s2 && fused && draws && a.cand_mode == CS_CAND_PHILOX && c.n_sessions == 1 && !c.ev_done) {
+  const bool ahead_table = a.cand_mode == CS_CAND_OFFSETS && c.next_cand != nullptr && c.log_tag != 0 && !a.cand_cs;
+  if (c.presort && tune().presort >= 0 && used_s2 && fused && draws && (a.cand_mode == CS_CAND_PHILOX || ahead_table) && c.n_sessions == 1 &&
+      !c.ev_done) {
     CsStepArgs b = a;
+    if (ahead_table) b.cand = c.next_cand;
     b.scan_index = a.scan_index + 1;
     b.s2_slot = a.s2_slot ^ 1;
     b.s2_sorted = c.hs->s2_sorted + (size_t)b.s2_slot * c.hs->s2_cap;
@@ -747,6 +759,9 @@ cudaError_t launch_step_ctx(const LaunchCtx& c, CsStepArgs a, int n_points, int 
     c.presort->cand_first = a.cand_first;
     c.presort->cand_count = a.cand_count;
     c.presort->slot = b.s2_slot;
+    c.presort->cand_mode = a.cand_mode;
+    c.presort->cand = ahead_table ? c.next_cand : nullptr;
+    c.presort->tag = ahead_table ? c.log_tag : 0;
   }
   if (c.ev_done) cudaEventRecord(c.ev_done, c.stream);
   return cudaGetLastError();
@@ -770,7 +785,8 @@ cudaError_t launch_obstacle_update(cudaStream_t stream, const CsSession* d_sess,
   return cudaGetLastError();
 }
 
-cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base, int phases = CS_PHASE_ALL) {
+cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bool timing, int ev_base, int phases = CS_PHASE_ALL,
+                      const float* next_cand = nullptr, uint64_t log_tag = 0) {
   LaunchCtx c{};
   c.num_sms = device_sm_count(h->device);
   c.stream = h->stream;
@@ -786,6 +802,8 @@ cs_status launch_step(cs_processor* h, CsStepArgs a, int n_points, int rings, bo
   c.s2_min_cand = cs_s2_min_cand(h->cfg.flags);
   c.s2_toggle = &h->s2_toggle;
   c.presort = &h->presort;
+  c.next_cand = next_cand;
+  c.log_tag = log_tag;
   c.hs = &h->hs;
   c.spec = h->d_spec;
   if (h->cfg.flags & CS_FLAG_DEBUG_BOUNDED_SPIN) c.stuck_dev = reinterpret_cast<volatile unsigned*>(h->d_slot + 96);
@@ -2033,6 +2051,8 @@ cs_status cs_scanlog_upload(cs_scanlog* log) {
     ok = cudaMemcpy(log->d_offsets, log->h_offsets.data(), log->h_offsets.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
   if (!ok) return fail(nullptr, CS_ERR_CUDA, "cs_scanlog_upload: %s", cudaGetErrorString(cudaGetLastError()));
   log->uploaded = true;
+  static std::atomic<uint64_t> g_log_generation{1};
+  log->generation = g_log_generation.fetch_add(1);
   return CS_OK;
 }
 
@@ -2211,7 +2231,10 @@ cs_status cs_replay(cs_processor* h, const cs_scanlog* log, int32_t first, int32
     a.cand_count = h->n_cand + 1;
     a.s2_host_points = log->h_hdr[sidx].n_points;
     apply_group(h, a);
-    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, rings_hint(h, log->h_max_range[sidx]), per_kernel, 2);
+    // (the next scan's table, if the log has one: its sort is queued behind this scan's draw kernel, see Presort)
+    const float* next_cand = (log->n_offsets > 0 && sidx + 1 < log->n_scans) ? log->d_offsets + (size_t)(sidx + 1) * log->n_offsets * 3 : nullptr;
+    cs_status st = launch_step(h, a, log->h_hdr[sidx].n_points, rings_hint(h, log->h_max_range[sidx]), per_kernel, 2, CS_PHASE_ALL,
+                               next_cand, log->generation);
     if (st != CS_OK) return st;
     h->parity ^= 1;
     h->update_count++;
