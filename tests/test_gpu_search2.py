@@ -344,3 +344,46 @@ def test_glue_table_is_used_and_changes_nothing():
     assert from_table == n_scans - 5, from_table
     assert np.array_equal(p.map_download(), np.array(o.map.pixels))
     p.close()
+
+
+def test_sort_queued_ahead_is_dropped_when_the_next_step_differs():
+    """Slab search, one session: behind every searched scan the next scan's candidate sort is queued (production mode, and
+    replays of a device-resident log with tables).  What was sorted ahead must only be used by the step it was sorted for:
+    here the log is re-uploaded with another table for the next scan, the replay jumps to a non-consecutive scan, and a
+    production-mode scan is followed by a table scan and back — every pose, distance and index must equal the oracle's."""
+    n_scans, P, size, phys, iters, threads = 14, 400, 512, 40.0, 300, 4  # 1201 candidates: slab search
+    n_cand = iters * threads
+    rp = synth.make_replay(n_scans, P, phys, seed=91)
+    offs = [synth.candidate_offsets(17, k, n_cand, 0.1, 0.17) for k in range(n_scans)]
+    p = sn.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads, max_points=P, seed=21)
+    o = orc.Processor(phys, size, rp.odometry[0], 0.1, 0.17, iters, threads)
+    assert p.search_plan(P)["slab"]
+    log = sn.ScanLog(n_scans, P, n_offsets=n_cand)
+    for k in range(n_scans):
+        log.set(k, rp.points[k], rp.odometry[k], offs[k])
+    log.upload()
+
+    def check(r, k, off):
+        o.update(rp.points[k], rp.odometry[k], off)
+        assert np.array_equal(r.pose, o.pose), k
+        if o.last_index >= 0:
+            assert (r.distance, r.index) == (o.last_distance, o.last_index), k
+
+    for k in range(7):                       # scans 0..6 one by one: scan k+1's sort is queued behind scan k
+        check(p.replay(log, k, 1)[0], k, offs[k])
+    new7 = synth.candidate_offsets(99, 7, n_cand, 0.1, 0.17)
+    log.set(7, rp.points[7], rp.odometry[7], new7)   # another table for the scan whose sort is already queued
+    log.upload()
+    check(p.replay(log, 7, 1)[0], 7, new7)
+    check(p.replay(log, 9, 1)[0], 9, offs[9])        # a jump: scan 8's sort was queued, scan 9 is asked for
+    ph = sn.philox_offsets(21, 9, n_cand, 0.1, 0.17)  # (the Philox counter is the number of Updates so far: 0..7 and 9 = nine)
+    r = p.update(rp.points[10], rp.odometry[10], None)  # production mode: sorted ahead of nothing, queues its own successor
+    check(r, 10, ph)
+    r = p.update(rp.points[11], rp.odometry[11], offs[11])  # a host table behind a production-mode scan
+    check(r, 11, offs[11])
+    ph = sn.philox_offsets(21, 11, n_cand, 0.1, 0.17)
+    r = p.update(rp.points[12], rp.odometry[12], None)
+    check(r, 12, ph)
+    assert np.array_equal(p.map_download(), np.array(o.map.pixels))
+    log.close()
+    p.close()
