@@ -1116,6 +1116,11 @@ def main():
                                                                     "p99": float(np.percentile(latp, 99) * 1e3)}},
                 "replay_l2_warm": {"ms_per_step": warm_ms_max, "value": world * lookups_per_step / (warm_ms_max * 1e-3),
                                    "note": "same replay without L2 flushes, %d scans back to back" % W},
+                "sort_ahead": ("off (CS_TUNE_PRESORT=-1): every step sorts its candidate table in front of its search" if os.environ.get("CS_TUNE_PRESORT") == "-1" else
+                               "`value` replays a device-resident log, so the library queues the candidate sort of scan k+1 behind the draw "
+                               "kernel of scan k: every timed step still holds exactly one sort (the next scan's, under its own draw kernel), "
+                               "none in front of its search; `e2e` uploads a table with every scan and sorts in front of the search; "
+                               "`e2e_production_mode` generates candidates on the device and sorts ahead like `value`"),
                 "roofline": roofline,
                 "cpu_baseline": cpu,
                 "wall_s_timed_region": wall_region,
