@@ -173,6 +173,37 @@ namespace CoreSLAM.B200
             // UpdateObstacleMap (:751) ran on the device too when the handle was created with obstacle_map_size > 0
         }
 
+        // ---- candidate split over the GPUs of a node (no counterpart in the reference: its split is over CPU threads,
+        // ParallelMonteCarloSearch :674-710).  One CoreSLAMProcessor per GPU, all fed the same scans in the same order; after
+        // AttachGroup every Update evaluates this rank's slice of the candidates and ends on the group's winner.
+        /// <summary>64-byte handle of this processor's exchange table, to be passed to the other processes of the group.</summary>
+        public byte[] ExportGroupHandle()
+        {
+            Native.Check(Native.cs_group_export(handle, out Native.CsIpcHandle h), handle);
+            var bytes = new byte[64];
+            for (int i = 0; i < 64; i++) bytes[i] = h.Bytes[i];
+            return bytes;
+        }
+
+        /// <summary>One process per GPU: attach the handles of all ranks (this rank's own entry is ignored).</summary>
+        public void AttachGroup(int rank, byte[][] handlesOfAllRanks)
+        {
+            var hs = new Native.CsIpcHandle[handlesOfAllRanks.Length];
+            for (int r = 0; r < hs.Length; r++)
+                for (int i = 0; i < 64; i++) hs[r].Bytes[i] = handlesOfAllRanks[r][i];
+            fixed (Native.CsIpcHandle* p = hs) Native.Check(Native.cs_group_attach(handle, rank, hs.Length, p), handle);
+        }
+
+        /// <summary>One process driving several GPUs: the processors of the group, this one at index rank.</summary>
+        public void AttachGroup(int rank, CoreSLAMProcessor[] group)
+        {
+            var hs = new IntPtr[group.Length];
+            for (int r = 0; r < hs.Length; r++) hs[r] = group[r].handle;
+            fixed (IntPtr* p = hs) Native.Check(Native.cs_group_attach_local(handle, rank, hs.Length, p), handle);
+        }
+
+        public void DetachGroup() => Native.Check(Native.cs_group_detach(handle), handle);
+
         public void Dispose()
         {
             if (handle == IntPtr.Zero) return;

@@ -57,3 +57,21 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 for b in banned:
                     assert b not in src, (f, b)
+
+
+def test_flag_values_agree_between_header_python_and_csharp():
+    """CS_FLAG_* of include/coreslam_b200.h = FLAG_* of the ctypes loader = CsFlags of the C# stubs (value by value)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "coreslam_b200.h")).read()
+    c_flags = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define CS_FLAG_(\w+)\s+0x([0-9a-fA-F]+)u", hdr)}
+    assert len(c_flags) >= 9
+    from slam.net_b200 import _native as N
+    for name, value in c_flags.items():
+        assert getattr(N, "FLAG_" + name) == value, name
+    cs = open(os.path.join(root, "dotnet", "CoreSlamNative.cs")).read()
+    enum = cs[cs.index("public enum CsFlags"):]
+    enum = enum[:enum.index("}")]
+    cs_flags = {m.group(1).lower(): int(m.group(2), 16) for m in re.finditer(r"(\w+)\s*=\s*0x([0-9a-fA-F]+)", enum)}
+    for name, value in c_flags.items():
+        assert cs_flags.get(name.replace("_", "").lower()) == value, name
